@@ -1,0 +1,105 @@
+// Shared device/host helpers for the amid_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+
+#include "../../include/amid_b200.h"
+
+namespace amid {
+
+constexpr int D = AMID_D;       // embedding width
+constexpr int H = AMID_HEADS;   // attention heads
+constexpr int DH = D / H;       // 16
+constexpr float LN_EPS = 1e-8f; // model_seq.py:342,345,352
+
+// ------------------------------------------------------------------ error plumbing
+int set_error(int code, const char* fmt, ...);
+#define AMID_REQUIRE(cond, ...)                                   \
+    do {                                                          \
+        if (!(cond)) return ::amid::set_error(-1, __VA_ARGS__);   \
+    } while (0)
+#define AMID_LAUNCH_CHECK(name)                                                         \
+    do {                                                                                \
+        cudaError_t e__ = cudaGetLastError();                                           \
+        if (e__ != cudaSuccess)                                                         \
+            return ::amid::set_error(-2, "%s: launch failed: %s", name, cudaGetErrorString(e__)); \
+    } while (0)
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+inline int64_t round_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
+
+// ------------------------------------------------------------------ warp helpers
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// ------------------------------------------------------------------ counter-based dropout RNG
+// One 64-bit hash yields four 16-bit lanes = the keep decisions of 4 consecutive elements
+// (idx4 = element_index >> 2).  keep <=> lane >= thr16, thr16 = round(p * 65536).
+__device__ __forceinline__ uint64_t rng4(uint64_t seed, uint32_t site, uint64_t idx4) {
+    uint64_t z = seed + 0x9E3779B97F4A7C15ull * (idx4 + 1) + 0xD1B54A32D192ED03ull * (uint64_t)(site + 1);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+__device__ __forceinline__ bool rng_keep(uint64_t r, int lane4, uint32_t thr16) {
+    return ((uint32_t)(r >> (16 * lane4)) & 0xFFFFu) >= thr16;
+}
+
+struct DropCfg {
+    int train;
+    uint32_t thr16;
+    float scale;
+    uint64_t seed;
+    uint32_t site_base;
+};
+inline DropCfg make_drop(const amid_dropout* d) {
+    DropCfg c{0, 0u, 1.0f, 0ull, 0u};
+    if (d && d->train && d->p > 0.f) {
+        c.train = 1;
+        double t = (double)d->p * 65536.0 + 0.5;
+        c.thr16 = (uint32_t)(t > 65535.0 ? 65535.0 : t);
+        c.scale = 1.0f / (1.0f - d->p);
+        c.seed = d->seed;
+    }
+    if (d) c.site_base = d->site_base;
+    return c;
+}
+
+// apply dropout to 4 consecutive elements starting at element index e0 (multiple of 4)
+__device__ __forceinline__ float4 drop4(float4 v, const DropCfg& c, uint32_t site, uint64_t e0) {
+    uint64_t r = rng4(c.seed, site, e0 >> 2);
+    v.x = rng_keep(r, 0, c.thr16) ? v.x * c.scale : 0.f;
+    v.y = rng_keep(r, 1, c.thr16) ? v.y * c.scale : 0.f;
+    v.z = rng_keep(r, 2, c.thr16) ? v.z * c.scale : 0.f;
+    v.w = rng_keep(r, 3, c.thr16) ? v.w * c.scale : 0.f;
+    return v;
+}
+
+// sites inside one encoder (relative to site_base)
+enum : uint32_t { SITE_EMB = 0, SITE_ATTN0 = 1, SITE_FFN1_0 = 2, SITE_FFN2_0 = 3 };
+__host__ __device__ inline uint32_t site_attn(int blk) { return 1u + 3u * blk; }
+__host__ __device__ inline uint32_t site_ffn1(int blk) { return 2u + 3u * blk; }
+__host__ __device__ inline uint32_t site_ffn2(int blk) { return 3u + 3u * blk; }
+
+// ------------------------------------------------------------------ cp.async
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
+}
+
+}  // namespace amid

@@ -1,0 +1,406 @@
+// Multi-interest information module: InterComp / InnerComp (model_seq.py:474-497 /
+// 450-472) in the exact closed form of SURVEY.md section 8a-6.  The reference builds
+// [bs,B,n,n] tensors whose outer axis is redundant; here the only O(n^2 d) work is one
+// similarity-max per sample (k_mim_scores), everything else is O(B n d) or smaller.
+#include "common.cuh"
+
+namespace amid {
+
+constexpr int MT = 64;        // tile edge of the similarity GEMM
+constexpr int MLD = D + 4;    // smem row stride
+constexpr size_t MIM_SMEM = (size_t)2 * MT * MLD * sizeof(float);
+
+// m[j] = max_{s,t} <a[j,s], b[j,t]>.  One CTA per sample, 256 threads, 4x4 micro-tiles.
+__global__ void __launch_bounds__(256)
+k_mim_scores(const float* __restrict__ a, const float* __restrict__ b, int n, float* __restrict__ m) {
+    extern __shared__ __align__(16) float smem[];
+    __shared__ float wmax[8];
+    float* As = smem;
+    float* Bs = smem + MT * MLD;
+    const int j = blockIdx.x;
+    const float* aj = a + (size_t)j * n * D;
+    const float* bj = b + (size_t)j * n * D;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int tx = lane & 15, ty = warp * 2 + (lane >> 4);   // rows ty+16*i of A, rows tx+16*jj of B
+    float best = -INFINITY;
+    for (int s0 = 0; s0 < n; s0 += MT) {
+        __syncthreads();
+        for (int idx = threadIdx.x; idx < MT * (D / 4); idx += 256) {
+            int r = idx >> 5, c4 = idx & 31;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (s0 + r < n) v = __ldg(reinterpret_cast<const float4*>(aj + (size_t)(s0 + r) * D) + c4);
+            *reinterpret_cast<float4*>(As + r * MLD + c4 * 4) = v;
+        }
+        for (int t0 = 0; t0 < n; t0 += MT) {
+            __syncthreads();
+            for (int idx = threadIdx.x; idx < MT * (D / 4); idx += 256) {
+                int r = idx >> 5, c4 = idx & 31;
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (t0 + r < n) v = __ldg(reinterpret_cast<const float4*>(bj + (size_t)(t0 + r) * D) + c4);
+                *reinterpret_cast<float4*>(Bs + r * MLD + c4 * 4) = v;
+            }
+            __syncthreads();
+            float acc[4][4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) acc[i][jj] = 0.f;
+#pragma unroll 4
+            for (int k = 0; k < D; k += 4) {
+                float4 av[4], bv[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) av[i] = *reinterpret_cast<const float4*>(As + (ty + 16 * i) * MLD + k);
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) bv[jj] = *reinterpret_cast<const float4*>(Bs + (tx + 16 * jj) * MLD + k);
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int jj = 0; jj < 4; ++jj) {
+                        acc[i][jj] = fmaf(av[i].x, bv[jj].x, acc[i][jj]);
+                        acc[i][jj] = fmaf(av[i].y, bv[jj].y, acc[i][jj]);
+                        acc[i][jj] = fmaf(av[i].z, bv[jj].z, acc[i][jj]);
+                        acc[i][jj] = fmaf(av[i].w, bv[jj].w, acc[i][jj]);
+                    }
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj)
+                    if (s0 + ty + 16 * i < n && t0 + tx + 16 * jj < n) best = fmaxf(best, acc[i][jj]);
+        }
+    }
+    best = warp_max(best);
+    if (lane == 0) wmax[warp] = best;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float r = wmax[0];
+        for (int w = 1; w < 8; ++w) r = fmaxf(r, wmax[w]);
+        m[j] = r;
+    }
+}
+
+// softmax over the batch + hard gate + ordered compaction.  Single CTA, 1024 threads.
+__global__ void __launch_bounds__(1024)
+k_mim_gate(const float* __restrict__ m, const float* __restrict__ w_bs, int B, float ts, float* __restrict__ p,
+           float* __restrict__ gate, float* __restrict__ coef, int* __restrict__ active, int* __restrict__ n_active,
+           float* __restrict__ scal) {
+    __shared__ float red[32];
+    __shared__ int cnt[1024];
+    __shared__ float bcast;
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    // max
+    float mx = -INFINITY;
+    for (int j = t; j < B; j += 1024) mx = fmaxf(mx, m[j]);
+    mx = warp_max(mx);
+    if (lane == 0) red[warp] = mx;
+    __syncthreads();
+    if (t == 0) { float r = red[0]; for (int w = 1; w < 32; ++w) r = fmaxf(r, red[w]); bcast = r; }
+    __syncthreads();
+    mx = bcast;
+    __syncthreads();
+    // sum of exp, fixed order: per-thread strided partial, warp tree, then warp 0 sequential
+    float se = 0.f, sw = 0.f;
+    for (int j = t; j < B; j += 1024) { se += expf(m[j] - mx); sw += w_bs[j]; }
+    se = warp_sum(se);
+    if (lane == 0) red[warp] = se;
+    __syncthreads();
+    if (t == 0) { float r = 0.f; for (int w = 0; w < 32; ++w) r += red[w]; bcast = r; }
+    __syncthreads();
+    const float denom = bcast;
+    __syncthreads();
+    sw = warp_sum(sw);
+    if (lane == 0) red[warp] = sw;
+    __syncthreads();
+    if (t == 0) { float r = 0.f; for (int w = 0; w < 32; ++w) r += red[w]; scal[0] = r; }
+    // gates; contiguous ranges per thread so the compaction keeps ascending order
+    const int per = (B + 1023) / 1024;
+    const int j0 = t * per, j1 = min(B, j0 + per);
+    int c = 0;
+    for (int j = j0; j < j1; ++j) {
+        const float pj = expf(m[j] - mx) / denom;
+        const bool g = pj > ts;               // getBinaryTensor, model_seq.py:445-448
+        p[j] = pj;
+        gate[j] = g ? 1.f : 0.f;
+        coef[j] = g ? w_bs[j] : 0.f;
+        c += g;
+    }
+    cnt[t] = c;
+    __syncthreads();
+    // exclusive scan of cnt (Hillis-Steele, 1024 entries)
+    for (int off = 1; off < 1024; off <<= 1) {
+        int v = t >= off ? cnt[t - off] : 0;
+        __syncthreads();
+        cnt[t] += v;
+        __syncthreads();
+    }
+    int pos = cnt[t] - c;
+    for (int j = j0; j < j1; ++j)
+        if (gate[j] != 0.f) active[pos++] = j;
+    if (t == 1023) n_active[0] = cnt[1023];
+}
+
+// Ssum[e] = sum over active local samples of coef * other  (float4 per thread)
+__global__ void k_mim_aggregate(const float* __restrict__ other, const float* __restrict__ coef,
+                                const int* __restrict__ active, const int* __restrict__ n_active, int j0, int Bl, int n,
+                                float* __restrict__ Ssum) {
+    const int e4 = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e4 >= n * D / 4) return;
+    const int na = n_active[0];
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int a = 0; a < na; ++a) {
+        const int j = active[a];
+        if (j < j0 || j >= j0 + Bl) continue;
+        const float c = coef[j];
+        const float4 v = __ldg(reinterpret_cast<const float4*>(other + (size_t)(j - j0) * n * D) + e4);
+        s.x = fmaf(c, v.x, s.x); s.y = fmaf(c, v.y, s.y); s.z = fmaf(c, v.z, s.z); s.w = fmaf(c, v.w, s.w);
+    }
+    reinterpret_cast<float4*>(Ssum)[e4] = s;
+}
+
+// E[t][c] = sum_k Ssum[t][k] W[c][k] + scal*b_nn[c] + b_bs     (one CTA per row t, 128 threads)
+__global__ void __launch_bounds__(128)
+k_mim_project(const float* __restrict__ Ssum, const float* __restrict__ W, const float* __restrict__ b_nn,
+              const float* __restrict__ b_bs, const float* __restrict__ scal, float* __restrict__ E) {
+    __shared__ __align__(16) float row[D];
+    const int t = blockIdx.x, c = threadIdx.x;
+    row[c] = Ssum[(size_t)t * D + c];
+    __syncthreads();
+    const float4* w4 = reinterpret_cast<const float4*>(W + (size_t)c * D);
+    float s = 0.f;
+#pragma unroll 8
+    for (int k4 = 0; k4 < D / 4; ++k4) {
+        const float4 w = __ldg(w4 + k4);
+        const float4 r = *reinterpret_cast<const float4*>(row + k4 * 4);
+        s = fmaf(r.x, w.x, s); s = fmaf(r.y, w.y, s); s = fmaf(r.z, w.z, s); s = fmaf(r.w, w.w, s);
+    }
+    E[(size_t)t * D + c] = s + scal[0] * b_nn[c] + b_bs[0];
+}
+// out[c] = scale * sum_t X[t][c]      (1 CTA, 128 threads)
+__global__ void k_colsum(const float* __restrict__ X, int n, float* __restrict__ out) {
+    const int c = threadIdx.x;
+    float s = 0.f;
+    for (int t = 0; t < n; ++t) s += X[(size_t)t * D + c];
+    out[c] = s;
+}
+
+__global__ void k_mim_concat(const float* __restrict__ self_, const float* __restrict__ E, int64_t B, int n,
+                             float* __restrict__ out) {
+    const int64_t e4 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t per = (int64_t)2 * n * D / 4;
+    if (e4 >= B * per) return;
+    const int64_t i = e4 / per, r = e4 % per;
+    const int64_t half = (int64_t)n * D / 4;
+    float4 v = r < half ? __ldg(reinterpret_cast<const float4*>(self_) + i * half + r)
+                        : __ldg(reinterpret_cast<const float4*>(E) + (r - half));
+    reinterpret_cast<float4*>(out)[e4] = v;
+}
+
+// ---- backward pieces
+// dS[t][k] = sum_c dE[t][c] W[c][k]    (CTA per row t, thread k: coalesced rows of W)
+__global__ void __launch_bounds__(128)
+k_mim_dS(const float* __restrict__ dE, const float* __restrict__ W, float* __restrict__ dS) {
+    __shared__ float row[D];
+    const int t = blockIdx.x, k = threadIdx.x;
+    row[k] = dE[(size_t)t * D + k];
+    __syncthreads();
+    float s = 0.f;
+#pragma unroll 8
+    for (int c = 0; c < D; ++c) s = fmaf(row[c], __ldg(W + (size_t)c * D + k), s);
+    dS[(size_t)t * D + k] = s;
+}
+// dW[c][k] = sum_t dE[t][c] Ssum[t][k] ; CTA per c, thread k.  Also db_nn, db_bs by CTA 0..: see below
+__global__ void __launch_bounds__(128)
+k_mim_dW(const float* __restrict__ dE, const float* __restrict__ Ssum, const float* __restrict__ scal, int n,
+         float* __restrict__ dW, float* __restrict__ db_nn, float* __restrict__ db_bs) {
+    __shared__ float red[4];
+    const int c = blockIdx.x, k = threadIdx.x;
+    float s = 0.f, cs = 0.f;
+    for (int t = 0; t < n; ++t) {
+        const float g = dE[(size_t)t * D + c];
+        s = fmaf(g, Ssum[(size_t)t * D + k], s);
+        cs += g;
+    }
+    dW[(size_t)c * D + k] = s;
+    if (k == 0) db_nn[c] = scal[0] * cs;
+    if (c == 0) {  // db_bs = sum of all dE: thread k sums column k, then fixed-order reduce
+        float col = 0.f;
+        for (int t = 0; t < n; ++t) col += dE[(size_t)t * D + k];
+        col = warp_sum(col);
+        if ((k & 31) == 0) red[k >> 5] = col;
+        __syncthreads();
+        if (k == 0) db_bs[0] = (red[0] + red[1]) + (red[2] + red[3]);
+    }
+}
+// per local sample j: dw_bs[j] = gate_j <dS, other[j]> + <colsum(dE), b_nn> ; d_other[j] (+)= coef_j dS if gate_j
+__global__ void __launch_bounds__(256)
+k_mim_dsample(const float* __restrict__ dS, const float* __restrict__ dE, const float* __restrict__ other,
+              const float* __restrict__ b_nn, const float* __restrict__ coef, const float* __restrict__ gate, int j0,
+              int n, int accumulate, float* __restrict__ dw_bs, float* __restrict__ d_other) {
+    __shared__ float red[8];
+    const int j = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const bool on = gate[j0 + j] != 0.f;
+    // constant term <colsum(dE), b_nn> = sum_{t,c} dE[t][c] b_nn[c]
+    float s = 0.f;
+    const int total4 = n * D / 4;
+    for (int e4 = t; e4 < total4; e4 += 256) {
+        const float4 g = __ldg(reinterpret_cast<const float4*>(dE) + e4);
+        const float4 bb = __ldg(reinterpret_cast<const float4*>(b_nn) + (e4 & 31));
+        s += g.x * bb.x + g.y * bb.y + g.z * bb.z + g.w * bb.w;
+        if (on) {
+            const float4 ds = __ldg(reinterpret_cast<const float4*>(dS) + e4);
+            const float4 o = __ldg(reinterpret_cast<const float4*>(other + (size_t)j * n * D) + e4);
+            s += ds.x * o.x + ds.y * o.y + ds.z * o.z + ds.w * o.w;
+            if (d_other) {
+                const float c = coef[j0 + j];
+                float4* dst = reinterpret_cast<float4*>(d_other + (size_t)j * n * D) + e4;
+                float4 cur = accumulate ? *dst : make_float4(0.f, 0.f, 0.f, 0.f);
+                cur.x = fmaf(c, ds.x, cur.x); cur.y = fmaf(c, ds.y, cur.y); cur.z = fmaf(c, ds.z, cur.z); cur.w = fmaf(c, ds.w, cur.w);
+                *dst = cur;
+            }
+        }
+    }
+    s = warp_sum(s);
+    if (lane == 0) red[warp] = s;
+    __syncthreads();
+    if (t == 0) {
+        float r = 0.f;
+        for (int w = 0; w < 8; ++w) r += red[w];
+        dw_bs[j] = r;
+    }
+}
+
+// ---- mean pool
+__global__ void __launch_bounds__(128)
+k_meanpool_fwd(const float* __restrict__ enc, const float* __restrict__ esum, int n, float inv, float* __restrict__ u) {
+    // CTA per sample, 4 warps stride over t, lanes over float4 columns
+    __shared__ float4 red[4][32];
+    const int i = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int t = warp; t < n; t += 4) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(enc + ((size_t)i * n + t) * D) + lane);
+        s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    }
+    red[warp][lane] = s;
+    __syncthreads();
+    if (warp == 0) {
+        float4 r = red[0][lane];
+        for (int w = 1; w < 4; ++w) { r.x += red[w][lane].x; r.y += red[w][lane].y; r.z += red[w][lane].z; r.w += red[w][lane].w; }
+        if (esum) {
+            const float4 e = __ldg(reinterpret_cast<const float4*>(esum) + lane);
+            r.x += e.x; r.y += e.y; r.z += e.z; r.w += e.w;
+        }
+        reinterpret_cast<float4*>(u + (size_t)i * D)[lane] = make_float4(r.x * inv, r.y * inv, r.z * inv, r.w * inv);
+    }
+}
+__global__ void k_meanpool_bwd(const float* __restrict__ du, int64_t B, int n, float inv, int accumulate,
+                               float* __restrict__ d_enc) {
+    const int64_t e4 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e4 >= B * n * (D / 4)) return;
+    const int64_t i = e4 / ((int64_t)n * (D / 4));
+    const int c4 = (int)(e4 & 31);
+    const float4 g = __ldg(reinterpret_cast<const float4*>(du + i * D) + c4);
+    float4* dst = reinterpret_cast<float4*>(d_enc) + e4;
+    float4 cur = accumulate ? *dst : make_float4(0.f, 0.f, 0.f, 0.f);
+    cur.x = fmaf(g.x, inv, cur.x); cur.y = fmaf(g.y, inv, cur.y); cur.z = fmaf(g.z, inv, cur.z); cur.w = fmaf(g.w, inv, cur.w);
+    *dst = cur;
+}
+// dcol[c] = inv * sum_i du[i][c]   (1 CTA, 128 threads, sequential over i)
+__global__ void k_du_colsum(const float* __restrict__ du, int B, float inv, float* __restrict__ dcol) {
+    const int c = threadIdx.x;
+    float s = 0.f;
+    for (int i = 0; i < B; ++i) s += du[(size_t)i * D + c];
+    dcol[c] = s * inv;
+}
+
+}  // namespace amid
+
+using namespace amid;
+
+extern "C" int amid_mim_scores(const float* a, const float* b, int32_t B, int32_t n, float* m, amid_stream_t s_) {
+    AMID_REQUIRE(a && b && m && B > 0 && n > 0, "mim_scores: bad argument");
+    AMID_REQUIRE(aligned16(a) && aligned16(b), "mim_scores: misaligned buffer");
+    cudaError_t e = cudaFuncSetAttribute((const void*)k_mim_scores, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MIM_SMEM);
+    if (e != cudaSuccess) return set_error(-3, "mim_scores: smem attribute: %s", cudaGetErrorString(e));
+    k_mim_scores<<<B, 256, MIM_SMEM, (cudaStream_t)s_>>>(a, b, n, m);
+    AMID_LAUNCH_CHECK("k_mim_scores");
+    return 0;
+}
+
+extern "C" int amid_mim_gate(const float* m, const float* w_bs, int32_t Bg, float ts, float* p, float* gate, float* coef,
+                             int32_t* active, int32_t* n_active, float* scal, amid_stream_t s_) {
+    AMID_REQUIRE(m && w_bs && p && gate && coef && active && n_active && scal && Bg > 0, "mim_gate: bad argument");
+    k_mim_gate<<<1, 1024, 0, (cudaStream_t)s_>>>(m, w_bs, Bg, ts, p, gate, coef, active, n_active, scal);
+    AMID_LAUNCH_CHECK("k_mim_gate");
+    return 0;
+}
+
+extern "C" int amid_mim_aggregate(const float* other, const float* coef, const int32_t* active, const int32_t* n_active,
+                                  int32_t j0, int32_t Bl, int32_t n, float* Ssum, amid_stream_t s_) {
+    AMID_REQUIRE(other && coef && active && n_active && Ssum && n > 0 && Bl > 0, "mim_aggregate: bad argument");
+    const int total4 = n * D / 4;
+    k_mim_aggregate<<<(total4 + 127) / 128, 128, 0, (cudaStream_t)s_>>>(other, coef, active, n_active, j0, Bl, n, Ssum);
+    AMID_LAUNCH_CHECK("k_mim_aggregate");
+    return 0;
+}
+
+extern "C" int amid_mim_project(const float* Ssum, const float* w_nn, const float* b_nn, const float* b_bs,
+                                const float* scal, int32_t n, float* E, float* esum, amid_stream_t s_) {
+    AMID_REQUIRE(Ssum && w_nn && b_nn && b_bs && scal && E && n > 0, "mim_project: bad argument");
+    k_mim_project<<<n, 128, 0, (cudaStream_t)s_>>>(Ssum, w_nn, b_nn, b_bs, scal, E);
+    AMID_LAUNCH_CHECK("k_mim_project");
+    if (esum) {
+        k_colsum<<<1, 128, 0, (cudaStream_t)s_>>>(E, n, esum);
+        AMID_LAUNCH_CHECK("k_colsum");
+    }
+    return 0;
+}
+
+extern "C" int amid_mim_concat(const float* self_, const float* E, int32_t B, int32_t n, float* out, amid_stream_t s_) {
+    AMID_REQUIRE(self_ && E && out && B > 0 && n > 0, "mim_concat: bad argument");
+    const int64_t total4 = (int64_t)B * 2 * n * D / 4;
+    k_mim_concat<<<(unsigned)((total4 + 255) / 256), 256, 0, (cudaStream_t)s_>>>(self_, E, B, n, out);
+    AMID_LAUNCH_CHECK("k_mim_concat");
+    return 0;
+}
+
+extern "C" int amid_mim_bwd(const float* dE, const float* Ssum, const float* other, const float* w_nn, const float* b_nn,
+                            const float* coef, const float* gate, const int32_t* active, const int32_t* n_active,
+                            const float* scal, int32_t j0, int32_t Bl, int32_t n, float* dW_nn, float* db_nn,
+                            float* db_bs, float* dw_bs, float* d_other, float* ws_dS, amid_stream_t s_) {
+    (void)active; (void)n_active;
+    AMID_REQUIRE(dE && Ssum && other && w_nn && b_nn && coef && gate && scal && dW_nn && db_nn && db_bs && dw_bs && ws_dS,
+                 "mim_bwd: null argument");
+    AMID_REQUIRE(Bl > 0 && n > 0, "mim_bwd: Bl=%d n=%d", Bl, n);
+    cudaStream_t s = (cudaStream_t)s_;
+    k_mim_dS<<<n, 128, 0, s>>>(dE, w_nn, ws_dS);
+    AMID_LAUNCH_CHECK("k_mim_dS");
+    k_mim_dW<<<D, 128, 0, s>>>(dE, Ssum, scal, n, dW_nn, db_nn, db_bs);
+    AMID_LAUNCH_CHECK("k_mim_dW");
+    k_mim_dsample<<<Bl, 256, 0, s>>>(ws_dS, dE, other, b_nn, coef, gate, j0, n, d_other ? 1 : 0, dw_bs, d_other);
+    AMID_LAUNCH_CHECK("k_mim_dsample");
+    return 0;
+}
+
+extern "C" int amid_meanpool_fwd(const float* enc, const float* esum, int32_t B, int32_t n, float denom, float* u,
+                                 amid_stream_t s_) {
+    AMID_REQUIRE(enc && u && B > 0 && n > 0 && denom > 0.f, "meanpool_fwd: bad argument");
+    k_meanpool_fwd<<<B, 128, 0, (cudaStream_t)s_>>>(enc, esum, n, 1.0f / denom, u);
+    AMID_LAUNCH_CHECK("k_meanpool_fwd");
+    return 0;
+}
+
+extern "C" int amid_meanpool_bwd(const float* du, int32_t B, int32_t n, float denom, int32_t accumulate, float* d_enc,
+                                 float* dcol, amid_stream_t s_) {
+    AMID_REQUIRE(du && B > 0 && n > 0 && denom > 0.f, "meanpool_bwd: bad argument");
+    cudaStream_t s = (cudaStream_t)s_;
+    if (d_enc) {
+        const int64_t total4 = (int64_t)B * n * (D / 4);
+        k_meanpool_bwd<<<(unsigned)((total4 + 255) / 256), 256, 0, s>>>(du, B, n, 1.0f / denom, accumulate, d_enc);
+        AMID_LAUNCH_CHECK("k_meanpool_bwd");
+    }
+    if (dcol) {
+        k_du_colsum<<<1, 128, 0, s>>>(du, B, 1.0f / denom, dcol);
+        AMID_LAUNCH_CHECK("k_du_colsum");
+    }
+    return 0;
+}

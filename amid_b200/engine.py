@@ -1,0 +1,158 @@
+"""Fused training / evaluation engine around the drop-in ``SASRec``.
+
+``Trainer.step`` is the whole reference training step (train_sr.py:201-215, or the two
+phases of train_sr_dr.py:205-225 / 378-398) executed as one kernel sequence over the C
+ABI: forward -> fused loss -> backward -> deterministic sort+segmented embedding-gradient
+reduction -> Adam (one fused launch over the flat dense-parameter buffer, and a
+row-sparse Adam on the table with exact dense-Adam semantics).
+Under data parallelism (one process per GPU) the dense gradients are all-reduced in one
+NCCL call and the locally pre-reduced table-gradient rows are all-gathered and reduced
+again in fixed rank order.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional
+
+import torch
+
+from . import _abi, hotpath
+from ._abi import call
+from .hotpath import D, _ptr, _stream
+
+TABLE = "item_emb_layer.emb_item.weight"
+BATCH_KEYS = ("i_node", "neg_samples", "seq_d1", "seq_d2", "domain_id", "label")
+
+
+class _AdamState:
+    def __init__(self, flat_numel: int, V: int, dev):
+        z = lambda *s: torch.zeros(*s, device=dev, dtype=torch.float32)
+        self.m, self.v = z(flat_numel), z(flat_numel)
+        self.tm, self.tv = z(V, D), z(V, D)
+        self.last = torch.zeros(V, device=dev, dtype=torch.int32)
+        self.step = 0
+
+
+class Trainer:
+    """Fused train step for an ``amid_b200.model_seq.SASRec`` on the current CUDA device."""
+
+    def __init__(self, model, lr: float = 5e-4, lr2: float = 1.0, dr_e_w: float = 0.01, betas=(0.9, 0.999),
+                 eps: float = 1e-8, dist: Optional[hotpath.DistCtx] = None, sparse_table: bool = True):
+        self.model, self.cfg, self.dist = model, model.cfg, dist
+        self.lr, self.lr2, self.dr_e_w, self.betas, self.eps = lr, lr * lr2, dr_e_w, betas, eps   # train_sr_dr.py:668-669
+        self.sparse_table = sparse_table
+        P = model.param_dict()
+        self.table = P[TABLE]
+        if not self.table.is_cuda:
+            raise _abi.AmidError("Trainer needs the model on a CUDA device (no CPU fallback)")
+        dev = self.table.device
+        # re-point every dense parameter at a view of one flat buffer (single Adam launch, single all-reduce)
+        self.names = [n for n in P if n != TABLE]
+        total = sum((P[n].numel() + 3) // 4 * 4 for n in self.names)
+        self.flat_p = torch.zeros(total, device=dev, dtype=torch.float32)
+        self.flat_g = torch.zeros(total, device=dev, dtype=torch.float32)
+        self.G: Dict[str, torch.Tensor] = {}
+        off = 0
+        for n in self.names:
+            k = P[n].numel()
+            view = self.flat_p[off:off + k].view(P[n].shape)
+            view.copy_(P[n].data)
+            P[n].data = view
+            self.G[n] = self.flat_g[off:off + k].view(P[n].shape)
+            off += (k + 3) // 4 * 4
+        self.P = {n: p.data for n, p in model.named_parameters()}
+        self.V = self.table.shape[0]
+        self.opt = [_AdamState(total, self.V, dev)]
+        if self.cfg.isDR:
+            self.opt.append(_AdamState(total, self.V, dev))     # optimizer2 (train_sr_dr.py:669)
+        self.active_opt = 0
+        self.world = dist.world if dist is not None else 1
+        self.last_losses = None
+        self._seed = 0
+
+    # ------------------------------------------------------------------ helpers
+    def _table_adam(self, st: _AdamState, uid, ug, nu, lr):
+        call("amid_adam_rows_lazy", _ptr(self.table.data), _ptr(st.tm), _ptr(st.tv), _ptr(st.last), _ptr(uid), _ptr(ug),
+             _ptr(nu), uid.numel(), st.step, lr, self.betas[0], self.betas[1], self.eps, _stream())
+
+    def flush(self):
+        """Apply the pending zero-gradient Adam steps to every table row (exact dense semantics)."""
+        for i, st in enumerate(self.opt):
+            if st.step > 0 and self.sparse_table:
+                lr = self.lr if i == 0 else self.lr2
+                call("amid_adam_rows_flush", _ptr(self.table.data), _ptr(st.tm), _ptr(st.tv), _ptr(st.last), self.V,
+                     st.step, lr, self.betas[0], self.betas[1], self.eps, _stream())
+
+    def to_device(self, host_batch: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+        """H2D of one batch (pinned host tensors recommended), ids as int64, labels fp32."""
+        dev = self.table.device
+        out = {}
+        for k, v in host_batch.items():
+            if k == "label":
+                out[k] = v.to(dev, dtype=torch.float32, non_blocking=True)
+            else:
+                out[k] = v.to(dev, dtype=torch.int64, non_blocking=True)
+        return out
+
+    # ------------------------------------------------------------------ the step
+    def step(self, batch: Dict[str, torch.Tensor], phase: int = 1) -> torch.Tensor:
+        """One optimisation step.  phase 1: loss_cls (+ dr_e_w * loss_dr_e when isDR) with
+        `optimizer`; phase 2 (isDR only): loss_dr_r with `optimizer2`.  Returns the device
+        tensor [loss_cls, loss_dr_e, loss_dr_r] (local-batch share of the global means)."""
+        cfg = self.cfg
+        oi = 0 if phase == 1 else 1
+        if phase == 2 and not cfg.isDR:
+            raise _abi.AmidError("phase 2 needs isDR=True (train_sr_dr.py:381-384)")
+        if oi != self.active_opt:
+            self.flush()                       # the two Adams interleave on the same parameters
+            self.active_opt = oi
+        st = self.opt[oi]
+        lr = self.lr if oi == 0 else self.lr2
+        self._seed += 1
+        seed = (self.model._seed_base * 1000003 + self._seed) & (2**63 - 1)
+        train = self.model.training
+        probs, ctx = hotpath.forward(self.P, cfg, batch["i_node"], batch["neg_samples"], batch["seq_d1"],
+                                     batch["seq_d2"], train=train, seed=seed, dist=self.dist)
+        mode = 0 if not cfg.isDR else (1 if phase == 1 else 2)
+        B = probs.shape[2]
+        losses, dprobs = hotpath.loss_fwd_bwd(probs, batch["label"], batch["domain_id"], batch.get("ob_label"), mode,
+                                              self.dr_e_w, B * self.world)
+        _, ids_all, rows_all = hotpath.backward(self.P, cfg, ctx, dprobs, G=self.G, dist=self.dist)
+        uid, ug, nu = hotpath.segreduce(ids_all, rows_all, self.V)
+        if self.world > 1:
+            self.dist.all_reduce(self.flat_g)                      # dense grads: one NCCL call
+            uid, ug, nu = self._exchange_table_grads(uid, ug, nu)
+            self.dist.all_reduce(losses)
+        st.step += 1
+        call("amid_adam_dense", _ptr(self.flat_p), _ptr(self.flat_g), _ptr(st.m), _ptr(st.v), self.flat_p.numel(),
+             st.step, lr, self.betas[0], self.betas[1], self.eps, _stream())
+        if self.sparse_table:
+            self._table_adam(st, uid, ug, nu, lr)
+        else:                                                      # reference-equivalent dense pass over [V,128]
+            dense = hotpath.dense_table_grad(uid, ug, nu, self.V)
+            call("amid_adam_dense", _ptr(self.table.data), _ptr(dense), _ptr(st.tm), _ptr(st.tv), self.table.numel(),
+                 st.step, lr, self.betas[0], self.betas[1], self.eps, _stream())
+        self.last_losses = losses
+        return losses
+
+    def _exchange_table_grads(self, uid, ug, nu):
+        """Replicated table under DP: all-gather every rank's pre-reduced (row id, gradient row)
+        list (unused slots carry the sentinel id V-1 with a zero row) and reduce again in rank
+        order, so every replica applies the identical update."""
+        n = uid.numel()
+        dev = ug.device
+        valid = torch.arange(n, device=dev) < nu.to(torch.int64)
+        uid = torch.where(valid, uid, torch.full_like(uid, self.V - 1))
+        ug = torch.where(valid.unsqueeze(1), ug, torch.zeros_like(ug))
+        all_ids = torch.empty(n * self.world, device=dev, dtype=torch.int64)
+        all_rows = torch.empty(n * self.world, D, device=dev, dtype=torch.float32)
+        self.dist.all_gather_into(all_ids, uid)
+        self.dist.all_gather_into(all_rows, ug)
+        return hotpath.segreduce(all_ids, all_rows, self.V)
+
+    # ------------------------------------------------------------------ evaluation forward
+    @torch.no_grad()
+    def scores(self, batch: Dict[str, torch.Tensor]) -> torch.Tensor:
+        """Eval-mode probabilities [n_heads, 2, B, C] for a batch (model.eval() semantics)."""
+        probs, _ = hotpath.forward(self.P, self.cfg, batch["i_node"], batch["neg_samples"], batch["seq_d1"],
+                                   batch["seq_d2"], train=False, seed=0, dist=self.dist, need_ctx=False)
+        return probs

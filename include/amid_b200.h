@@ -1,0 +1,223 @@
+/* amid_b200 -- C ABI of the B200-native AMID SASRec hot path.
+ *
+ * The reference (WujiangXu/AMID) is pure Python/PyTorch and has no FFI of its own; its
+ * "plugin API" for this path is the nn.Module contract of model_seq.SASRec
+ * (model_seq.py:390-443).  amid_b200/model_seq.py keeps that contract and binds the
+ * entry points below with ctypes.  Each entry point names the
+ * reference code it replaces.
+ *
+ * Conventions: raw device pointers + sizes only; the caller owns every buffer,
+ * including workspaces (sizes via the *_workspace_bytes functions); no allocation and no
+ * device synchronisation inside (the two *_host_sync helpers excepted and named so);
+ * kernels are launched on the passed stream; return value 0 = ok, negative = error and
+ * amid_last_error() (thread local) says why.  Shapes: d = 128, heads = 8 (the reference
+ * hard-codes 8 heads at model_seq.py:348; d = 128 is the run.sh/argparse default),
+ * hid <= 64.  All floats are fp32, ids are int64, row-major contiguous, 16-byte aligned.
+ * There is no CPU fallback.
+ */
+#ifndef AMID_B200_H
+#define AMID_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* amid_stream_t; /* cudaStream_t */
+
+#define AMID_D 128
+#define AMID_HEADS 8
+#define AMID_BLOCKS 2
+
+/* dropout description; train = 0 disables every dropout site (model.eval()). */
+typedef struct {
+    int32_t train;      /* 0 = eval */
+    float p;            /* drop probability (reference: 0.5 everywhere, model_seq.py:335,350,355) */
+    uint64_t seed;      /* per-step seed */
+    uint32_t site_base; /* first site id used by this call (an encoder uses 7 sites) */
+} amid_dropout;
+
+/* One Log2feats encoder (model_seq.py:331-357).  Used for parameters (read) and for
+ * gradients (written).  Index [i] = block i. */
+typedef struct {
+    float* pos_emb;                  /* pos_emb.weight                [Lmax,128] */
+    float* ln1_w[AMID_BLOCKS];       /* attention_layernorms.i.weight [128] */
+    float* ln1_b[AMID_BLOCKS];
+    float* in_w[AMID_BLOCKS];        /* attention_layers.i.in_proj_weight [384,128] */
+    float* in_b[AMID_BLOCKS];        /* in_proj_bias [384] */
+    float* out_w[AMID_BLOCKS];       /* out_proj.weight [128,128] */
+    float* out_b[AMID_BLOCKS];
+    float* ln2_w[AMID_BLOCKS];       /* forward_layernorms.i */
+    float* ln2_b[AMID_BLOCKS];
+    float* c1_w[AMID_BLOCKS];        /* forward_layers.i.conv1.weight [128,128,1] */
+    float* c1_b[AMID_BLOCKS];
+    float* c2_w[AMID_BLOCKS];
+    float* c2_b[AMID_BLOCKS];
+    float* ln3_w;                    /* last_layernorm */
+    float* ln3_b;
+} amid_encoder_tensors;
+
+/* Activations the forward keeps for the backward, all [B*L,128] unless noted. */
+typedef struct {
+    float* qn[AMID_BLOCKS];   /* LN1 output (the "Q" of model_seq.py:373) */
+    float* q[AMID_BLOCKS];    /* scaled query projection */
+    float* k[AMID_BLOCKS];
+    float* v[AMID_BLOCKS];
+    float* o[AMID_BLOCKS];    /* attention output before out_proj */
+    float* lse[AMID_BLOCKS];  /* [B,8,L] log-sum-exp of the attention rows */
+    float* x1[AMID_BLOCKS];   /* Q + mha  (model_seq.py:378) */
+    float* y[AMID_BLOCKS];    /* LN2 output */
+    float* h[AMID_BLOCKS];    /* relu(dropout1(conv1)) */
+    float* xout[AMID_BLOCKS]; /* block output after the timeline mask (model_seq.py:383) */
+    float* st1[AMID_BLOCKS];  /* [B*L,2] mean, rstd of LN1 */
+    float* st2[AMID_BLOCKS];
+    float* st3;               /* last_layernorm stats */
+} amid_encoder_saved;
+
+const char* amid_last_error(void);
+int amid_version(void);
+
+/* ---- a1: embItemLayerEnhance.forward (model_seq.py:27-29, calls :418-421) ---------- */
+/* out[r,:] = table[ids[r],:]  for r < n_rows.  Bit-exact copy. */
+int amid_emb_gather_fwd(const float* table, int64_t V, const int64_t* ids, int64_t n_rows,
+                        float* out, amid_stream_t stream);
+/* 1 if a gather since the last call saw an id outside [0,V) (such rows are skipped);
+ * synchronises the device -- for tests / debugging, never on the hot path. */
+int amid_gather_error_host_sync(void);
+
+/* ---- a1+a2: gather fused with the Log2feats prologue (model_seq.py:360-366) -------- */
+/* x0[b,l,:] = dropout(table[ids[b,l]] + pos[l]) * ~tmask,  tmask = (table[id]+pos == 0)
+ * element-wise, bit-packed: tmask[(b*L+l)*4 + e] bit j  <->  column 4*j+e.
+ * If ids == NULL the rows are read from `rows` ([B,L,128], the InnerComp path
+ * model_seq.py:422-424) instead of the table. */
+int amid_seq_embed_fwd(const float* table, int64_t V, const int64_t* ids, const float* rows,
+                       const float* pos, int32_t B, int32_t L, float* x0, uint32_t* tmask,
+                       const amid_dropout* drop, amid_stream_t stream);
+/* backward of the above: dx0 <- dx0 * ~tmask * keep/(1-p) in place (this is then the
+ * per-row table gradient), dpos[l,:] = sum_b dx0[b,l,:]. */
+int amid_seq_embed_bwd(float* dx0, const uint32_t* tmask, int32_t B, int32_t L, float* dpos,
+                       const amid_dropout* drop, amid_stream_t stream);
+
+/* ---- a3-a5: Log2feats blocks + last LN (model_seq.py:371-385; MHA arithmetic from
+ *      torch/nn/functional.py:5849-5856, 6630-6653; FFN model_seq.py:322-326) --------- */
+int64_t amid_encoder_fwd_workspace_bytes(int32_t B, int32_t L);
+int amid_encoder_fwd(const amid_encoder_tensors* P, const float* x0, const uint32_t* tmask,
+                     int32_t B, int32_t L, const amid_dropout* drop, amid_encoder_saved* S,
+                     float* enc_out, void* workspace, int64_t workspace_bytes, amid_stream_t stream);
+int64_t amid_encoder_bwd_workspace_bytes(int32_t B, int32_t L);
+/* d_enc [B*L,128] is consumed; G receives the parameter gradients (overwritten, pos_emb
+ * excluded -- see amid_seq_embed_bwd); dx0 [B*L,128] receives the input gradient. */
+int amid_encoder_bwd(const amid_encoder_tensors* P, const float* x0, const uint32_t* tmask,
+                     int32_t B, int32_t L, const amid_dropout* drop, const amid_encoder_saved* S,
+                     const float* enc_out, const float* d_enc, amid_encoder_tensors* G, float* dx0,
+                     void* workspace, int64_t workspace_bytes, amid_stream_t stream);
+
+/* ---- a6: InterComp / InnerComp in closed form (model_seq.py:474-497 / 450-472) ----- */
+/* m[j] = max_{s,t} <a[j,s,:], b[j,t,:]>,  a,b: [B,n,128]  (the [bs,B,n,n] matmul+max of
+ * model_seq.py:489-490 without its redundant outer axis). */
+int amid_mim_scores(const float* a, const float* b, int32_t B, int32_t n, float* m, amid_stream_t stream);
+/* p = softmax_j(m) over the (global) batch, g = 1[p > ts], coef[j] = w_bs[j]*g[j];
+ * scal[0] = sum_j w_bs[j]; active list = indices with g=1 (ascending), n_active[0]. */
+int amid_mim_gate(const float* m, const float* w_bs, int32_t Bglobal, float ts, float* p, float* gate, float* coef,
+                  int32_t* active, int32_t* n_active, float* scal, amid_stream_t stream);
+/* Ssum[n,128] = sum_{j active, j0<=j<j0+Blocal} coef[j]*other[j-j0]  (fixed ascending order). */
+int amid_mim_aggregate(const float* other, const float* coef, const int32_t* active, const int32_t* n_active,
+                       int32_t j0, int32_t Blocal, int32_t n, float* Ssum, amid_stream_t stream);
+/* E[n,128] = Ssum W_nn^T + scal[0]*b_nn + b_bs ; esum[128] = sum_t E[t,:]. */
+int amid_mim_project(const float* Ssum, const float* w_nn, const float* b_nn, const float* b_bs,
+                     const float* scal, int32_t n, float* E, float* esum, amid_stream_t stream);
+/* out[i] = cat(self[i], E) : [B,2n,128]  (only the InnerComp path materialises it). */
+int amid_mim_concat(const float* self_, const float* E, int32_t B, int32_t n, float* out, amid_stream_t stream);
+/* backward given dE [n,128]: dSsum = dE W_nn; dW_nn = dE^T Ssum; db_nn = scal[0]*colsum(dE);
+ * db_bs = sum(dE); dw_bs[j] = g_j <dSsum, other[j]> + <colsum(dE), b_nn>;
+ * d_other[j] (+)= coef[j]*dSsum for active j (accumulate != 0 adds, else rows of
+ * inactive j are left untouched: the caller zero-fills or accumulates). */
+int amid_mim_bwd(const float* dE, const float* Ssum, const float* other, const float* w_nn, const float* b_nn,
+                 const float* coef, const float* gate, const int32_t* active, const int32_t* n_active,
+                 const float* scal, int32_t j0, int32_t Blocal, int32_t n,
+                 float* dW_nn, float* db_nn, float* db_bs, float* dw_bs /*[Blocal]*/, float* d_other,
+                 float* ws_dS /*[n,128]*/, amid_stream_t stream);
+
+/* ---- a7: mean pool (model_seq.py:432-434) ------------------------------------------ */
+/* u[i,:] = (sum_t enc[i,t,:] + (esum ? esum[:] : 0)) / denom */
+int amid_meanpool_fwd(const float* enc, const float* esum, int32_t B, int32_t n, float denom, float* u,
+                      amid_stream_t stream);
+/* d_enc[i,t,:] (+)= du[i,:]/denom ; dcol[:] = sum_i du[i,:]/denom (the dE row when ItC). */
+int amid_meanpool_bwd(const float* du, int32_t B, int32_t n, float denom, int32_t accumulate, float* d_enc,
+                      float* dcol, amid_stream_t stream);
+
+/* ---- a8: predictModule (model_seq.py:32-54), up to 3 heads (isDR :436-440) --------- */
+typedef struct {
+    float* w0; /* fc.0.weight [hid,256] */
+    float* b0; /* fc.0.bias   [hid] */
+    float* w2; /* fc.2.weight [1,hid] */
+    float* b2; /* fc.2.bias   [1] */
+} amid_head_tensors;
+/* probs[head][dom][b,c] = sigmoid(w2 . relu(W0 [u_dom[b] ; items[b,c]] + b0) + b2)
+ * probs: [n_heads,2,B,C] contiguous. */
+int amid_score_fwd(const float* u1, const float* u2, const float* items, const amid_head_tensors* heads,
+                   int32_t n_heads, int32_t hid, int32_t B, int32_t C, float* probs, amid_stream_t stream);
+int64_t amid_score_bwd_workspace_bytes(int32_t n_heads, int32_t hid, int32_t B, int32_t C);
+/* dprobs: [n_heads,2,B,C] gradient w.r.t. the probabilities.  Outputs du1,du2 [B,128],
+ * ditems [B,C,128], head gradients G[n_heads]. */
+int amid_score_bwd(const float* u1, const float* u2, const float* items, const amid_head_tensors* heads,
+                   int32_t n_heads, int32_t hid, int32_t B, int32_t C, const float* probs, const float* dprobs,
+                   float* du1, float* du2, float* ditems, amid_head_tensors* G,
+                   void* workspace, int64_t workspace_bytes, amid_stream_t stream);
+
+/* ---- a9: losses (train_sr.py:205-212; train_sr_dr.py:212-221, 385-395) -------------- */
+/* mode 0: loss_cls                      (train_sr.py:210-211)
+ * mode 1: loss_cls + dr_e_w*loss_dr_e   (train_sr_dr.py:217-221)  needs 3 heads
+ * mode 2: loss_dr_r                     (train_sr_dr.py:392-394)  needs 3 heads + ob_label
+ * probs/dprobs [n_heads,2,B,C]; labels [B,C] fp32; domain_id, ob_label [B] int64.
+ * inv_count = 1/(Bglobal*C) (the torch.mean divisor).  losses[0..2] = (cls, dr_e, dr_r)
+ * means of the LOCAL batch rows scaled by inv_count.  BCE semantics = nn.BCELoss on
+ * probabilities: log clamp at -100, backward divides by max(p(1-p), 1e-12). */
+int amid_loss_fwd_bwd(const float* probs, int32_t n_heads, int32_t B, int32_t C, const float* labels,
+                      const int64_t* domain_id, const int64_t* ob_label, int32_t mode, float dr_e_w,
+                      float inv_count, float* losses, float* dprobs, amid_stream_t stream);
+
+/* ---- a9: embedding backward = deterministic sort-by-index segmented reduction ------ */
+int64_t amid_embgrad_workspace_bytes(int64_t n_rows);
+/* ids [n_rows] int64, grad_rows [n_rows,128].  Produces the unique ids (ascending) in
+ * uniq_ids, their summed gradient rows in uniq_grads [n_rows,128] (first n_uniq valid)
+ * and n_uniq[0].  Rows with equal id are added in ascending source-row order. */
+int amid_embgrad_segreduce(const int64_t* ids, const float* grad_rows, int64_t n_rows, int64_t V,
+                           int64_t* uniq_ids, float* uniq_grads, int32_t* n_uniq,
+                           void* workspace, int64_t workspace_bytes, amid_stream_t stream);
+/* dense[uniq_ids[u],:] = uniq_grads[u,:]  (dense [V,128] must be zero-filled by the caller;
+ * this is the drop-in path that feeds torch.optim.Adam a dense .grad like aten::embedding_dense_backward). */
+int amid_embgrad_scatter_dense(const int64_t* uniq_ids, const float* uniq_grads, const int32_t* n_uniq,
+                               int64_t max_rows, float* dense, int64_t V, amid_stream_t stream);
+
+/* ---- a9: Adam (torch.optim.Adam, betas (.9,.999), eps 1e-8, no weight decay) -------- */
+/* dense: one fused pass over n elements; step = 1-based step number of this update. */
+int amid_adam_dense(float* p, const float* g, float* m, float* v, int64_t n, int32_t step, float lr,
+                    float beta1, float beta2, float eps, amid_stream_t stream);
+/* row-sparse with EXACT dense semantics: for each unique row, first replay the
+ * zero-gradient steps last_step[row]+1 .. step-1 that a dense Adam would have applied,
+ * then apply step `step` with the row gradient; last_step[row] = step. */
+int amid_adam_rows_lazy(float* table, float* m, float* v, int32_t* last_step, const int64_t* uniq_ids,
+                        const float* uniq_grads, const int32_t* n_uniq, int64_t max_rows, int32_t step,
+                        float lr, float beta1, float beta2, float eps, amid_stream_t stream);
+/* bring every row of the table up to `step` (before eval / state_dict / optimizer switch). */
+int amid_adam_rows_flush(float* table, float* m, float* v, int32_t* last_step, int64_t V, int32_t step,
+                         float lr, float beta1, float beta2, float eps, amid_stream_t stream);
+
+/* ---- a10: eval ranking (utils.py:296-301, train_sr.py:114-115) ---------------------- */
+/* scores [N,C], positive in column 0.  s0 = scores[r,0] - fix (fp32).  n_greater[r] =
+ * #{c>=1 : scores[r,c] > s0}, n_equal[r] = #{c>=1 : scores[r,c] == s0}.  The rank of the
+ * positive under argsort(argsort(-scores)) is n_greater when n_equal == 0. */
+int amid_rank_counts(const float* scores, int64_t N, int32_t C, float fix, int32_t* n_greater,
+                     int32_t* n_equal, amid_stream_t stream);
+
+/* ---- test support: the keep-mask a dropout site uses (for oracle mask injection) ---- */
+/* feature site: out[r*128+c] for r<rows; attention site: out[((b*8+h)*L+i)*L+j]. */
+int amid_dropout_mask_feature(const amid_dropout* drop, uint32_t site, int64_t rows, uint8_t* out, amid_stream_t stream);
+int amid_dropout_mask_attn(const amid_dropout* drop, uint32_t site, int32_t B, int32_t L, uint8_t* out, amid_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AMID_B200_H */

@@ -154,6 +154,7 @@ def save(name, **arrs):
 
 def main():
     d, hid = 128, 32
+    only = os.environ.get("GOLDEN_ONLY")
     crit = nn.BCELoss(reduce=False)
 
     # ---- F1: C1-shape eval-mode forward on a real cloth_sport_train75 batch (bs=256, L=20, ItC, ts2=0.4)
@@ -326,6 +327,50 @@ def main():
     with torch.no_grad():
         p1, p2 = fwd(m, bt[0])
     save("tmask.npz", V=V, pad=pad, p1=p1.numpy(), p2=p2.numpy(), enc1=feats["enc1"].numpy(), **batch_np(bt[0]))
+
+    # ---- F8: train mode with dropout DISABLED (p = 0): fwd, loss, grads, 3 Adam steps -- directly
+    #      comparable with the CUDA path (whose dropout RNG differs from torch's), bs=16, L=20
+    bs, L = 16, 20
+    bt = draw_batches("cloth_sport_train75.csv", bs, L, True, 199, 3, seed=6)
+    V, pad = compact(bt)
+    P = make_params(18, V, d, L, hid, bs)
+    m = build(P, V, d, L, hid, bs, False, True, 0.5, 0.07, False).train()
+    for mod in m.modules():
+        if isinstance(mod, nn.Dropout):
+            mod.p = 0.0
+        if isinstance(mod, nn.MultiheadAttention):
+            mod.dropout = 0.0
+    opt = torch.optim.Adam(m.parameters(), lr=5e-4)
+    sel8 = ["predictModule.fc.0.weight", "predictModule.fc.0.bias", "predictModule.fc.2.weight",
+            "predictModule.fc.2.bias", "itc_d1.trans_bs.weight", "itc_d1.trans_bs.bias", "itc_d2.trans_nn.weight",
+            "itc_d2.trans_nn.bias", "sac1.pos_emb.weight", "sac1.attention_layers.0.in_proj_weight",
+            "sac1.attention_layers.0.in_proj_bias", "sac2.attention_layers.1.out_proj.weight",
+            "sac2.attention_layers.1.out_proj.bias", "sac1.forward_layers.1.conv1.weight",
+            "sac2.forward_layers.0.conv2.weight", "sac2.forward_layers.0.conv2.bias",
+            "sac1.attention_layernorms.0.weight", "sac1.attention_layernorms.1.bias",
+            "sac2.forward_layernorms.0.weight", "sac2.forward_layernorms.1.bias", "sac2.last_layernorm.weight",
+            "sac1.last_layernorm.bias"]
+    arrs = {"V": V, "pad": pad}
+    for step, b in enumerate(bt):
+        p1, p2 = fwd(m, b)
+        loss = ref_loss_cls(crit, p1, p2, b["label"].float(), b["domain_id"])
+        opt.zero_grad(); loss.backward()
+        if step == 0:
+            arrs.update(p1=p1.detach().numpy(), p2=p2.detach().numpy())
+            for n, prm in m.named_parameters():
+                if n == "item_emb_layer.emb_item.weight":
+                    arrs["gtab_idx"], arrs["gtab_rows"] = sparse_rows(prm.grad)
+                elif n in sel8:
+                    arrs["grad/" + n] = prm.grad.numpy().copy()
+        opt.step()
+        arrs[f"loss_step{step}"] = loss.detach().numpy()
+        arrs.update({f"b{step}_{k}": v.numpy() for k, v in b.items()})
+    for n, prm in m.named_parameters():
+        if n == "item_emb_layer.emb_item.weight":
+            arrs["after3/" + n] = prm.detach().numpy().copy()
+        elif n in sel8:
+            arrs["after3/" + n] = prm.detach().numpy().copy()
+    save("train_p0.npz", **arrs)
 
 
 if __name__ == "__main__":

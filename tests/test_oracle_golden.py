@@ -161,3 +161,30 @@ def test_c1_eval_scores_on_test_batches():
         p1, p2 = _fwd(P, z, pre=f"b{i}_", isInC=False, isItC=True, ts1=0.5, ts2=0.4, isDR=False)
         np.testing.assert_allclose(p1.numpy(), z["p1"][i * 256:(i + 1) * 256], rtol=0, atol=3e-6)
         np.testing.assert_allclose(p2.numpy(), z["p2"][i * 256:(i + 1) * 256], rtol=0, atol=3e-6)
+
+
+def test_train_p0_trajectory():
+    """Train mode with dropout disabled -- the fixture the CUDA path is compared with directly."""
+    z = load("train_p0.npz")
+    V = int(z["V"])
+    P = {k: v.clone().requires_grad_(True) for k, v in make_params(18, V, D, 20, HID, 16).items()}
+    st = {k: (torch.zeros_like(v), torch.zeros_like(v)) for k, v in P.items()}
+    for step in range(3):
+        p1, p2 = _fwd(P, z, pre=f"b{step}_", isInC=False, isItC=True, ts1=0.5, ts2=0.07, isDR=False)
+        loss = O.loss_cls(p1, p2, T(z[f"b{step}_label"]).float(), T(z[f"b{step}_domain_id"]))
+        np.testing.assert_allclose(loss.detach().numpy(), z[f"loss_step{step}"], rtol=2e-5)
+        for v in P.values():
+            v.grad = None
+        loss.backward()
+        if step == 0:
+            for k in z:
+                if k.startswith("grad/"):
+                    g = z[k]
+                    np.testing.assert_allclose(P[k[5:]].grad.numpy(), g, rtol=1e-3, atol=1e-7 + 1e-4 * np.abs(g).max(),
+                                               err_msg=k)
+        with torch.no_grad():
+            for k, v in P.items():
+                O.adam_step(v, v.grad, st[k][0], st[k][1], step + 1, 5e-4)
+    for k in z:
+        if k.startswith("after3/"):
+            np.testing.assert_allclose(P[k[7:]].detach().numpy(), z[k], rtol=0, atol=3e-5, err_msg=k)
