@@ -46,6 +46,9 @@ class HeadTensors(C.Structure):
 P = c_void_p
 _SIGS = {
     "amid_version": (c_int32, []),
+    "amid_launch_count": (c_int64, []),
+    "amid_profile_enable": (c_int32, [c_int32]),
+    "amid_profile_report_host_sync": (c_int64, [C.c_char_p, c_int64]),
     "amid_emb_gather_fwd": (c_int32, [P, c_int64, P, c_int64, P, P]),
     "amid_gather_error_host_sync": (c_int32, []),
     "amid_seq_embed_fwd": (c_int32, [P, c_int64, P, P, P, c_int32, c_int32, P, P, POINTER(Dropout), P]),
@@ -111,3 +114,23 @@ def call(name: str, *args):
         raise AmidError(f"{name} failed ({rc}): {l.amid_last_error().decode()}")
     launches += 1
     return rc
+
+
+def kernel_launches() -> int:
+    """Kernels launched by libamid_b200.so so far in this process."""
+    return int(lib().amid_launch_count())
+
+
+def profile(on: bool) -> None:
+    lib().amid_profile_enable(1 if on else 0)
+
+
+def profile_report() -> dict:
+    """{kernel: (count, total_ms)} recorded since profile(True); synchronises the device."""
+    buf = C.create_string_buffer(1 << 16)
+    lib().amid_profile_report_host_sync(buf, len(buf))
+    out = {}
+    for line in buf.value.decode().splitlines():
+        name, cnt, ms = line.split()
+        out[name] = (int(cnt), float(ms))
+    return out

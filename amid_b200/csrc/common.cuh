@@ -20,8 +20,14 @@ int set_error(int code, const char* fmt, ...);
     do {                                                          \
         if (!(cond)) return ::amid::set_error(-1, __VA_ARGS__);   \
     } while (0)
+// every launch site: AMID_K(name, stream); kernel<<<...>>>(...); AMID_LAUNCH_CHECK(name);
+// counts the launch and, in profile mode, brackets it with CUDA events on its stream.
+void prof_begin(const char* name, cudaStream_t s);
+void prof_end();
+#define AMID_K(name, stream) ::amid::prof_begin(name, (cudaStream_t)(stream))
 #define AMID_LAUNCH_CHECK(name)                                                         \
     do {                                                                                \
+        ::amid::prof_end();                                                             \
         cudaError_t e__ = cudaGetLastError();                                           \
         if (e__ != cudaSuccess)                                                         \
             return ::amid::set_error(-2, "%s: launch failed: %s", name, cudaGetErrorString(e__)); \

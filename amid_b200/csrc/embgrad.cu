@@ -281,29 +281,37 @@ extern "C" int amid_embgrad_segreduce(const int64_t* ids, const float* grad_rows
     SegWs w = carve(workspace, n);
     AMID_REQUIRE((int64_t)w.total <= workspace_bytes, "embgrad_segreduce: workspace too small (%lld < %zu)",
                  (long long)workspace_bytes, w.total);
+    AMID_K("k_make_keys", s);
     k_make_keys<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(ids, n, w.keys_in, w.vals_in);
     AMID_LAUNCH_CHECK("k_make_keys");
     int end_bit = 1;
     while (end_bit < 32 && (1ull << end_bit) < (unsigned long long)V) ++end_bit;
     size_t tb = w.cub_bytes;
+    AMID_K("cub_radix_sort_pairs", s);
     cudaError_t e = cub::DeviceRadixSort::SortPairs(w.cub_tmp, tb, w.keys_in, w.keys_out, w.vals_in, w.vals_out, (int)n,
                                                     0, end_bit, s);
+    ::amid::prof_end();
     if (e != cudaSuccess) return set_error(-2, "embgrad: radix sort: %s", cudaGetErrorString(e));
+    AMID_K("cub_rle_scan", s);
     tb = w.cub_bytes;
     e = cub::DeviceRunLengthEncode::Encode(w.cub_tmp, tb, w.keys_out, w.ukeys, w.counts, n_uniq, (int)n, s);
     if (e != cudaSuccess) return set_error(-2, "embgrad: run-length encode: %s", cudaGetErrorString(e));
     tb = w.cub_bytes;
     e = cub::DeviceScan::ExclusiveSum(w.cub_tmp, tb, w.counts, w.offsets, (int)n, s);
+    ::amid::prof_end();
     if (e != cudaSuccess) return set_error(-2, "embgrad: scan: %s", cudaGetErrorString(e));
     e = cudaMemsetAsync(w.n_long, 0, 4, s);
     if (e != cudaSuccess) return set_error(-2, "embgrad: memset: %s", cudaGetErrorString(e));
     const unsigned blocks = (unsigned)((n * 32 + 255) / 256);
+    AMID_K("k_segreduce", s);
     k_segreduce<<<blocks, 256, 0, s>>>(grad_rows, w.vals_out, w.ukeys, w.counts, w.offsets, n_uniq, uniq_ids, uniq_grads,
                                        w.long_list, w.n_long);
     AMID_LAUNCH_CHECK("k_segreduce");
+    AMID_K("k_long_partial", s);
     k_long_partial<<<dim3(LONG_CHUNKS, MAX_LONG), 32, 0, s>>>(grad_rows, w.vals_out, w.counts, w.offsets, w.long_list,
                                                                w.n_long, w.lpart);
     AMID_LAUNCH_CHECK("k_long_partial");
+    AMID_K("k_long_final", s);
     k_long_final<<<MAX_LONG, 32, 0, s>>>(w.lpart, w.long_list, w.n_long, uniq_grads);
     AMID_LAUNCH_CHECK("k_long_final");
     return 0;
@@ -312,6 +320,7 @@ extern "C" int amid_embgrad_segreduce(const int64_t* ids, const float* grad_rows
 extern "C" int amid_embgrad_scatter_dense(const int64_t* uniq_ids, const float* uniq_grads, const int32_t* n_uniq,
                                           int64_t max_rows, float* dense, int64_t V, amid_stream_t s_) {
     AMID_REQUIRE(uniq_ids && uniq_grads && n_uniq && dense && max_rows > 0 && V > 0, "embgrad_scatter_dense: bad argument");
+    AMID_K("k_scatter_dense", (cudaStream_t)s_);
     k_scatter_dense<<<(unsigned)((max_rows * 32 + 255) / 256), 256, 0, (cudaStream_t)s_>>>(uniq_ids, uniq_grads, n_uniq,
                                                                                             dense, V);
     AMID_LAUNCH_CHECK("k_scatter_dense");
@@ -324,6 +333,7 @@ extern "C" int amid_adam_dense(float* p, const float* g, float* m, float* v, int
     AMID_REQUIRE(aligned16(p) && aligned16(g) && aligned16(m) && aligned16(v), "adam_dense: misaligned buffer");
     const AdamStep a = adam_consts(step, lr, beta1, beta2, eps);
     const int64_t n4 = (n + 3) / 4;
+    AMID_K("k_adam_dense", (cudaStream_t)s_);
     k_adam_dense<<<(unsigned)((n4 + 255) / 256), 256, 0, (cudaStream_t)s_>>>(p, g, m, v, n, a);
     AMID_LAUNCH_CHECK("k_adam_dense");
     return 0;
@@ -335,6 +345,7 @@ extern "C" int amid_adam_rows_lazy(float* table, float* m, float* v, int32_t* la
     AMID_REQUIRE(table && m && v && last_step && uniq_ids && uniq_grads && n_uniq && max_rows > 0 && step >= 1,
                  "adam_rows_lazy: bad argument");
     const AdamStep a = adam_consts(step, lr, beta1, beta2, eps);
+    AMID_K("k_adam_rows_lazy", (cudaStream_t)s_);
     k_adam_rows_lazy<<<(unsigned)((max_rows * 32 + 255) / 256), 256, 0, (cudaStream_t)s_>>>(
         table, m, v, last_step, uniq_ids, uniq_grads, n_uniq, step, lr, beta1, beta2, eps, a);
     AMID_LAUNCH_CHECK("k_adam_rows_lazy");
@@ -345,6 +356,7 @@ extern "C" int amid_adam_rows_flush(float* table, float* m, float* v, int32_t* l
                                     float lr, float beta1, float beta2, float eps, amid_stream_t s_) {
     AMID_REQUIRE(table && m && v && last_step && V > 0 && step >= 0, "adam_rows_flush: bad argument");
     if (step == 0) return 0;
+    AMID_K("k_adam_rows_flush", (cudaStream_t)s_);
     k_adam_rows_flush<<<(unsigned)((V * 32 + 255) / 256), 256, 0, (cudaStream_t)s_>>>(table, m, v, last_step, V, step,
                                                                                        lr, beta1, beta2, eps);
     AMID_LAUNCH_CHECK("k_adam_rows_flush");

@@ -756,6 +756,7 @@ extern "C" int amid_encoder_fwd(const amid_encoder_tensors* P, const float* x0, 
         tj.src[i * 6 + 4] = P->c1_w[i];
         tj.src[i * 6 + 5] = P->c2_w[i];
     }
+    AMID_K("k_transpose128", stream);
     k_transpose128<<<dim3(4, 4, 12), dim3(32, 8), 0, stream>>>(tj, wt);
     AMID_LAUNCH_CHECK("k_transpose128");
     if (int rc = ensure_smem((const void*)k_ln_qkv, ENC_SMEM_BYTES)) return rc;
@@ -766,13 +767,16 @@ extern "C" int amid_encoder_fwd(const amid_encoder_tensors* P, const float* x0, 
     const float* xin = x0;
     for (int i = 0; i < 2; ++i) {
         const float* W = wt + (size_t)i * 6 * D * D;
+        AMID_K("k_ln_qkv", stream);
         k_ln_qkv<<<tiles, NT, ENC_SMEM_BYTES, stream>>>(xin, M, P->ln1_w[i], P->ln1_b[i], W, W + D * D, W + 2 * D * D,
                                                         P->in_b[i], S->qn[i], S->st1[i], S->q[i], S->k[i], S->v[i]);
         AMID_LAUNCH_CHECK("k_ln_qkv");
+        AMID_K("k_attn_fwd", stream);
         k_attn_fwd<<<B * H, attn_threads, attn_smem, stream>>>(S->q[i], S->k[i], S->v[i], S->o[i], S->lse[i], L, dc,
                                                                dc.site_base + site_attn(i));
         AMID_LAUNCH_CHECK("k_attn_fwd");
         const bool last = i == 1;
+        AMID_K("k_proj_ffn", stream);
         k_proj_ffn<<<tiles, NT, ENC_SMEM_BYTES, stream>>>(
             S->o[i], S->qn[i], M, W + 3 * D * D, P->out_b[i], P->ln2_w[i], P->ln2_b[i], W + 4 * D * D, P->c1_b[i],
             W + 5 * D * D, P->c2_b[i], tmask, dc, dc.site_base + site_ffn1(i), dc.site_base + site_ffn2(i), S->x1[i],
@@ -834,28 +838,35 @@ extern "C" int amid_encoder_bwd(const amid_encoder_tensors* P, const float* x0, 
     const int attn_threads = (int)round_up((L + 1) / 2, 32);
 
     // last LayerNorm
+    AMID_K("k_ln_bwd", stream);
     k_ln_bwd<<<tiles, NT, 0, stream>>>(d_enc, S->xout[1], S->st3, P->ln3_w, M, dxa, lnp0);
     AMID_LAUNCH_CHECK("k_ln_bwd");
+    AMID_K("k_reduce_ln", stream);
     k_reduce_ln<<<1, 2 * D, 0, stream>>>(lnp0, tiles, G->ln3_w, G->ln3_b);
     AMID_LAUNCH_CHECK("k_reduce_ln");
 
     for (int i = 1; i >= 0; --i) {
         const float* xin = i == 0 ? x0 : S->xout[0];
         float* dxin = i == 0 ? dx0 : dxb;
+        AMID_K("k_ffn_bwd", stream);
         k_ffn_bwd<<<tiles, NT, ENC_SMEM_BYTES, stream>>>(dxa, S->h[i], S->x1[i], S->st2[i], tmask, M, P->c2_w[i],
                                                          P->c1_w[i], P->out_w[i], P->ln2_w[i], dc,
                                                          dc.site_base + site_ffn1(i), dc.site_base + site_ffn2(i), do2,
                                                          dhp, dx1, dO, lnp0);
         AMID_LAUNCH_CHECK("k_ffn_bwd");
+        AMID_K("k_reduce_ln", stream);
         k_reduce_ln<<<1, 2 * D, 0, stream>>>(lnp0, tiles, G->ln2_w[i], G->ln2_b[i]);
         AMID_LAUNCH_CHECK("k_reduce_ln");
+        AMID_K("k_attn_bwd", stream);
         k_attn_bwd<<<B * H, attn_threads, attn_smem, stream>>>(S->q[i], S->k[i], S->v[i], S->o[i], S->lse[i], dO, dq, dk,
                                                                dv, L, dc, dc.site_base + site_attn(i));
         AMID_LAUNCH_CHECK("k_attn_bwd");
+        AMID_K("k_qkv_bwd", stream);
         k_qkv_bwd<<<tiles, NT, ENC_SMEM_BYTES, stream>>>(dq, dk, dv, dx1, xin, S->st1[i], M, P->in_w[i],
                                                          P->in_w[i] + D * D, P->in_w[i] + 2 * D * D, P->ln1_w[i], dxin,
                                                          lnp1);
         AMID_LAUNCH_CHECK("k_qkv_bwd");
+        AMID_K("k_reduce_ln", stream);
         k_reduce_ln<<<1, 2 * D, 0, stream>>>(lnp1, tiles, G->ln1_w[i], G->ln1_b[i]);
         AMID_LAUNCH_CHECK("k_reduce_ln");
         // weight gradients of the block, one launch: W2, W1, Wo, Wq, Wk, Wv
@@ -866,6 +877,7 @@ extern "C" int amid_encoder_bwd(const amid_encoder_tensors* P, const float* x0, 
         wj.dY[3] = dq;  wj.X[3] = S->qn[i];
         wj.dY[4] = dk;  wj.X[4] = xin;
         wj.dY[5] = dv;  wj.X[5] = xin;
+        AMID_K("k_wgrad", stream);
         k_wgrad<<<dim3(SW, 6), NT, WG_SMEM_BYTES, stream>>>(wj, M, rp, wpart, bpart);
         AMID_LAUNCH_CHECK("k_wgrad");
         ReduceJobs rw, rb;
@@ -875,8 +887,10 @@ extern "C" int amid_encoder_bwd(const amid_encoder_tensors* P, const float* x0, 
         rw.out[3] = G->in_w[i]; rb.out[3] = G->in_b[i];
         rw.out[4] = G->in_w[i] + D * D; rb.out[4] = G->in_b[i] + D;
         rw.out[5] = G->in_w[i] + 2 * D * D; rb.out[5] = G->in_b[i] + 2 * D;
+        AMID_K("k_reduce_partials", stream);
         k_reduce_partials<<<dim3(D * D / 256, 6), 256, 0, stream>>>(wpart, SW, D * D, rw);
         AMID_LAUNCH_CHECK("k_reduce_partials(w)");
+        AMID_K("k_reduce_partials", stream);
         k_reduce_partials<<<dim3(1, 6), 128, 0, stream>>>(bpart, SW, D, rb);
         AMID_LAUNCH_CHECK("k_reduce_partials(b)");
         // the input gradient of block 1 is the output gradient of block 0

@@ -161,6 +161,7 @@ extern "C" int amid_emb_gather_fwd(const float* table, int64_t V, const int64_t*
     AMID_REQUIRE(err, "emb_gather_fwd: cannot allocate error flag");
     const int64_t warps = (n_rows + ROWS_PER_WARP - 1) / ROWS_PER_WARP;
     const int64_t blocks = (warps + 7) / 8;
+    AMID_K("k_gather", stream);
     k_gather<<<(unsigned)blocks, 256, 0, stream>>>(table, ids, n_rows, V, out, err);
     AMID_LAUNCH_CHECK("k_gather");
     return 0;
@@ -191,10 +192,13 @@ extern "C" int amid_seq_embed_fwd(const float* table, int64_t V, const int64_t* 
     const int64_t warps = (n_rows + ROWS_PER_WARP - 1) / ROWS_PER_WARP;
     const unsigned blocks = (unsigned)((warps + 7) / 8);
     const DropCfg dc = make_drop(drop);
-    if (ids)
+    if (ids) {
+        AMID_K("k_seq_embed", stream);
         k_seq_embed<true><<<blocks, 256, 0, stream>>>(table, ids, nullptr, pos, n_rows, L, V, x0, tmask, dc, err);
-    else
+    } else {
+        AMID_K("k_seq_embed", stream);
         k_seq_embed<false><<<blocks, 256, 0, stream>>>(nullptr, nullptr, rows, pos, n_rows, L, V, x0, tmask, dc, err);
+    }
     AMID_LAUNCH_CHECK("k_seq_embed");
     return 0;
 }
@@ -205,6 +209,7 @@ extern "C" int amid_seq_embed_bwd(float* dx0, const uint32_t* tmask, int32_t B, 
     AMID_REQUIRE(dx0 && tmask && dpos, "seq_embed_bwd: null argument");
     AMID_REQUIRE(B > 0 && L > 0, "seq_embed_bwd: B=%d L=%d", B, L);
     const DropCfg dc = make_drop(drop);
+    AMID_K("k_seq_embed_bwd", stream);
     k_seq_embed_bwd<<<L, 256, 0, stream>>>(dx0, tmask, B, L, dpos, dc);
     AMID_LAUNCH_CHECK("k_seq_embed_bwd");
     return 0;
@@ -214,6 +219,7 @@ extern "C" int amid_dropout_mask_feature(const amid_dropout* drop, uint32_t site
                                          amid_stream_t stream_) {
     const DropCfg dc = make_drop(drop);
     const int64_t n = rows * D;
+    AMID_K("k_mask_feature", (cudaStream_t)stream_);
     k_mask_feature<<<(unsigned)((n / 4 + 255) / 256 + 1), 256, 0, (cudaStream_t)stream_>>>(dc, site, n, out);
     AMID_LAUNCH_CHECK("k_mask_feature");
     return 0;
@@ -222,6 +228,7 @@ extern "C" int amid_dropout_mask_attn(const amid_dropout* drop, uint32_t site, i
                                       amid_stream_t stream_) {
     const DropCfg dc = make_drop(drop);
     const int64_t n = (int64_t)B * H * L * L;
+    AMID_K("k_mask_attn", (cudaStream_t)stream_);
     k_mask_attn<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream_>>>(dc, site, (int64_t)B * H, L, out);
     AMID_LAUNCH_CHECK("k_mask_attn");
     return 0;

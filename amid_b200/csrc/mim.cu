@@ -321,6 +321,7 @@ extern "C" int amid_mim_scores(const float* a, const float* b, int32_t B, int32_
     AMID_REQUIRE(aligned16(a) && aligned16(b), "mim_scores: misaligned buffer");
     cudaError_t e = cudaFuncSetAttribute((const void*)k_mim_scores, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MIM_SMEM);
     if (e != cudaSuccess) return set_error(-3, "mim_scores: smem attribute: %s", cudaGetErrorString(e));
+    AMID_K("k_mim_scores", (cudaStream_t)s_);
     k_mim_scores<<<B, 256, MIM_SMEM, (cudaStream_t)s_>>>(a, b, n, m);
     AMID_LAUNCH_CHECK("k_mim_scores");
     return 0;
@@ -329,6 +330,7 @@ extern "C" int amid_mim_scores(const float* a, const float* b, int32_t B, int32_
 extern "C" int amid_mim_gate(const float* m, const float* w_bs, int32_t Bg, float ts, float* p, float* gate, float* coef,
                              int32_t* active, int32_t* n_active, float* scal, amid_stream_t s_) {
     AMID_REQUIRE(m && w_bs && p && gate && coef && active && n_active && scal && Bg > 0, "mim_gate: bad argument");
+    AMID_K("k_mim_gate", (cudaStream_t)s_);
     k_mim_gate<<<1, 1024, 0, (cudaStream_t)s_>>>(m, w_bs, Bg, ts, p, gate, coef, active, n_active, scal);
     AMID_LAUNCH_CHECK("k_mim_gate");
     return 0;
@@ -338,6 +340,7 @@ extern "C" int amid_mim_aggregate(const float* other, const float* coef, const i
                                   int32_t j0, int32_t Bl, int32_t n, float* Ssum, amid_stream_t s_) {
     AMID_REQUIRE(other && coef && active && n_active && Ssum && n > 0 && Bl > 0, "mim_aggregate: bad argument");
     const int total4 = n * D / 4;
+    AMID_K("k_mim_aggregate", (cudaStream_t)s_);
     k_mim_aggregate<<<(total4 + 127) / 128, 128, 0, (cudaStream_t)s_>>>(other, coef, active, n_active, j0, Bl, n, Ssum);
     AMID_LAUNCH_CHECK("k_mim_aggregate");
     return 0;
@@ -346,9 +349,11 @@ extern "C" int amid_mim_aggregate(const float* other, const float* coef, const i
 extern "C" int amid_mim_project(const float* Ssum, const float* w_nn, const float* b_nn, const float* b_bs,
                                 const float* scal, int32_t n, float* E, float* esum, amid_stream_t s_) {
     AMID_REQUIRE(Ssum && w_nn && b_nn && b_bs && scal && E && n > 0, "mim_project: bad argument");
+    AMID_K("k_mim_project", (cudaStream_t)s_);
     k_mim_project<<<n, 128, 0, (cudaStream_t)s_>>>(Ssum, w_nn, b_nn, b_bs, scal, E);
     AMID_LAUNCH_CHECK("k_mim_project");
     if (esum) {
+        AMID_K("k_colsum", (cudaStream_t)s_);
         k_colsum<<<1, 128, 0, (cudaStream_t)s_>>>(E, n, esum);
         AMID_LAUNCH_CHECK("k_colsum");
     }
@@ -358,6 +363,7 @@ extern "C" int amid_mim_project(const float* Ssum, const float* w_nn, const floa
 extern "C" int amid_mim_concat(const float* self_, const float* E, int32_t B, int32_t n, float* out, amid_stream_t s_) {
     AMID_REQUIRE(self_ && E && out && B > 0 && n > 0, "mim_concat: bad argument");
     const int64_t total4 = (int64_t)B * 2 * n * D / 4;
+    AMID_K("k_mim_concat", (cudaStream_t)s_);
     k_mim_concat<<<(unsigned)((total4 + 255) / 256), 256, 0, (cudaStream_t)s_>>>(self_, E, B, n, out);
     AMID_LAUNCH_CHECK("k_mim_concat");
     return 0;
@@ -372,10 +378,13 @@ extern "C" int amid_mim_bwd(const float* dE, const float* Ssum, const float* oth
                  "mim_bwd: null argument");
     AMID_REQUIRE(Bl > 0 && n > 0, "mim_bwd: Bl=%d n=%d", Bl, n);
     cudaStream_t s = (cudaStream_t)s_;
+    AMID_K("k_mim_dS", s);
     k_mim_dS<<<n, 128, 0, s>>>(dE, w_nn, ws_dS);
     AMID_LAUNCH_CHECK("k_mim_dS");
+    AMID_K("k_mim_dW", s);
     k_mim_dW<<<D, 128, 0, s>>>(dE, Ssum, scal, n, dW_nn, db_nn, db_bs);
     AMID_LAUNCH_CHECK("k_mim_dW");
+    AMID_K("k_mim_dsample", s);
     k_mim_dsample<<<Bl, 256, 0, s>>>(ws_dS, dE, other, b_nn, coef, gate, j0, n, d_other ? 1 : 0, dw_bs, d_other);
     AMID_LAUNCH_CHECK("k_mim_dsample");
     return 0;
@@ -384,6 +393,7 @@ extern "C" int amid_mim_bwd(const float* dE, const float* Ssum, const float* oth
 extern "C" int amid_meanpool_fwd(const float* enc, const float* esum, int32_t B, int32_t n, float denom, float* u,
                                  amid_stream_t s_) {
     AMID_REQUIRE(enc && u && B > 0 && n > 0 && denom > 0.f, "meanpool_fwd: bad argument");
+    AMID_K("k_meanpool_fwd", (cudaStream_t)s_);
     k_meanpool_fwd<<<B, 128, 0, (cudaStream_t)s_>>>(enc, esum, n, 1.0f / denom, u);
     AMID_LAUNCH_CHECK("k_meanpool_fwd");
     return 0;
@@ -395,10 +405,12 @@ extern "C" int amid_meanpool_bwd(const float* du, int32_t B, int32_t n, float de
     cudaStream_t s = (cudaStream_t)s_;
     if (d_enc) {
         const int64_t total4 = (int64_t)B * n * (D / 4);
+        AMID_K("k_meanpool_bwd", s);
         k_meanpool_bwd<<<(unsigned)((total4 + 255) / 256), 256, 0, s>>>(du, B, n, 1.0f / denom, accumulate, d_enc);
         AMID_LAUNCH_CHECK("k_meanpool_bwd");
     }
     if (dcol) {
+        AMID_K("k_du_colsum", s);
         k_du_colsum<<<1, 128, 0, s>>>(du, B, 1.0f / denom, dcol);
         AMID_LAUNCH_CHECK("k_du_colsum");
     }

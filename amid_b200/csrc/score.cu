@@ -12,6 +12,8 @@ namespace amid {
 constexpr int MAXH = 3;      // heads: predictModule, predict_ips, predict_gfunc
 constexpr int MAXHID = 64;
 
+__host__ __device__ inline int pad4(int x) { return (x + 3) & ~3; }   // keep float4 smem views 16B aligned
+
 struct HeadPtrs {
     const float* w0[MAXH];
     const float* b0[MAXH];
@@ -26,7 +28,7 @@ k_score_fwd(const float* __restrict__ u1, const float* __restrict__ u2, const fl
     extern __shared__ __align__(16) float smem[];
     float* WiT = smem;
     float* A = WiT + nh * D * hid;
-    float* U = A + nh * 2 * hid;
+    float* U = A + pad4(nh * 2 * hid);
     float* IT = U + 2 * D;
     const int b = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
     for (int idx = t; idx < nh * hid * D; idx += 128) {   // transpose the item half into smem
@@ -88,11 +90,11 @@ k_score_bwd(const float* __restrict__ u1, const float* __restrict__ u2, const fl
     extern __shared__ __align__(16) float smem[];
     const int HG = head_grad_floats(hid);
     float* G = smem;                        // [nh][HG] gradient accumulators
-    float* A = G + nh * HG;                 // [nh][2][hid]
-    float* dA = A + nh * 2 * hid;           // [nh][2][hid]
-    float* dBc = dA + nh * 2 * hid;         // [nh][hid]
-    float* PRE = dBc + nh * hid;            // [nh][hid] Bc of the current candidate
-    float* U = PRE + nh * hid;              // [2][128]
+    float* A = G + pad4(nh * HG);           // [nh][2][hid]
+    float* dA = A + pad4(nh * 2 * hid);     // [nh][2][hid]
+    float* dBc = dA + pad4(nh * 2 * hid);   // [nh][hid]
+    float* PRE = dBc + pad4(nh * hid);      // [nh][hid] Bc of the current candidate
+    float* U = PRE + pad4(nh * hid);        // [2][128]
     float* IT = U + 2 * D;                  // [128]
     float* DZ = IT + D;                     // [nh][2]
     const int t = threadIdx.x;
@@ -320,9 +322,10 @@ extern "C" int amid_score_fwd(const float* u1, const float* u2, const float* ite
     AMID_REQUIRE(aligned16(items) && aligned16(u1) && aligned16(u2), "score_fwd: misaligned buffer");
     HeadPtrs hp{};
     if (int rc = fill_heads(heads, nh, &hp)) return rc;
-    const size_t smem = (size_t)(nh * D * hid + nh * 2 * hid + 2 * D + 4 * D) * sizeof(float);
+    const size_t smem = (size_t)(nh * D * hid + pad4(nh * 2 * hid) + 2 * D + 4 * D) * sizeof(float);
     cudaError_t e = cudaFuncSetAttribute((const void*)k_score_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return set_error(-3, "score_fwd: smem attribute: %s", cudaGetErrorString(e));
+    AMID_K("k_score_fwd", (cudaStream_t)s_);
     k_score_fwd<<<B, 128, smem, (cudaStream_t)s_>>>(u1, u2, items, hp, nh, hid, B, C, probs);
     AMID_LAUNCH_CHECK("k_score_fwd");
     return 0;
@@ -345,10 +348,11 @@ extern "C" int amid_score_bwd(const float* u1, const float* u2, const float* ite
     if (int rc = fill_heads(heads, nh, &hp)) return rc;
     const int HG = head_grad_floats(hid);
     const int groups = (B + SB - 1) / SB;
-    const size_t smem = (size_t)(nh * HG + 2 * nh * 2 * hid + 2 * nh * hid + 2 * D + D + nh * 2 + 8) * sizeof(float);
+    const size_t smem = (size_t)(pad4(nh * HG) + 2 * pad4(nh * 2 * hid) + 2 * pad4(nh * hid) + 2 * D + D + nh * 2 + 8) * sizeof(float);
     cudaError_t e = cudaFuncSetAttribute((const void*)k_score_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return set_error(-3, "score_bwd: smem attribute: %s", cudaGetErrorString(e));
     cudaStream_t s = (cudaStream_t)s_;
+    AMID_K("k_score_bwd", s);
     k_score_bwd<<<groups, 256, smem, s>>>(u1, u2, items, hp, nh, hid, B, C, probs, dprobs, du1, du2, ditems,
                                           (float*)workspace);
     AMID_LAUNCH_CHECK("k_score_bwd");
@@ -357,6 +361,7 @@ extern "C" int amid_score_bwd(const float* u1, const float* u2, const float* ite
         AMID_REQUIRE(G[i].w0 && G[i].b0 && G[i].w2 && G[i].b2, "score_bwd: grad head %d has null tensors", i);
         gp.w0[i] = G[i].w0; gp.b0[i] = G[i].b0; gp.w2[i] = G[i].w2; gp.b2[i] = G[i].b2;
     }
+    AMID_K("k_score_reduce", s);
     k_score_reduce<<<(nh * HG + 255) / 256, 256, 0, s>>>((const float*)workspace, groups, nh, hid, gp);
     AMID_LAUNCH_CHECK("k_score_reduce");
     return 0;
@@ -370,6 +375,7 @@ extern "C" int amid_loss_fwd_bwd(const float* probs, int32_t nh, int32_t B, int3
     AMID_REQUIRE(nh == 1 || nh == 3, "loss: n_heads=%d must be 1 or 3", nh);
     AMID_REQUIRE(mode == 0 || nh == 3, "loss: the doubly-robust losses need the 3 isDR heads");
     AMID_REQUIRE(mode != 2 || ob_label, "loss: mode 2 needs ob_label");
+    AMID_K("k_loss", (cudaStream_t)s_);
     k_loss<<<1, 1024, 0, (cudaStream_t)s_>>>(probs, nh, B, C, labels, domain_id, ob_label, mode, dr_e_w, inv_count,
                                              losses, dprobs);
     AMID_LAUNCH_CHECK("k_loss");
@@ -380,6 +386,7 @@ extern "C" int amid_rank_counts(const float* scores, int64_t N, int32_t C, float
                                 int32_t* n_equal, amid_stream_t s_) {
     AMID_REQUIRE(scores && n_greater && n_equal && N >= 0 && C >= 1, "rank_counts: bad argument");
     if (N == 0) return 0;
+    AMID_K("k_rank_counts", (cudaStream_t)s_);
     k_rank_counts<<<(unsigned)((N * 32 + 255) / 256), 256, 0, (cudaStream_t)s_>>>(scores, N, C, fix, n_greater, n_equal);
     AMID_LAUNCH_CHECK("k_rank_counts");
     return 0;

@@ -23,6 +23,15 @@ TABLE = "item_emb_layer.emb_item.weight"
 BATCH_KEYS = ("i_node", "neg_samples", "seq_d1", "seq_d2", "domain_id", "label")
 
 
+def pad_for_exchange(uid: torch.Tensor, ug: torch.Tensor, nu: torch.Tensor, V: int):
+    """Fixed-size (row id, gradient row) list for the all-gather: slots past n_uniq get the
+    sentinel id V-1 with a zero row, which a dense Adam would also step with zero gradient."""
+    valid = torch.arange(uid.numel(), device=uid.device) < nu.to(torch.int64)
+    uid = torch.where(valid, uid, torch.full_like(uid, V - 1))
+    ug = torch.where(valid.unsqueeze(1), ug, torch.zeros_like(ug))
+    return uid, ug
+
+
 class _AdamState:
     def __init__(self, flat_numel: int, V: int, dev):
         z = lambda *s: torch.zeros(*s, device=dev, dtype=torch.float32)
@@ -140,9 +149,7 @@ class Trainer:
         order, so every replica applies the identical update."""
         n = uid.numel()
         dev = ug.device
-        valid = torch.arange(n, device=dev) < nu.to(torch.int64)
-        uid = torch.where(valid, uid, torch.full_like(uid, self.V - 1))
-        ug = torch.where(valid.unsqueeze(1), ug, torch.zeros_like(ug))
+        uid, ug = pad_for_exchange(uid, ug, nu, self.V)
         all_ids = torch.empty(n * self.world, device=dev, dtype=torch.int64)
         all_rows = torch.empty(n * self.world, D, device=dev, dtype=torch.float32)
         self.dist.all_gather_into(all_ids, uid)

@@ -145,7 +145,7 @@ def _mim_forward(P, name: str, m_global: torch.Tensor, other: torch.Tensor, n: i
     that gets aggregated (seq_d2 features for itc_d1, model_seq.py:483-497)."""
     dev = other.device
     Bg = m_global.numel()
-    Bl = other.shape[0]
+    Bl = other.numel() // (n * D)
     w_bs = P[name + ".trans_bs.weight"]
     if w_bs.numel() != Bg:
         raise _abi.AmidError(f"{name}: batch {Bg} != bs {w_bs.numel()} baked into trans_bs (model_seq.py:480); "
@@ -172,7 +172,7 @@ def _mim_forward(P, name: str, m_global: torch.Tensor, other: torch.Tensor, n: i
 
 
 def _mim_scores(a: torch.Tensor, b: torch.Tensor, n: int, dist: Optional[DistCtx]) -> torch.Tensor:
-    Bl = a.shape[0]
+    Bl = a.numel() // (n * D)
     m = torch.empty(Bl, device=a.device, dtype=torch.float32)
     call("amid_mim_scores", _ptr(a), _ptr(b), Bl, n, _ptr(m), _stream())
     if dist is not None and dist.world > 1:
@@ -184,7 +184,7 @@ def _mim_scores(a: torch.Tensor, b: torch.Tensor, n: int, dist: Optional[DistCtx
 
 def _mim_backward(P, G, st: _Mim, dE: torch.Tensor, d_other: torch.Tensor, j0: int, dist: Optional[DistCtx]):
     dev = dE.device
-    Bl = st.other.shape[0]
+    Bl = st.other.numel() // (st.n * D)
     ws = torch.empty(st.n, D, device=dev, dtype=torch.float32)
     dw_bs_local = torch.empty(Bl, device=dev, dtype=torch.float32)
     call("amid_mim_bwd", _ptr(dE), _ptr(st.Ssum), _ptr(st.other), _ptr(P[st.name + ".trans_nn.weight"]),

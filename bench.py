@@ -1,0 +1,333 @@
+"""bench.py -- training throughput of the AMID SASRec hot path on B200 (BASELINE.json metric
+"train seqs/sec at 1/2/4/8 B200").
+
+    python bench.py --gpus N --steps K --warmup W            # this repo (one process per GPU under torchrun)
+    python bench.py --impl reference --steps K --warmup W    # the reference path's CPU port on the host cores
+
+A "step" is one full training step of train_sr.py:201-215 on one synthetic batch of the C3
+shape: forward, domain-masked BCE, backward, embedding-gradient
+reduction and Adam on every parameter.  `value` = global sequences / second with the batch
+already resident in HBM; `e2e` = the same through the public `Trainer` API with the batch in
+pinned HOST memory (H2D every step, loss read back every step).  Prints ONE JSON line.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "tests", "golden")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+V_ITEMS = 894820          # train_sr.py:450,456  item_length * 2
+D, HID = 128, 32
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=1024, help="per-GPU batch (weak scaling)")
+    ap.add_argument("--seq-len", type=int, default=200)
+    ap.add_argument("--neg", type=int, default=1, help="negatives per row in training (dataset_seq.py:197-199)")
+    ap.add_argument("--dr", action="store_true", help="isDR=True, phase-1 loss (train_sr_dr.py config)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-sample", type=int, default=32, help="sequences per CPU-baseline step (bounded sample)")
+    ap.add_argument("--dense-table", action="store_true", help="dense Adam over the whole table (reference-style)")
+    return ap.parse_args()
+
+
+def workload_name(a):
+    return (f"C3 synthetic train step: per-GPU batch {a.batch}, L={a.seq_len}, d={D}, hid={HID}, C={1 + a.neg}, "
+            f"V={V_ITEMS}, SASRec+ItC(ts2=0.4){'+DR' if a.dr else ''}, dropout 0.5, uniform ids (roofline variant), "
+            f"exact-fp32 path")
+
+
+def synth_batch(rng, B, L, C, V):
+    """Uniform-random ids over [0,V), no padding (SURVEY.md section 8d roofline variant)."""
+    return {
+        "i_node": torch.from_numpy(rng.integers(0, V, B)),
+        "neg_samples": torch.from_numpy(rng.integers(0, V, (B, C - 1))),
+        "seq_d1": torch.from_numpy(rng.integers(0, V, (B, L))),
+        "seq_d2": torch.from_numpy(rng.integers(0, V, (B, L))),
+        "domain_id": torch.from_numpy(rng.integers(0, 2, B)),
+        "ob_label": torch.from_numpy(rng.integers(0, 2, B)),
+        "label": torch.cat((torch.ones(B, 1), torch.zeros(B, C - 1)), 1),
+    }
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference path + torch.optim.Adam, on the host cores
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_steps(a, steps, warmup, sample):
+    """Times `steps` CPU train steps on `sample` sequences of the workload; returns seq/s."""
+    from common import make_keep_masks, make_params
+    from oracle import amid_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    L, C = a.seq_len, 1 + a.neg
+    rng = np.random.default_rng(1234)
+    P = {k: v.requires_grad_(True) for k, v in make_params(7, V_ITEMS, D, L, HID, sample, isDR=a.dr).items()}
+    opt = torch.optim.Adam(list(P.values()), lr=5e-4)              # train_sr.py:480
+    times = []
+    for it in range(warmup + steps):
+        b = synth_batch(rng, sample, L, C, V_ITEMS)
+        t0 = time.perf_counter()
+        masks = make_keep_masks(it, sample, L, D)                   # F.dropout's Bernoulli draws
+        outs = O.sasrec_forward(P, b["i_node"], b["neg_samples"], b["seq_d1"], b["seq_d2"], isInC=False, isItC=True,
+                                ts1=0.5, ts2=0.4, isDR=a.dr, masks=masks, closed_form=True)
+        loss = O.loss_cls(outs[0], outs[1], b["label"], b["domain_id"])
+        if a.dr:
+            loss = loss + 0.01 * O.loss_dr_e(*outs, b["label"], b["domain_id"])
+        opt.zero_grad()
+        loss.backward()
+        opt.step()                                                   # dense Adam over the [V,128] table too
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+    ms = 1e3 * float(np.mean(times))
+    return sample / (ms / 1e3), ms, cores
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    value, ms, cores = cpu_reference_steps(a, a.steps, a.warmup, a.cpu_sample)
+    sample = (f"{a.cpu_sample} sequences per step of the same workload (L={a.seq_len}); oracle port of the reference "
+              f"path + torch.optim.Adam (dense table), closed-form ItC (the literal [bs,bs,n,n] ItC needs 275 GB here)")
+    line = {
+        "impl": "reference", "metric": "train_seqs_per_sec", "value": value, "unit": "seq/s", "n_gpus": a.gpus,
+        "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": {"workload": workload_name(a)},
+        "cpu_baseline": {"value": value, "unit": "seq/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "seq/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks sampler (B200_PROFILING.md "clocks DURING the timed region")
+# ------------------------------------------------------------------------------------------------
+class Clocks:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc = index, None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            out = self.proc.communicate(timeout=5)[0]
+        except Exception:
+            out = ""
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in out.splitlines():
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return {"hbm": p["hbm_gbs"], "tensor": p.get("bf16_tflops_sustained", p["bf16_tflops"]), "src": "measured"}
+    return {"hbm": 6650.0, "tensor": 1400.0, "src": "fallback"}
+
+
+def kernel_work(name, B, L, C):
+    """ALGORITHMIC work of ONE launch of a kernel at this workload: (kind, amount) in FLOP or bytes
+    (DESIGN.md section 'Kernels').  M = B*L tokens."""
+    M = B * L
+    gemm = 2.0 * M * D * D                      # one [M,128]x[128,128] contraction
+    attn_full = 4.0 * B * L * L * D             # q k^T and P v over the full square, all 8 heads
+    rows_seq, rows_items = M, B * C
+    table = {
+        "k_ln_qkv": ("flop", 3 * gemm), "k_proj_ffn": ("flop", 3 * gemm), "k_ffn_bwd": ("flop", 3 * gemm),
+        "k_qkv_bwd": ("flop", 3 * gemm), "k_wgrad": ("flop", 6 * gemm),
+        "k_attn_fwd": ("flop", attn_full), "k_attn_bwd": ("flop", 2.5 * attn_full),
+        "k_seq_embed": ("byte", rows_seq * (2 * D * 4 + 8)), "k_gather": ("byte", rows_items * (2 * D * 4 + 8)),
+        "k_mim_scores": ("flop", 2.0 * B * L * L * D),
+    }
+    return table.get(name)
+
+
+def run_ours(a):
+    from amid_b200 import _abi
+    from amid_b200.engine import Trainer
+    from amid_b200.hotpath import DistCtx
+    from amid_b200.model_seq import SASRec
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the amid_b200 hot path has no CPU fallback "
+                         "(use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dctx = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        dctx = DistCtx()
+    B, L, C = a.batch, a.seq_len, 1 + a.neg
+    Bg = B * world
+    torch.manual_seed(0)
+    model = SASRec(user_length=0, user_emb_dim=D, item_length=V_ITEMS, item_emb_dim=D, seq_len=L, hid_dim=HID, bs=Bg,
+                   isInC=False, isItC=True, threshold1=0.5, threshold2=0.4, isDR=a.dr).cuda().train()
+    tr = Trainer(model, lr=5e-4, dist=dctx, sparse_table=not a.dense_table)
+    rng = np.random.default_rng(100 + rank)
+    n_pool = 4
+    host = [{k: v.pin_memory() for k, v in synth_batch(rng, B, L, C, V_ITEMS).items()} for _ in range(n_pool)]
+    devb = [tr.to_device(h) for h in host]
+    torch.cuda.synchronize()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, n):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(n):
+            fn(i)
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    dev_step = lambda i: tr.step(devb[i % n_pool])
+
+    def host_step(i):
+        losses = tr.step(tr.to_device(host[i % n_pool]))
+        return losses.cpu()                          # D2H of the step's loss
+
+    for i in range(a.warmup):
+        dev_step(i)
+    clocks = Clocks(local)
+    if rank == 0:
+        clocks.start()
+    l0 = _abi.kernel_launches()
+    ms_total = timed(dev_step, a.steps)
+    launches = _abi.kernel_launches() - l0
+    clk = clocks.stop() if rank == 0 else None
+    for i in range(2):
+        host_step(i)
+    ms_e2e = timed(host_step, a.steps)
+    h2d = sum(v.numel() * (4 if k == "label" else 8) for k, v in host[0].items())
+
+    # per-kernel CUDA-event profile of 3 more steps of the same workload (rank 0 reports)
+    _abi.profile(True)
+    prof_steps = 3
+    for i in range(prof_steps):
+        dev_step(i)
+    rep = _abi.profile_report()
+    _abi.profile(False)
+    final_loss = float(tr.last_losses[0].item())
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    pk = peaks()
+    ms_step = ms_total / a.steps
+    tot = sum(ms for _, ms in rep.values()) or 1.0
+    breakdown = []
+    for name, (cnt, ms) in sorted(rep.items(), key=lambda kv: -kv[1][1]):
+        ent = {"kernel": name, "launches_per_step": cnt / prof_steps, "ms_per_step": ms / prof_steps,
+               "share": ms / tot}
+        w = kernel_work(name, B, L, C)
+        if w:
+            per_launch_s = (ms / cnt) / 1e3
+            if w[0] == "flop":
+                ent.update(bound="tensor", achieved=w[1] / per_launch_s / 1e12, unit="TFLOP/s")
+                ent["frac"] = ent["achieved"] / pk["tensor"]
+            else:
+                ent.update(bound="hbm", achieved=w[1] / per_launch_s / 1e9, unit="GB/s")
+                ent["frac"] = ent["achieved"] / pk["hbm"]
+        breakdown.append(ent)
+    dom = next((e for e in breakdown if "bound" in e), None)
+    roofline = None
+    if dom:
+        roofline = {"kernel": dom["kernel"], "bound": dom["bound"], "achieved": dom["achieved"],
+                    "peak": pk["tensor"] if dom["bound"] == "tensor" else pk["hbm"], "unit": dom["unit"],
+                    "frac": dom["frac"], "traffic": None, "peak_source": pk["src"], "share_of_step": dom["share"]}
+    gat = next((e for e in breakdown if e["kernel"] == "k_seq_embed"), None)
+    line = {
+        "metric": "train_seqs_per_sec", "value": Bg / (ms_step / 1e3), "unit": "seq/s", "n_gpus": world,
+        "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(a), "global_batch": Bg, "seq_len": L, "parallelism": f"dp{world}",
+                   "l2": "no explicit flush: each step streams ~8 GB of activations, far larger than the 126 MB L2",
+                   "table_update": "dense" if a.dense_table else "row-sparse lazy Adam (exact dense semantics)"},
+        "clocks": clk,
+        "e2e": {"value": Bg / (ms_e2e / a.steps / 1e3), "unit": "seq/s", "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": 12, "ms_per_step": ms_e2e / a.steps},
+        "gpu_launches": launches,
+        "roofline": roofline,
+        "roofline_gather": None if gat is None else {"kernel": "k_seq_embed", "bound": "hbm", "achieved": gat["achieved"],
+                                                     "peak": pk["hbm"], "unit": "GB/s", "frac": gat["frac"],
+                                                     "traffic": None, "peak_source": pk["src"]},
+        "kernel_breakdown": breakdown[:12],
+        "final_loss": final_loss,
+    }
+    if world == 1 and not a.no_cpu_baseline:
+        try:
+            v, ms, cores = cpu_reference_steps(a, 2, 1, a.cpu_sample)
+            line["cpu_baseline"] = {"value": v, "unit": "seq/s", "cores": cores, "kind": "port", "ms_per_step": ms,
+                                    "sample": f"{a.cpu_sample} sequences per step of the same workload, 1 warm-up + 2 "
+                                              f"timed steps; oracle port + torch.optim.Adam, closed-form ItC"}
+        except Exception as e:  # the baseline is reported beside the number, never a reason to lose it
+            line["cpu_baseline"] = {"value": None, "unit": "seq/s", "cores": os.cpu_count(), "kind": "port",
+                                    "sample": f"failed: {e!r}"}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)

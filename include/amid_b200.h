@@ -77,6 +77,12 @@ typedef struct {
 
 const char* amid_last_error(void);
 int amid_version(void);
+/* number of kernels this library has launched in this process (bench.py's gpu_launches) */
+int64_t amid_launch_count(void);
+/* optional per-kernel CUDA-event profiler: enable(1) starts recording every launch on its
+ * own stream, report() synchronises and writes "kernel count total_ms" lines. */
+int amid_profile_enable(int32_t on);
+int64_t amid_profile_report_host_sync(char* buf, int64_t cap);
 
 /* ---- a1: embItemLayerEnhance.forward (model_seq.py:27-29, calls :418-421) ---------- */
 /* out[r,:] = table[ids[r],:]  for r < n_rows.  Bit-exact copy. */

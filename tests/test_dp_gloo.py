@@ -1,0 +1,111 @@
+"""world_size-2 gloo tests (CPU) of the data-parallel decomposition used by amid_b200.hotpath /
+engine: batch-sharded MIM exchange and the table-gradient exchange.
+The per-rank arithmetic is done with the oracle (checker only); what is under test is the
+host-side sharding algebra and the DistCtx collectives."""
+import os
+import socket
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from common import make_params
+from oracle import amid_oracle as O
+
+D = 128
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from amid_b200.engine import pad_for_exchange
+        from amid_b200.hotpath import DistCtx
+        ctx = DistCtx()
+        torch.manual_seed(0)                       # same "global batch" on every rank
+        Bg, n, ts = 8, 5, 0.15
+        Bl, j0 = Bg // world, rank * (Bg // world)
+        P = make_params(3, 4, D, n, 32, Bg)
+        e1, e2 = torch.randn(Bg, n, D) * 0.3, torch.randn(Bg, n, D) * 0.3
+        e1[2] *= 3; e2[2] *= 3; e1[6] *= 3; e2[6] = e1[6].clone()          # gates fire on both shards
+        w_nn, b_nn = P["itc_d1.trans_nn.weight"], P["itc_d1.trans_nn.bias"]
+        w_bs, b_bs = P["itc_d1.trans_bs.weight"], P["itc_d1.trans_bs.bias"]
+        # ---- global (single-process) answer
+        col = {}
+        ref = O.mim_closed(e1, e2, w_nn, b_nn, w_bs, b_bs, ts, collect=col)
+        assert 0 < col["g"].sum() < Bg
+        # ---- sharded: all-gather m, global gate, local partial aggregate, all-reduce
+        m_loc = O.mim_scores(e1[j0:j0 + Bl], e2[j0:j0 + Bl])
+        m_glob = torch.empty(Bg)
+        ctx.all_gather_into(m_glob, m_loc)
+        assert torch.equal(m_glob, col["m"])
+        g = (torch.softmax(m_glob, 0) > ts).float()
+        coef = w_bs.reshape(-1) * g
+        S = torch.einsum("j,jnd->nd", coef[j0:j0 + Bl], e2[j0:j0 + Bl])
+        ctx.all_reduce(S)
+        E = S @ w_nn.T + w_bs.sum() * b_nn + b_bs
+        np.testing.assert_allclose(E.numpy(), col["E"].numpy(), rtol=0, atol=2e-6)
+        np.testing.assert_allclose(E.numpy(), ref[0, n:].numpy(), rtol=0, atol=2e-6)
+        # ---- backward of the shared half: dE = all-reduce of the local column sums; w_bs slices are disjoint
+        du = torch.randn(Bg, D)
+        dcol = du[j0:j0 + Bl].sum(0) / (2 * n)
+        ctx.all_reduce(dcol)
+        np.testing.assert_allclose(dcol.numpy(), (du.sum(0) / (2 * n)).numpy(), rtol=1e-5, atol=1e-6)
+        dE = dcol.expand(n, D)
+        dS = dE @ w_nn
+        dw_loc = g[j0:j0 + Bl] * torch.einsum("nd,jnd->j", dS, e2[j0:j0 + Bl]) + (dE.sum(0) * b_nn).sum()
+        gw = torch.zeros(Bg)
+        gw[j0:j0 + Bl] = dw_loc
+        ctx.all_reduce(gw)
+        wv = w_bs.clone().requires_grad_(True)
+        out = O.mim_closed(e1, e2, w_nn, b_nn, wv, b_bs, ts)
+        (out[:, n:] * (du / (2 * n)).unsqueeze(1)).sum().backward()
+        np.testing.assert_allclose(gw.numpy(), wv.grad.reshape(-1).numpy(), rtol=1e-4, atol=1e-5)
+        # ---- table-gradient exchange: padded all-gather + second reduction == global reduction
+        V = 50
+        gen = torch.Generator().manual_seed(5)
+        ids = torch.randint(0, V - 1, (world, 40), generator=gen)
+        rows = torch.randn(world, 40, D, generator=gen)
+        uid_l, inv = torch.unique(ids[rank], return_inverse=True)
+        ug_l = torch.zeros(len(uid_l), D).index_add_(0, inv, rows[rank])
+        k = len(uid_l)
+        uid_p = torch.cat((uid_l, torch.full((40 - k,), 12345)))             # garbage past n_uniq
+        ug_p = torch.cat((ug_l, torch.full((40 - k, D), float("nan"))))
+        uid_x, ug_x = pad_for_exchange(uid_p, ug_p, torch.tensor([k], dtype=torch.int32), V)
+        assert (uid_x[k:] == V - 1).all() and (ug_x[k:] == 0).all()
+        all_ids, all_rows = torch.empty(40 * world, dtype=torch.int64), torch.empty(40 * world, D)
+        ctx.all_gather_into(all_ids, uid_x)
+        ctx.all_gather_into(all_rows, ug_x)
+        dense = torch.zeros(V, D).index_add_(0, all_ids, all_rows)
+        want = torch.zeros(V, D).index_add_(0, ids.reshape(-1), rows.reshape(-1, D))
+        np.testing.assert_allclose(dense.numpy(), want.numpy(), rtol=1e-5, atol=1e-5)
+        q.put((rank, "ok"))
+    except Exception as e:  # pragma: no cover
+        import traceback
+        q.put((rank, traceback.format_exc()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_dp_decomposition_world2_gloo():
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=240) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    for rank, msg in res:
+        assert msg == "ok", f"rank {rank}: {msg}"

@@ -79,7 +79,8 @@ def test_seq_embed_bit_exact_and_mask_bits(B, L):
         for j in range(32):
             mask[:, 4 * j + e] = (bits[:, e] >> j) & 1
     assert np.array_equal(mask, (want == 0).view(B * L, D).numpy())
-    assert mask[0].all() and mask[B * L - 1, 3]
+    if B * L > 1:
+        assert mask[0].all() and mask[B * L - 1, 3]
 
 
 # ------------------------------------------------------------------ whole forward vs reference goldens
