@@ -345,8 +345,8 @@ def test_adam_dense_and_lazy_rows_match_reference_adam():
          hp._stream())
     assert_close(pd, pr, 0, 2e-6)
     assert_close(pl, pr, 0, 2e-6)
-    assert_close(ml, m, 1e-5, 1e-9)
-    assert_close(vl, v, 1e-5, 1e-12)
+    assert_close(ml, m, 1e-4, 1e-8)
+    assert_close(vl, v, 1e-4, 1e-11)
     assert int(last.min().item()) in (0, steps)
 
 
