@@ -9,6 +9,7 @@
 // A 128-token tile stays in shared memory across the chained GEMMs of a kernel, so each
 // activation crosses HBM once per kernel instead of once per op.
 #include "tile.cuh"
+#include "encoder_tc.cuh"
 
 namespace amid {
 
@@ -735,9 +736,9 @@ using namespace amid;
 
 extern "C" int64_t amid_encoder_fwd_workspace_bytes(int32_t, int32_t) { return (int64_t)12 * D * D * sizeof(float); }
 
-extern "C" int amid_encoder_fwd(const amid_encoder_tensors* P, const float* x0, const uint32_t* tmask, int32_t B,
-                                int32_t L, const amid_dropout* drop, amid_encoder_saved* S, float* enc_out,
-                                void* workspace, int64_t workspace_bytes, amid_stream_t stream_) {
+static int encoder_fwd_impl(const amid_encoder_tensors* P, const float* x0, const uint32_t* tmask, int32_t B,
+                            int32_t L, const amid_dropout* drop, amid_encoder_saved* S, float* enc_out,
+                            void* workspace, int64_t workspace_bytes, amid_stream_t stream_, bool use_tc) {
     cudaStream_t stream = (cudaStream_t)stream_;
     if (int rc = check_encoder_args(B, L)) return rc;
     AMID_REQUIRE(P && S && x0 && tmask && enc_out && workspace, "encoder_fwd: null argument");
@@ -746,6 +747,35 @@ extern "C" int amid_encoder_fwd(const amid_encoder_tensors* P, const float* x0, 
     const int M = B * L;
     const int tiles = (M + TM - 1) / TM;
     const DropCfg dc = make_drop(drop);
+    const size_t attn_smem = (size_t)2 * L * DH * sizeof(float);
+    if (int rc = ensure_smem((const void*)k_attn_fwd, attn_smem)) return rc;
+    const int attn_threads = (int)round_up((L + 1) / 2, 32);
+    if (use_tc) {   // tcgen05 path: the weights are consumed K-major in their natural [out][in] layout
+        if (int rc = ensure_smem((const void*)tcenc::k_ln_qkv_tc, tcenc::CHAIN_SMEM)) return rc;
+        if (int rc = ensure_smem((const void*)tcenc::k_proj_ffn_tc, tcenc::CHAIN_SMEM)) return rc;
+        const float* xin = x0;
+        for (int i = 0; i < 2; ++i) {
+            AMID_K("k_ln_qkv_tc", stream);
+            tcenc::k_ln_qkv_tc<<<tiles, 256, tcenc::CHAIN_SMEM, stream>>>(
+                xin, M, P->ln1_w[i], P->ln1_b[i], P->in_w[i], P->in_w[i] + D * D, P->in_w[i] + 2 * D * D, P->in_b[i],
+                S->qn[i], S->st1[i], S->q[i], S->k[i], S->v[i]);
+            AMID_LAUNCH_CHECK("k_ln_qkv_tc");
+            AMID_K("k_attn_fwd", stream);
+            k_attn_fwd<<<B * H, attn_threads, attn_smem, stream>>>(S->q[i], S->k[i], S->v[i], S->o[i], S->lse[i], L, dc,
+                                                                   dc.site_base + site_attn(i));
+            AMID_LAUNCH_CHECK("k_attn_fwd");
+            const bool last = i == 1;
+            AMID_K("k_proj_ffn_tc", stream);
+            tcenc::k_proj_ffn_tc<<<tiles, 256, tcenc::CHAIN_SMEM, stream>>>(
+                S->o[i], S->qn[i], M, P->out_w[i], P->out_b[i], P->ln2_w[i], P->ln2_b[i], P->c1_w[i], P->c1_b[i],
+                P->c2_w[i], P->c2_b[i], tmask, dc, dc.site_base + site_ffn1(i), dc.site_base + site_ffn2(i), S->x1[i],
+                S->st2[i], S->y[i], S->h[i], S->xout[i], last ? P->ln3_w : nullptr, last ? P->ln3_b : nullptr,
+                last ? enc_out : nullptr, last ? S->st3 : nullptr);
+            AMID_LAUNCH_CHECK("k_proj_ffn_tc");
+            xin = S->xout[i];
+        }
+        return 0;
+    }
     float* wt = (float*)workspace;
     TransJobs tj;
     for (int i = 0; i < 2; ++i) {
@@ -761,9 +791,6 @@ extern "C" int amid_encoder_fwd(const amid_encoder_tensors* P, const float* x0, 
     AMID_LAUNCH_CHECK("k_transpose128");
     if (int rc = ensure_smem((const void*)k_ln_qkv, ENC_SMEM_BYTES)) return rc;
     if (int rc = ensure_smem((const void*)k_proj_ffn, ENC_SMEM_BYTES)) return rc;
-    const size_t attn_smem = (size_t)2 * L * DH * sizeof(float);
-    if (int rc = ensure_smem((const void*)k_attn_fwd, attn_smem)) return rc;
-    const int attn_threads = (int)round_up((L + 1) / 2, 32);
     const float* xin = x0;
     for (int i = 0; i < 2; ++i) {
         const float* W = wt + (size_t)i * 6 * D * D;
@@ -788,21 +815,36 @@ extern "C" int amid_encoder_fwd(const amid_encoder_tensors* P, const float* x0, 
     return 0;
 }
 
+extern "C" int amid_encoder_fwd(const amid_encoder_tensors* P, const float* x0, const uint32_t* tmask, int32_t B,
+                                int32_t L, const amid_dropout* drop, amid_encoder_saved* S, float* enc_out,
+                                void* workspace, int64_t workspace_bytes, amid_stream_t stream) {
+    return encoder_fwd_impl(P, x0, tmask, B, L, drop, S, enc_out, workspace, workspace_bytes, stream, false);
+}
+extern "C" int amid_encoder_fwd_tc(const amid_encoder_tensors* P, const float* x0, const uint32_t* tmask, int32_t B,
+                                   int32_t L, const amid_dropout* drop, amid_encoder_saved* S, float* enc_out,
+                                   void* workspace, int64_t workspace_bytes, amid_stream_t stream) {
+    return encoder_fwd_impl(P, x0, tmask, B, L, drop, S, enc_out, workspace, workspace_bytes, stream, true);
+}
+
+constexpr int WG_TC_S = 24;   // CTAs per weight-gradient job on the tensor-core path (6 jobs -> 144 CTAs)
+
 extern "C" int64_t amid_encoder_bwd_workspace_bytes(int32_t B, int32_t L) {
     const int64_t M = (int64_t)B * L;
     const int64_t tiles = (M + TM - 1) / TM;
     int rp;
-    const int S = wgrad_chunks((int)M, &rp);
+    int S = wgrad_chunks((int)M, &rp);
+    if (S < WG_TC_S) S = WG_TC_S;
     int64_t fl = 9 * M * D;                  // dxa, dxb, do2, dhpre, dx1, dO, dq, dk, dv
     fl += (int64_t)6 * S * (D * D + D);      // weight / bias partials
     fl += 2 * tiles * 2 * D;                 // LN partials (two in flight)
+    fl += (int64_t)12 * D * D;               // transposed weights (tensor-core path)
     return fl * (int64_t)sizeof(float) + 256;
 }
 
-extern "C" int amid_encoder_bwd(const amid_encoder_tensors* P, const float* x0, const uint32_t* tmask, int32_t B,
-                                int32_t L, const amid_dropout* drop, const amid_encoder_saved* S, const float* enc_out,
-                                const float* d_enc, amid_encoder_tensors* G, float* dx0, void* workspace,
-                                int64_t workspace_bytes, amid_stream_t stream_) {
+static int encoder_bwd_impl(const amid_encoder_tensors* P, const float* x0, const uint32_t* tmask, int32_t B,
+                            int32_t L, const amid_dropout* drop, const amid_encoder_saved* S, const float* enc_out,
+                            const float* d_enc, amid_encoder_tensors* G, float* dx0, void* workspace,
+                            int64_t workspace_bytes, amid_stream_t stream_, bool use_tc) {
     (void)enc_out;
     cudaStream_t stream = (cudaStream_t)stream_;
     if (int rc = check_encoder_args(B, L)) return rc;
@@ -813,7 +855,9 @@ extern "C" int amid_encoder_bwd(const amid_encoder_tensors* P, const float* x0, 
     const int tiles = (M + TM - 1) / TM;
     const DropCfg dc = make_drop(drop);
     int rp;
-    const int SW = wgrad_chunks(M, &rp);
+    int SW = wgrad_chunks(M, &rp);
+    const int SWmax = SW < WG_TC_S ? WG_TC_S : SW;
+    if (use_tc) SW = tiles < WG_TC_S ? tiles : WG_TC_S;
     float* w = (float*)workspace;
     const size_t MD = (size_t)M * D;
     float* dxa = w;            // gradient of the current block output
@@ -826,9 +870,27 @@ extern "C" int amid_encoder_bwd(const amid_encoder_tensors* P, const float* x0, 
     float* dk = w + 7 * MD;
     float* dv = w + 8 * MD;
     float* wpart = w + 9 * MD;
-    float* bpart = wpart + (size_t)6 * SW * D * D;
-    float* lnp0 = bpart + (size_t)6 * SW * D;
+    float* bpart = wpart + (size_t)6 * SWmax * D * D;
+    float* lnp0 = bpart + (size_t)6 * SWmax * D;
     float* lnp1 = lnp0 + (size_t)tiles * 2 * D;
+    float* wtr = lnp1 + (size_t)tiles * 2 * D;   // 12 transposed weights: per block W2t, W1t, Wot, Wqt, Wkt, Wvt
+    if (use_tc) {
+        if (int rc = ensure_smem((const void*)tcenc::k_ffn_bwd_tc, tcenc::CHAIN_SMEM)) return rc;
+        if (int rc = ensure_smem((const void*)tcenc::k_qkv_bwd_tc, tcenc::CHAIN_SMEM)) return rc;
+        if (int rc = ensure_smem((const void*)tcenc::k_wgrad_tc, tcenc::WGRAD_SMEM)) return rc;
+        TransJobs tj;
+        for (int i = 0; i < 2; ++i) {
+            tj.src[i * 6 + 0] = P->c2_w[i];
+            tj.src[i * 6 + 1] = P->c1_w[i];
+            tj.src[i * 6 + 2] = P->out_w[i];
+            tj.src[i * 6 + 3] = P->in_w[i];
+            tj.src[i * 6 + 4] = P->in_w[i] + D * D;
+            tj.src[i * 6 + 5] = P->in_w[i] + 2 * D * D;
+        }
+        AMID_K("k_transpose128", stream);
+        k_transpose128<<<dim3(4, 4, 12), dim3(32, 8), 0, stream>>>(tj, wtr);
+        AMID_LAUNCH_CHECK("k_transpose128");
+    }
 
     if (int rc = ensure_smem((const void*)k_ffn_bwd, ENC_SMEM_BYTES)) return rc;
     if (int rc = ensure_smem((const void*)k_qkv_bwd, ENC_SMEM_BYTES)) return rc;
@@ -848,12 +910,21 @@ extern "C" int amid_encoder_bwd(const amid_encoder_tensors* P, const float* x0, 
     for (int i = 1; i >= 0; --i) {
         const float* xin = i == 0 ? x0 : S->xout[0];
         float* dxin = i == 0 ? dx0 : dxb;
+        const float* Wt = wtr + (size_t)i * 6 * D * D;
+        if (use_tc) {
+            AMID_K("k_ffn_bwd_tc", stream);
+            tcenc::k_ffn_bwd_tc<<<tiles, 256, tcenc::CHAIN_SMEM, stream>>>(
+                dxa, S->h[i], S->x1[i], S->st2[i], tmask, M, Wt, Wt + D * D, Wt + 2 * D * D, P->ln2_w[i], dc,
+                dc.site_base + site_ffn1(i), dc.site_base + site_ffn2(i), do2, dhp, dx1, dO, lnp0);
+            AMID_LAUNCH_CHECK("k_ffn_bwd_tc");
+        } else {
         AMID_K("k_ffn_bwd", stream);
         k_ffn_bwd<<<tiles, NT, ENC_SMEM_BYTES, stream>>>(dxa, S->h[i], S->x1[i], S->st2[i], tmask, M, P->c2_w[i],
                                                          P->c1_w[i], P->out_w[i], P->ln2_w[i], dc,
                                                          dc.site_base + site_ffn1(i), dc.site_base + site_ffn2(i), do2,
                                                          dhp, dx1, dO, lnp0);
         AMID_LAUNCH_CHECK("k_ffn_bwd");
+        }
         AMID_K("k_reduce_ln", stream);
         k_reduce_ln<<<1, 2 * D, 0, stream>>>(lnp0, tiles, G->ln2_w[i], G->ln2_b[i]);
         AMID_LAUNCH_CHECK("k_reduce_ln");
@@ -861,11 +932,19 @@ extern "C" int amid_encoder_bwd(const amid_encoder_tensors* P, const float* x0, 
         k_attn_bwd<<<B * H, attn_threads, attn_smem, stream>>>(S->q[i], S->k[i], S->v[i], S->o[i], S->lse[i], dO, dq, dk,
                                                                dv, L, dc, dc.site_base + site_attn(i));
         AMID_LAUNCH_CHECK("k_attn_bwd");
+        if (use_tc) {
+            AMID_K("k_qkv_bwd_tc", stream);
+            tcenc::k_qkv_bwd_tc<<<tiles, 256, tcenc::CHAIN_SMEM, stream>>>(dq, dk, dv, dx1, xin, S->st1[i], M, Wt + 3 * D * D,
+                                                                          Wt + 4 * D * D, Wt + 5 * D * D, P->ln1_w[i], dxin,
+                                                                          lnp1);
+            AMID_LAUNCH_CHECK("k_qkv_bwd_tc");
+        } else {
         AMID_K("k_qkv_bwd", stream);
         k_qkv_bwd<<<tiles, NT, ENC_SMEM_BYTES, stream>>>(dq, dk, dv, dx1, xin, S->st1[i], M, P->in_w[i],
                                                          P->in_w[i] + D * D, P->in_w[i] + 2 * D * D, P->ln1_w[i], dxin,
                                                          lnp1);
         AMID_LAUNCH_CHECK("k_qkv_bwd");
+        }
         AMID_K("k_reduce_ln", stream);
         k_reduce_ln<<<1, 2 * D, 0, stream>>>(lnp1, tiles, G->ln1_w[i], G->ln1_b[i]);
         AMID_LAUNCH_CHECK("k_reduce_ln");
@@ -877,9 +956,17 @@ extern "C" int amid_encoder_bwd(const amid_encoder_tensors* P, const float* x0, 
         wj.dY[3] = dq;  wj.X[3] = S->qn[i];
         wj.dY[4] = dk;  wj.X[4] = xin;
         wj.dY[5] = dv;  wj.X[5] = xin;
+        if (use_tc) {
+            tcenc::WgradJobsTc wt6;
+            for (int j = 0; j < 6; ++j) { wt6.dY[j] = wj.dY[j]; wt6.X[j] = wj.X[j]; }
+            AMID_K("k_wgrad_tc", stream);
+            tcenc::k_wgrad_tc<<<dim3(SW, 6), 256, tcenc::WGRAD_SMEM, stream>>>(wt6, M, wpart, bpart);
+            AMID_LAUNCH_CHECK("k_wgrad_tc");
+        } else {
         AMID_K("k_wgrad", stream);
         k_wgrad<<<dim3(SW, 6), NT, WG_SMEM_BYTES, stream>>>(wj, M, rp, wpart, bpart);
         AMID_LAUNCH_CHECK("k_wgrad");
+        }
         ReduceJobs rw, rb;
         rw.out[0] = G->c2_w[i]; rb.out[0] = G->c2_b[i];
         rw.out[1] = G->c1_w[i]; rb.out[1] = G->c1_b[i];
@@ -899,4 +986,17 @@ extern "C" int amid_encoder_bwd(const amid_encoder_tensors* P, const float* x0, 
         }
     }
     return 0;
+}
+
+extern "C" int amid_encoder_bwd(const amid_encoder_tensors* P, const float* x0, const uint32_t* tmask, int32_t B,
+                                int32_t L, const amid_dropout* drop, const amid_encoder_saved* S, const float* enc_out,
+                                const float* d_enc, amid_encoder_tensors* G, float* dx0, void* workspace,
+                                int64_t workspace_bytes, amid_stream_t stream) {
+    return encoder_bwd_impl(P, x0, tmask, B, L, drop, S, enc_out, d_enc, G, dx0, workspace, workspace_bytes, stream, false);
+}
+extern "C" int amid_encoder_bwd_tc(const amid_encoder_tensors* P, const float* x0, const uint32_t* tmask, int32_t B,
+                                   int32_t L, const amid_dropout* drop, const amid_encoder_saved* S, const float* enc_out,
+                                   const float* d_enc, amid_encoder_tensors* G, float* dx0, void* workspace,
+                                   int64_t workspace_bytes, amid_stream_t stream) {
+    return encoder_bwd_impl(P, x0, tmask, B, L, drop, S, enc_out, d_enc, G, dx0, workspace, workspace_bytes, stream, true);
 }

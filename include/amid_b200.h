@@ -119,6 +119,16 @@ int amid_encoder_bwd(const amid_encoder_tensors* P, const float* x0, const uint3
                      const float* enc_out, const float* d_enc, amid_encoder_tensors* G, float* dx0,
                      void* workspace, int64_t workspace_bytes, amid_stream_t stream);
 
+/* Tensor-core variants (same arguments, same tensors): the 128x128x128 stages run as tcgen05.mma
+ * with TF32 operands and fp32 accumulation in TMEM instead of fp32 CUDA-core tiles. */
+int amid_encoder_fwd_tc(const amid_encoder_tensors* P, const float* x0, const uint32_t* tmask,
+                        int32_t B, int32_t L, const amid_dropout* drop, amid_encoder_saved* S,
+                        float* enc_out, void* workspace, int64_t workspace_bytes, amid_stream_t stream);
+int amid_encoder_bwd_tc(const amid_encoder_tensors* P, const float* x0, const uint32_t* tmask,
+                        int32_t B, int32_t L, const amid_dropout* drop, const amid_encoder_saved* S,
+                        const float* enc_out, const float* d_enc, amid_encoder_tensors* G, float* dx0,
+                        void* workspace, int64_t workspace_bytes, amid_stream_t stream);
+
 /* ---- a6: InterComp / InnerComp in closed form (model_seq.py:474-497 / 450-472) ----- */
 /* m[j] = max_{s,t} <a[j,s,:], b[j,t,:]>,  a,b: [B,n,128]  (the [bs,B,n,n] matmul+max of
  * model_seq.py:489-490 without its redundant outer axis). */
@@ -222,6 +232,12 @@ int amid_rank_counts(const float* scores, int64_t N, int32_t C, float fix, int32
 /* feature site: out[r*128+c] for r<rows; attention site: out[((b*8+h)*L+i)*L+j]. */
 int amid_dropout_mask_feature(const amid_dropout* drop, uint32_t site, int64_t rows, uint8_t* out, amid_stream_t stream);
 int amid_dropout_mask_attn(const amid_dropout* drop, uint32_t site, int32_t B, int32_t L, uint8_t* out, amid_stream_t stream);
+
+/* ---- tcgen05 bring-up / unit-test entry points (TF32 operands, fp32 accumulate in TMEM) ------ */
+/* y[M,128] = x[M,128] w[128,128]^T + b   (what nn.Linear / Conv1d(k=1) compute on the path) */
+int amid_tc_linear_test(const float* x, const float* w, const float* b, int32_t M, float* y, amid_stream_t stream);
+/* part[cta][n][k] = sum over the CTA's 128-token tiles of dy[m][n] x[m][k]; sum over cta = dy^T x */
+int amid_tc_wgrad_test(const float* dy, const float* x, int32_t M, float* part, int32_t n_ctas, amid_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -14,7 +14,8 @@ def T(a):
     return torch.from_numpy(np.asarray(a))
 
 
-def build_model(P, V, L, bs, *, isInC=False, isItC=True, ts1=0.5, ts2=0.4, isDR=False, hid=HID, drop_p=0.5):
+def build_model(P, V, L, bs, *, isInC=False, isItC=True, ts1=0.5, ts2=0.4, isDR=False, hid=HID, drop_p=0.5,
+                precision="fp32"):
     """The drop-in SASRec on cuda:0 with the given reference-named parameters."""
     from amid_b200.model_seq import SASRec
     m = SASRec(user_length=10, user_emb_dim=D, item_length=V, item_emb_dim=D, seq_len=L, hid_dim=hid, bs=bs,
@@ -22,6 +23,7 @@ def build_model(P, V, L, bs, *, isInC=False, isItC=True, ts1=0.5, ts2=0.4, isDR=
     res = m.load_state_dict(P, strict=True)
     assert not res.missing_keys and not res.unexpected_keys
     m.cfg.drop_p = drop_p
+    m.cfg.precision = precision
     return m.cuda()
 
 

@@ -1,0 +1,132 @@
+"""tcgen05 / TMEM tile pipeline (amid_b200/csrc/tc.cuh) against torch fp32 references.
+TF32 operands (10-bit mantissa), fp32 accumulation: tolerance 2e-3 relative to the row scale."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+D = 128
+
+
+@pytest.mark.parametrize("M", [128, 1, 200, 1000, 4096 + 77])
+def test_tc_linear_tf32(M):
+    from amid_b200 import hotpath as hp
+    from amid_b200._abi import call
+    g = torch.Generator().manual_seed(M)
+    x = torch.randn(M, D, generator=g).cuda()
+    w = (torch.randn(D, D, generator=g) / 11.3).cuda()
+    b = torch.randn(D, generator=g).cuda()
+    y = torch.full((M, D), float("nan"), device="cuda")
+    call("amid_tc_linear_test", hp._ptr(x), hp._ptr(w), hp._ptr(b), M, hp._ptr(y), hp._stream())
+    torch.cuda.synchronize()
+    ref = (x.double() @ w.double().T + b.double()).float()
+    err = (y - ref).abs().max().item()
+    assert torch.isfinite(y).all()
+    assert err < 2e-3 * ref.abs().max().item(), err
+
+
+@pytest.mark.parametrize("M,ctas", [(128, 1), (1000, 3), (5000, 148)])
+def test_tc_wgrad_tf32(M, ctas):
+    from amid_b200 import hotpath as hp
+    from amid_b200._abi import call
+    g = torch.Generator().manual_seed(M)
+    dy = torch.randn(M, D, generator=g).cuda()
+    x = torch.randn(M, D, generator=g).cuda()
+    part = torch.full((ctas, D, D), float("nan"), device="cuda")
+    call("amid_tc_wgrad_test", hp._ptr(dy), hp._ptr(x), M, hp._ptr(part), ctas, hp._stream())
+    torch.cuda.synchronize()
+    ref = (dy.double().T @ x.double()).float()
+    got = part.sum(0)
+    err = (got - ref).abs().max().item()
+    assert err < 2e-3 * ref.abs().max().item() + 1e-3, err
+
+
+# ------------------------------------------------------------------ the encoder on the tensor-core path
+# TF32 operands: 10-bit mantissa, truncated by the MMA unit.  Stated tolerance for this path:
+# probabilities 5e-3 abs, losses 3e-3 rel, gradient tensors 2e-2 in relative Frobenius norm (a ReLU
+# pre-activation within TF32 noise of zero flips its gate and moves one term of a row of a weight
+# gradient, so single elements are only held to 0.2 of the tensor's max magnitude).
+import numpy as np
+
+
+def assert_grad_tf32(got, ref, name):
+    got = got.detach().float().cpu()
+    ref = torch.as_tensor(np.asarray(ref) if not torch.is_tensor(ref) else ref).float().cpu()
+    num, den = (got - ref).norm().item(), ref.norm().item()
+    assert num <= 2e-2 * den + 1e-9, f"{name}: relative Frobenius error {num / max(den, 1e-30):.3e}"
+    assert (got - ref).abs().max().item() <= 0.2 * ref.abs().max().item() + 1e-9, name
+
+
+from helpers import (HID, O, T, assert_close, batch_from, build_model, grad_tol, load, make_params, oracle_forward,
+                     random_batch, run_model, to_cuda)
+
+
+@pytest.mark.parametrize("B,L,C", [(1, 1, 2), (7, 13, 5), (3, 130, 2), (9, 200, 2)])
+def test_forward_tf32_vs_oracle(B, L, C):
+    rng = np.random.default_rng(B * 1000 + L)
+    V = 211
+    P = make_params(41, V, D, L, HID, B)
+    b = random_batch(rng, B, L, C, V)
+    col = {}
+    outs = oracle_forward(P, b, isInC=False, isItC=True, ts1=0.3, ts2=0.3, isDR=False, collect=col)
+    pj = torch.softmax(O.mim_scores(col["enc1"], col["enc2"]), 0)
+    if (pj - 0.3).abs().min() < 2e-2:
+        pytest.skip("gate margin too small for a TF32 comparison")
+    m = build_model(P, V, L, B, ts1=0.3, ts2=0.3, precision="tf32").eval()
+    with torch.no_grad():
+        p1, p2 = run_model(m, to_cuda(b))
+    assert_close(p1.reshape(B, C), outs[0], 0, 5e-3)
+    assert_close(p2.reshape(B, C), outs[1], 0, 5e-3)
+    from amid_b200 import hotpath as hp
+    cb = to_cuda(b)
+    _, ctx = hp.forward(m.param_dict(), m.cfg, cb["i_node"], cb["neg_samples"], cb["seq_d1"], cb["seq_d2"], train=False)
+    assert_close(ctx.encs[0].view(B, L, D), col["enc1"], 0, 3e-2)
+
+
+def test_train_p0_tf32_golden():
+    from amid_b200.engine import Trainer
+    z = load("train_p0.npz")
+    V = int(z["V"])
+    P = make_params(18, V, D, 20, HID, 16)
+    m = build_model(P, V, 20, 16, ts2=0.07, drop_p=0.0, precision="tf32").train()
+    b = batch_from(z, pre="b0_")
+    p1, p2 = run_model(m, b)
+    crit = torch.nn.BCELoss(reduction="none")
+    dom = b["domain_id"]
+    loss = torch.mean(crit(p1, b["label"]) * (1 - dom).unsqueeze(1) + crit(p2, b["label"]) * dom.unsqueeze(1))
+    assert_close(loss, z["loss_step0"], 2e-3, 0)
+    loss.backward()
+    named = dict(m.named_parameters())
+    for k in z:
+        if k.startswith("grad/"):
+            assert_grad_tf32(named[k[5:]].grad, z[k], k)
+    m2 = build_model(P, V, 20, 16, ts2=0.07, drop_p=0.0, precision="tf32").train()
+    tr = Trainer(m2, lr=5e-4)
+    for step in range(3):
+        losses = tr.step(batch_from(z, pre=f"b{step}_"))
+        assert_close(losses[0], z[f"loss_step{step}"], 3e-3, 0, f"step {step}")
+
+
+def test_train_dropout_tf32_vs_oracle():
+    from amid_b200 import hotpath as hp
+    B, L, C, V = 6, 40, 2, 97
+    rng = np.random.default_rng(77)
+    P = make_params(31, V, D, L, HID, B)
+    m = build_model(P, V, L, B, ts2=0.2, precision="tf32").train()
+    b = to_cuda(random_batch(rng, B, L, C, V))
+    probs, ctx = hp.forward(m.param_dict(), m.cfg, b["i_node"], b["neg_samples"], b["seq_d1"], b["seq_d2"], train=True, seed=99)
+    masks = {s: {k: v.cpu() for k, v in d.items()} for s, d in hp.dropout_masks(m.cfg, B, L, 99, "cuda").items()}
+    Po = {k: v.clone().requires_grad_(True) for k, v in P.items()}
+    col = {}
+    outs = oracle_forward(Po, b, isInC=False, isItC=True, ts1=0.5, ts2=0.2, isDR=False, masks=masks, collect=col)
+    pj = torch.softmax(O.mim_scores(col["enc1"], col["enc2"]), 0)
+    if (pj - 0.2).abs().min() < 2e-2:
+        pytest.skip("gate margin too small for a TF32 comparison")
+    assert_close(probs[0, 0], outs[0], 0, 5e-3)
+    lo = O.loss_cls(outs[0], outs[1], b["label"].cpu(), b["domain_id"].cpu())
+    lo.backward()
+    losses, dprobs = hp.loss_fwd_bwd(probs, b["label"], b["domain_id"], None, 0, 0.0, B)
+    assert_close(losses[0], lo, 3e-3, 0)
+    G, ids_all, rows_all = hp.backward(m.param_dict(), m.cfg, ctx, dprobs)
+    for k, v in Po.items():
+        if k != "item_emb_layer.emb_item.weight":
+            assert_grad_tf32(G[k], v.grad, k)
