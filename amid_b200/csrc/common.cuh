@@ -49,33 +49,38 @@ __device__ __forceinline__ float warp_max(float v) {
 }
 
 // ------------------------------------------------------------------ counter-based dropout RNG
-// One 64-bit hash yields four 16-bit lanes = the keep decisions of 4 consecutive elements
-// (idx4 = element_index >> 2).  keep <=> lane >= thr16, thr16 = round(p * 65536).
-__device__ __forceinline__ uint64_t rng4(uint64_t seed, uint32_t site, uint64_t idx4) {
-    uint64_t z = seed + 0x9E3779B97F4A7C15ull * (idx4 + 1) + 0xD1B54A32D192ED03ull * (uint64_t)(site + 1);
-    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
-    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-    return z ^ (z >> 31);
+// One 32-bit integer hash yields four 8-bit lanes = the keep decisions of 4 consecutive elements
+// (idx4 = element_index >> 2).  keep <=> lane >= thr8, thr8 = round(p * 256)  (p = 0.5 is exact).
+__device__ __forceinline__ uint32_t rng4(uint32_t seed32, uint32_t site, uint64_t idx4) {
+    uint32_t x = (uint32_t)idx4 * 0x9E3779B1u + (uint32_t)(idx4 >> 32) * 0x85EBCA77u + (seed32 ^ ((site + 1u) * 0xC2B2AE3Du));
+    x ^= x >> 16; x *= 0x7FEB352Du;      // "lowbias32" finaliser
+    x ^= x >> 15; x *= 0x846CA68Bu;
+    x ^= x >> 16;
+    return x;
 }
-__device__ __forceinline__ bool rng_keep(uint64_t r, int lane4, uint32_t thr16) {
-    return ((uint32_t)(r >> (16 * lane4)) & 0xFFFFu) >= thr16;
+__device__ __forceinline__ bool rng_keep(uint32_t r, int lane4, uint32_t thr8) {
+    return ((r >> (8 * lane4)) & 0xFFu) >= thr8;
 }
 
 struct DropCfg {
     int train;
-    uint32_t thr16;
+    uint32_t thr16;      // 8-bit threshold (name kept for brevity at the call sites)
     float scale;
-    uint64_t seed;
+    uint32_t seed;       // 32-bit digest of the 64-bit step seed
     uint32_t site_base;
 };
 inline DropCfg make_drop(const amid_dropout* d) {
-    DropCfg c{0, 0u, 1.0f, 0ull, 0u};
+    DropCfg c{0, 0u, 1.0f, 0u, 0u};
     if (d && d->train && d->p > 0.f) {
         c.train = 1;
-        double t = (double)d->p * 65536.0 + 0.5;
-        c.thr16 = (uint32_t)(t > 65535.0 ? 65535.0 : t);
+        double t = (double)d->p * 256.0 + 0.5;
+        c.thr16 = (uint32_t)(t > 255.0 ? 255.0 : t);
         c.scale = 1.0f / (1.0f - d->p);
-        c.seed = d->seed;
+        uint64_t z = d->seed + 0x9E3779B97F4A7C15ull;           // splitmix64 digest on the host
+        z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+        z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+        z ^= z >> 31;
+        c.seed = (uint32_t)(z ^ (z >> 32));
     }
     if (d) c.site_base = d->site_base;
     return c;
@@ -83,7 +88,7 @@ inline DropCfg make_drop(const amid_dropout* d) {
 
 // apply dropout to 4 consecutive elements starting at element index e0 (multiple of 4)
 __device__ __forceinline__ float4 drop4(float4 v, const DropCfg& c, uint32_t site, uint64_t e0) {
-    uint64_t r = rng4(c.seed, site, e0 >> 2);
+    const uint32_t r = rng4(c.seed, site, e0 >> 2);
     v.x = rng_keep(r, 0, c.thr16) ? v.x * c.scale : 0.f;
     v.y = rng_keep(r, 1, c.thr16) ? v.y * c.scale : 0.f;
     v.z = rng_keep(r, 2, c.thr16) ? v.z * c.scale : 0.f;

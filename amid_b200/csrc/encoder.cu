@@ -10,6 +10,7 @@
 // activation crosses HBM once per kernel instead of once per op.
 #include "tile.cuh"
 #include "encoder_tc.cuh"
+#include "attn_mma.cuh"
 
 namespace amid {
 
@@ -251,7 +252,7 @@ __global__ void k_attn_fwd(const float* __restrict__ q, const float* __restrict_
             l *= corr;
 #pragma unroll
             for (int c = 0; c < 16; ++c) acc[c] *= corr;
-            uint64_t r = 0;
+            uint32_t r = 0;
             if (dc.train) r = rng4(dc.seed, site, (((uint64_t)bh * L + i) * Lp + j0) >> 2);
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
@@ -320,7 +321,7 @@ __global__ void k_attn_bwd(const float* __restrict__ q, const float* __restrict_
         const float li = ls[i], Di = Dv[i];
         for (int j0 = 0; j0 <= imax; j0 += 4) {
             if (j0 > i) continue;
-            uint64_t r = 0;
+            uint32_t r = 0;
             if (dc.train) r = rng4(dc.seed, site, (((uint64_t)bh * L + i) * Lp + j0) >> 2);
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
@@ -356,7 +357,7 @@ __global__ void k_attn_bwd(const float* __restrict__ q, const float* __restrict_
             float dp = dot16(vr, ds + i * DH);
             float pd = p;
             if (dc.train) {
-                const uint64_t r = rng4(dc.seed, site, (((uint64_t)bh * L + i) * Lp + j) >> 2);
+                const uint32_t r = rng4(dc.seed, site, (((uint64_t)bh * L + i) * Lp + j) >> 2);
                 const bool kp = rng_keep(r, j & 3, dc.thr16);
                 dp = kp ? dp * dc.scale : 0.f;
                 pd = kp ? p * dc.scale : 0.f;
@@ -697,12 +698,21 @@ __global__ void k_reduce_partials(const float* __restrict__ part, int S, int n, 
     for (int i = 0; i < S; ++i) s += p[(size_t)i * n];
     outs.out[blockIdx.y][e] = s;
 }
-// LN partials are [S][256] = (dw[128], db[128]) per tile
-__global__ void k_reduce_ln(const float* __restrict__ part, int S, float* __restrict__ dw, float* __restrict__ db) {
-    const int e = threadIdx.x;  // 256 threads
+// LN partials are [S][256] = (dw[128], db[128]) per tile.  1024 threads: 4 row groups x 256 columns,
+// each group sums its rows in order, then the 4 group sums are added in fixed order (deterministic).
+__global__ void __launch_bounds__(1024)
+k_reduce_ln(const float* __restrict__ part, int S, float* __restrict__ dw, float* __restrict__ db) {
+    __shared__ float red[4][2 * D];
+    const int e = threadIdx.x & (2 * D - 1), g = threadIdx.x >> 8;
     float s = 0.f;
-    for (int i = 0; i < S; ++i) s += part[(size_t)i * 2 * D + e];
-    if (e < D) dw[e] = s; else db[e - D] = s;
+#pragma unroll 8
+    for (int i = g; i < S; i += 4) s += part[(size_t)i * 2 * D + e];
+    red[g][e] = s;
+    __syncthreads();
+    if (g == 0) {
+        const float t = (red[0][e] + red[1][e]) + (red[2][e] + red[3][e]);
+        if (e < D) dw[e] = t; else db[e - D] = t;
+    }
 }
 
 // ----------------------------------------------------------------------------------
@@ -753,6 +763,8 @@ static int encoder_fwd_impl(const amid_encoder_tensors* P, const float* x0, cons
     if (use_tc) {   // tcgen05 path: the weights are consumed K-major in their natural [out][in] layout
         if (int rc = ensure_smem((const void*)tcenc::k_ln_qkv_tc, tcenc::CHAIN_SMEM)) return rc;
         if (int rc = ensure_smem((const void*)tcenc::k_proj_ffn_tc, tcenc::CHAIN_SMEM)) return rc;
+        const size_t mma_smem = (size_t)3 * L * attn::LDS * sizeof(float);
+        if (int rc = ensure_smem((const void*)attn::k_attn_fwd_mma, mma_smem)) return rc;
         const float* xin = x0;
         for (int i = 0; i < 2; ++i) {
             AMID_K("k_ln_qkv_tc", stream);
@@ -760,10 +772,10 @@ static int encoder_fwd_impl(const amid_encoder_tensors* P, const float* x0, cons
                 xin, M, P->ln1_w[i], P->ln1_b[i], P->in_w[i], P->in_w[i] + D * D, P->in_w[i] + 2 * D * D, P->in_b[i],
                 S->qn[i], S->st1[i], S->q[i], S->k[i], S->v[i]);
             AMID_LAUNCH_CHECK("k_ln_qkv_tc");
-            AMID_K("k_attn_fwd", stream);
-            k_attn_fwd<<<B * H, attn_threads, attn_smem, stream>>>(S->q[i], S->k[i], S->v[i], S->o[i], S->lse[i], L, dc,
-                                                                   dc.site_base + site_attn(i));
-            AMID_LAUNCH_CHECK("k_attn_fwd");
+            AMID_K("k_attn_fwd_mma", stream);
+            attn::k_attn_fwd_mma<<<B * H, attn::NW * 32, mma_smem, stream>>>(S->q[i], S->k[i], S->v[i], S->o[i], S->lse[i], L,
+                                                                             dc, dc.site_base + site_attn(i));
+            AMID_LAUNCH_CHECK("k_attn_fwd_mma");
             const bool last = i == 1;
             AMID_K("k_proj_ffn_tc", stream);
             tcenc::k_proj_ffn_tc<<<tiles, 256, tcenc::CHAIN_SMEM, stream>>>(
@@ -904,7 +916,7 @@ static int encoder_bwd_impl(const amid_encoder_tensors* P, const float* x0, cons
     k_ln_bwd<<<tiles, NT, 0, stream>>>(d_enc, S->xout[1], S->st3, P->ln3_w, M, dxa, lnp0);
     AMID_LAUNCH_CHECK("k_ln_bwd");
     AMID_K("k_reduce_ln", stream);
-    k_reduce_ln<<<1, 2 * D, 0, stream>>>(lnp0, tiles, G->ln3_w, G->ln3_b);
+    k_reduce_ln<<<1, 1024, 0, stream>>>(lnp0, tiles, G->ln3_w, G->ln3_b);
     AMID_LAUNCH_CHECK("k_reduce_ln");
 
     for (int i = 1; i >= 0; --i) {
@@ -926,12 +938,21 @@ static int encoder_bwd_impl(const amid_encoder_tensors* P, const float* x0, cons
         AMID_LAUNCH_CHECK("k_ffn_bwd");
         }
         AMID_K("k_reduce_ln", stream);
-        k_reduce_ln<<<1, 2 * D, 0, stream>>>(lnp0, tiles, G->ln2_w[i], G->ln2_b[i]);
+        k_reduce_ln<<<1, 1024, 0, stream>>>(lnp0, tiles, G->ln2_w[i], G->ln2_b[i]);
         AMID_LAUNCH_CHECK("k_reduce_ln");
+        if (use_tc) {
+            const size_t mma_smem = (size_t)(4 * L * attn::LDS + 2 * L) * sizeof(float);
+            if (int rc = ensure_smem((const void*)attn::k_attn_bwd_mma, mma_smem)) return rc;
+            AMID_K("k_attn_bwd_mma", stream);
+            attn::k_attn_bwd_mma<<<B * H, attn::NW * 32, mma_smem, stream>>>(S->q[i], S->k[i], S->v[i], S->o[i], S->lse[i], dO,
+                                                                             dq, dk, dv, L, dc, dc.site_base + site_attn(i));
+            AMID_LAUNCH_CHECK("k_attn_bwd_mma");
+        } else {
         AMID_K("k_attn_bwd", stream);
         k_attn_bwd<<<B * H, attn_threads, attn_smem, stream>>>(S->q[i], S->k[i], S->v[i], S->o[i], S->lse[i], dO, dq, dk,
                                                                dv, L, dc, dc.site_base + site_attn(i));
         AMID_LAUNCH_CHECK("k_attn_bwd");
+        }
         if (use_tc) {
             AMID_K("k_qkv_bwd_tc", stream);
             tcenc::k_qkv_bwd_tc<<<tiles, 256, tcenc::CHAIN_SMEM, stream>>>(dq, dk, dv, dx1, xin, S->st1[i], M, Wt + 3 * D * D,
@@ -946,7 +967,7 @@ static int encoder_bwd_impl(const amid_encoder_tensors* P, const float* x0, cons
         AMID_LAUNCH_CHECK("k_qkv_bwd");
         }
         AMID_K("k_reduce_ln", stream);
-        k_reduce_ln<<<1, 2 * D, 0, stream>>>(lnp1, tiles, G->ln1_w[i], G->ln1_b[i]);
+        k_reduce_ln<<<1, 1024, 0, stream>>>(lnp1, tiles, G->ln1_w[i], G->ln1_b[i]);
         AMID_LAUNCH_CHECK("k_reduce_ln");
         // weight gradients of the block, one launch: W2, W1, Wo, Wq, Wk, Wv
         WgradJobs wj;

@@ -122,7 +122,7 @@ k_seq_embed_bwd(float* __restrict__ dx0, const uint32_t* __restrict__ tmask, int
 __global__ void k_mask_feature(DropCfg dc, uint32_t site, int64_t n, uint8_t* __restrict__ out) {
     const int64_t e4 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e4 * 4 >= n) return;
-    const uint64_t r = rng4(dc.seed, site, (uint64_t)e4);
+    const uint32_t r = rng4(dc.seed, site, (uint64_t)e4);
     for (int u = 0; u < 4; ++u)
         if (e4 * 4 + u < n) out[e4 * 4 + u] = dc.train ? (rng_keep(r, u, dc.thr16) ? 1 : 0) : 1;
 }
@@ -132,7 +132,7 @@ __global__ void k_mask_attn(DropCfg dc, uint32_t site, int64_t BH, int L, uint8_
     const int j = (int)(e % L);
     const int64_t bi = e / L;   // bh*L + i
     const int Lp = (L + 3) & ~3;
-    const uint64_t r = rng4(dc.seed, site, ((uint64_t)bi * Lp + j) >> 2);
+    const uint32_t r = rng4(dc.seed, site, ((uint64_t)bi * Lp + j) >> 2);
     out[e] = dc.train ? (rng_keep(r, j & 3, dc.thr16) ? 1 : 0) : 1;
 }
 

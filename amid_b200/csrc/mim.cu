@@ -304,12 +304,22 @@ __global__ void k_meanpool_bwd(const float* __restrict__ du, int64_t B, int n, f
     cur.x = fmaf(g.x, inv, cur.x); cur.y = fmaf(g.y, inv, cur.y); cur.z = fmaf(g.z, inv, cur.z); cur.w = fmaf(g.w, inv, cur.w);
     *dst = cur;
 }
-// dcol[c] = inv * sum_i du[i][c]   (1 CTA, 128 threads, sequential over i)
-__global__ void k_du_colsum(const float* __restrict__ du, int B, float inv, float* __restrict__ dcol) {
-    const int c = threadIdx.x;
+// dcol[c] = inv * sum_i du[i][c]   (1 CTA, 1024 threads = 8 row groups x 128 columns, fixed-order combine)
+__global__ void __launch_bounds__(1024)
+k_du_colsum(const float* __restrict__ du, int B, float inv, float* __restrict__ dcol) {
+    __shared__ float red[8][D];
+    const int c = threadIdx.x & (D - 1), g = threadIdx.x >> 7;
     float s = 0.f;
-    for (int i = 0; i < B; ++i) s += du[(size_t)i * D + c];
-    dcol[c] = s * inv;
+#pragma unroll 8
+    for (int i = g; i < B; i += 8) s += du[(size_t)i * D + c];
+    red[g][c] = s;
+    __syncthreads();
+    if (g == 0) {
+        float t = red[0][c];
+#pragma unroll
+        for (int k = 1; k < 8; ++k) t += red[k][c];
+        dcol[c] = t * inv;
+    }
 }
 
 }  // namespace amid
@@ -411,7 +421,7 @@ extern "C" int amid_meanpool_bwd(const float* du, int32_t B, int32_t n, float de
     }
     if (dcol) {
         AMID_K("k_du_colsum", s);
-        k_du_colsum<<<1, 128, 0, s>>>(du, B, 1.0f / denom, dcol);
+        k_du_colsum<<<1, 1024, 0, s>>>(du, B, 1.0f / denom, dcol);
         AMID_LAUNCH_CHECK("k_du_colsum");
     }
     return 0;

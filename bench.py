@@ -185,6 +185,7 @@ def kernel_work(name, B, L, C):
         "k_ln_qkv_tc": ("flop", 3 * gemm), "k_proj_ffn_tc": ("flop", 3 * gemm), "k_ffn_bwd_tc": ("flop", 3 * gemm),
         "k_qkv_bwd_tc": ("flop", 3 * gemm), "k_wgrad_tc": ("flop", 6 * gemm),
         "k_attn_fwd": ("flop", attn_full), "k_attn_bwd": ("flop", 2.5 * attn_full),
+        "k_attn_fwd_mma": ("flop", attn_full), "k_attn_bwd_mma": ("flop", 2.5 * attn_full),
         "k_seq_embed": ("byte", rows_seq * (2 * D * 4 + 8)), "k_gather": ("byte", rows_items * (2 * D * 4 + 8)),
         "k_mim_scores": ("flop", 2.0 * B * L * L * D),
     }
