@@ -84,7 +84,6 @@ _SIGS = {
     "amid_adam_rows_flush": (c_int32, [P, P, P, P, c_int64, c_int32, c_float, c_float, c_float, c_float, P]),
     "amid_rank_counts": (c_int32, [P, c_int64, c_int32, c_float, P, P, P]),
     "amid_tc_linear_test": (c_int32, [P, P, P, c_int32, P, P]),
-    "amid_tc_wgrad_test": (c_int32, [P, P, c_int32, P, c_int32, P]),
     "amid_dropout_mask_feature": (c_int32, [POINTER(Dropout), c_uint32, c_int64, P, P]),
     "amid_dropout_mask_attn": (c_int32, [POINTER(Dropout), c_uint32, c_int32, c_int32, P, P]),
 }

@@ -15,7 +15,8 @@ namespace amid {
 namespace attn {
 
 constexpr int LDS = 20;          // smem row stride (floats)
-constexpr int NW = 4;            // warps per CTA
+constexpr int NW = 4;            // warps per CTA (forward)
+constexpr int NWB = 8;           // warps per CTA (backward: 2 x ntile work items)
 constexpr float LOG2E = 1.4426950408889634f;
 
 __device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
@@ -25,10 +26,22 @@ __device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], 
         : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 __device__ __forceinline__ uint32_t fbits(float x) { return __float_as_uint(x); }
+// 2^x for x <= 0 (softmax numerators): one MUFU, inputs below -126 flush to 0
+__device__ __forceinline__ float ex2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+// dynamic work queue of a CTA: warps take items in order (callers order items by decreasing cost)
+__device__ __forceinline__ int next_item(int* counter, int lane) {
+    int it = 0;
+    if (lane == 0) it = atomicAdd(counter, 1);
+    return __shfl_sync(0xffffffffu, it, 0);
+}
 
 // head slice [L,16] of a [M,128] tensor -> smem [L][LDS]
 __device__ __forceinline__ void stage(float* s, const float* __restrict__ g, int L) {
-    for (int idx = threadIdx.x; idx < L * 4; idx += NW * 32) {
+    for (int idx = threadIdx.x; idx < L * 4; idx += blockDim.x) {
         const int r = idx >> 2, c4 = idx & 3;
         *reinterpret_cast<float4*>(s + r * LDS + c4 * 4) = __ldg(reinterpret_cast<const float4*>(g + (size_t)r * D) + c4);
     }
@@ -42,6 +55,18 @@ __device__ __forceinline__ void load_a16(uint32_t (&a)[2][4], const float* s, in
         a[ks][1] = fbits(s[rb * LDS + 8 * ks + t]);
         a[ks][2] = fbits(s[ra * LDS + 8 * ks + t + 4]);
         a[ks][3] = fbits(s[rb * LDS + 8 * ks + t + 4]);
+    }
+}
+// the same from global memory (row stride D): used where the matrix is only ever an A operand
+__device__ __forceinline__ void load_a16_g(uint32_t (&a)[2][4], const float* __restrict__ p, int r0, int L, int g, int t) {
+    const float* pa = p + (size_t)min(r0 + g, L - 1) * D;
+    const float* pb = p + (size_t)min(r0 + g + 8, L - 1) * D;
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks) {
+        a[ks][0] = fbits(__ldg(pa + 8 * ks + t));
+        a[ks][1] = fbits(__ldg(pb + 8 * ks + t));
+        a[ks][2] = fbits(__ldg(pa + 8 * ks + t + 4));
+        a[ks][3] = fbits(__ldg(pb + 8 * ks + t + 4));
     }
 }
 // D[16 x 8] = A[16 x 16] * X[n0..n0+8][16]^T   (X rows are the n index; k = feature)
@@ -79,26 +104,27 @@ __global__ void __launch_bounds__(NW * 32)
 k_attn_fwd_mma(const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v,
                float* __restrict__ o, float* __restrict__ lse, int L, DropCfg dc, uint32_t site) {
     extern __shared__ __align__(16) float smem[];
-    float* qs = smem;
-    float* ks = qs + L * LDS;
+    __shared__ int queue;
+    float* ks = smem;
     float* vs = ks + L * LDS;
     const int bh = blockIdx.x, b = bh / H, hd = bh % H;
     const size_t base = (size_t)b * L * D + hd * DH;
-    stage(qs, q + base, L);
+    if (threadIdx.x == 0) queue = 0;
     stage(ks, k + base, L);
     stage(vs, v + base, L);
     __syncthreads();
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
     const int ntile = (L + 15) / 16, Lp = (L + 3) & ~3;
     const uint64_t bhL = (uint64_t)bh * L;
-    // balanced causal schedule: warp w takes row tiles w, w+4, ... from the front and their mirrors from the back
-    for (int pi = warp; pi < (ntile + 1) / 2; pi += NW) {
-        for (int side = 0; side < 2; ++side) {
-            const int rt = side == 0 ? pi : ntile - 1 - pi;
-            if (side == 1 && rt == pi) break;
+    // causal work per row tile grows with its index: hand tiles out from the last (heaviest) to the first
+    for (;;) {
+        {
+            const int item = next_item(&queue, lane);
+            if (item >= ntile) break;
+            const int rt = ntile - 1 - item;
             const int r0 = rt * 16;
             uint32_t aq[2][4];
-            load_a16(aq, qs, r0, L, g, t);
+            load_a16_g(aq, q + base, r0, L, g, t);
             float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
             float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
             const int row_a = r0 + g, row_b = r0 + g + 8;
@@ -122,7 +148,7 @@ k_attn_fwd_mma(const float* __restrict__ q, const float* __restrict__ k, const f
                 const float mn0 = fmaxf(m0, quad_max(mx0)), mn1 = fmaxf(m1, quad_max(mx1));
                 // rows beyond the sequence (clamped loads) can stay at -inf for a while: guard the subtraction
                 const float sub0 = mn0 == -INFINITY ? 0.f : mn0, sub1 = mn1 == -INFINITY ? 0.f : mn1;
-                const float c0 = exp2f((m0 - sub0) * LOG2E), c1 = exp2f((m1 - sub1) * LOG2E);
+                const float c0 = ex2((m0 - sub0) * LOG2E), c1 = ex2((m1 - sub1) * LOG2E);
                 l0 *= c0; l1 *= c1;
 #pragma unroll
                 for (int dt = 0; dt < 2; ++dt) { acc[dt][0] *= c0; acc[dt][1] *= c0; acc[dt][2] *= c1; acc[dt][3] *= c1; }
@@ -132,8 +158,8 @@ k_attn_fwd_mma(const float* __restrict__ q, const float* __restrict__ k, const f
                     const int n0 = kb + 8 * nt;
                     if (n0 >= kend) continue;                               // warp-uniform
                     float p[4];
-                    p[0] = exp2f((s[nt][0] - sub0) * LOG2E); p[1] = exp2f((s[nt][1] - sub0) * LOG2E);
-                    p[2] = exp2f((s[nt][2] - sub1) * LOG2E); p[3] = exp2f((s[nt][3] - sub1) * LOG2E);
+                    p[0] = ex2((s[nt][0] - sub0) * LOG2E); p[1] = ex2((s[nt][1] - sub0) * LOG2E);
+                    p[2] = ex2((s[nt][2] - sub1) * LOG2E); p[3] = ex2((s[nt][3] - sub1) * LOG2E);
                     l0 += p[0] + p[1]; l1 += p[2] + p[3];
                     if (dc.train) {
                         bool ka, kb_, kc, kd;
@@ -166,11 +192,13 @@ k_attn_fwd_mma(const float* __restrict__ q, const float* __restrict__ k, const f
 // ----------------------------------------------------------------------------------------------
 // backward: pass A (query tiles -> dq), pass B (key tiles -> dk, dv); P recomputed from lse
 // ----------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(NW * 32)
+__global__ void __launch_bounds__(NWB * 32)
 k_attn_bwd_mma(const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v,
                const float* __restrict__ o, const float* __restrict__ lse, const float* __restrict__ dO,
                float* __restrict__ dq, float* __restrict__ dk, float* __restrict__ dv, int L, DropCfg dc, uint32_t site) {
     extern __shared__ __align__(16) float smem[];
+    __shared__ int queue;
+    if (threadIdx.x == 0) queue = 0;
     float* qs = smem;
     float* ks = qs + L * LDS;
     float* vs = ks + L * LDS;
@@ -183,7 +211,7 @@ k_attn_bwd_mma(const float* __restrict__ q, const float* __restrict__ k, const f
     stage(ks, k + base, L);
     stage(vs, v + base, L);
     stage(gs, dO + base, L);
-    for (int i = threadIdx.x; i < L; i += NW * 32) {
+    for (int i = threadIdx.x; i < L; i += blockDim.x) {
         const float4* po = reinterpret_cast<const float4*>(o + base + (size_t)i * D);
         const float4* pg = reinterpret_cast<const float4*>(dO + base + (size_t)i * D);
         float s = 0.f;
@@ -196,14 +224,16 @@ k_attn_bwd_mma(const float* __restrict__ q, const float* __restrict__ k, const f
         ls[i] = lse[(size_t)bh * L + i];
     }
     __syncthreads();
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
     const int ntile = (L + 15) / 16, Lp = (L + 3) & ~3;
     const uint64_t bhL = (uint64_t)bh * L;
-    // ---------------- pass A: dq[i] = 0.25 * sum_j dS_ij k_j
-    for (int pi = warp; pi < (ntile + 1) / 2; pi += NW) {
-        for (int side = 0; side < 2; ++side) {
-            const int rt = side == 0 ? pi : ntile - 1 - pi;
-            if (side == 1 && rt == pi) break;
+    // Work items, heaviest first: item 2n = pass A on query tile ntile-1-n, item 2n+1 = pass B on key tile n.
+    for (;;) {
+        const int item = next_item(&queue, lane);
+        if (item >= 2 * ntile) break;
+        if ((item & 1) == 0) {
+            // ---------------- pass A: dq[i] = 0.25 * sum_j dS_ij k_j
+            const int rt = ntile - 1 - (item >> 1);
             const int r0 = rt * 16;
             uint32_t aq[2][4], ag[2][4];
             load_a16(aq, qs, r0, L, g, t);
@@ -222,10 +252,10 @@ k_attn_bwd_mma(const float* __restrict__ q, const float* __restrict__ k, const f
                 if (dc.train) { keep2(dc, site, bhL, ra, c, Lp, k0, k1); keep2(dc, site, bhL, rb, c, Lp, k2, k3); }
                 const float sc = dc.train ? dc.scale : 1.0f;
                 float ds[4];
-                ds[0] = (c <= row_a && c < L) ? exp2f((s[0] - la) * LOG2E) * ((k0 ? dp[0] * sc : 0.f) - Da) : 0.f;
-                ds[1] = (c + 1 <= row_a && c + 1 < L) ? exp2f((s[1] - la) * LOG2E) * ((k1 ? dp[1] * sc : 0.f) - Da) : 0.f;
-                ds[2] = (c <= row_b && c < L) ? exp2f((s[2] - lb) * LOG2E) * ((k2 ? dp[2] * sc : 0.f) - Db) : 0.f;
-                ds[3] = (c + 1 <= row_b && c + 1 < L) ? exp2f((s[3] - lb) * LOG2E) * ((k3 ? dp[3] * sc : 0.f) - Db) : 0.f;
+                ds[0] = (c <= row_a && c < L) ? ex2((s[0] - la) * LOG2E) * ((k0 ? dp[0] * sc : 0.f) - Da) : 0.f;
+                ds[1] = (c + 1 <= row_a && c + 1 < L) ? ex2((s[1] - la) * LOG2E) * ((k1 ? dp[1] * sc : 0.f) - Da) : 0.f;
+                ds[2] = (c <= row_b && c < L) ? ex2((s[2] - lb) * LOG2E) * ((k2 ? dp[2] * sc : 0.f) - Db) : 0.f;
+                ds[3] = (c + 1 <= row_b && c + 1 < L) ? ex2((s[3] - lb) * LOG2E) * ((k3 ? dp[3] * sc : 0.f) - Db) : 0.f;
                 mma_px(acc, ds, ks, n0, L, g, t);
             }
             if (row_a < L) {
@@ -238,13 +268,9 @@ k_attn_bwd_mma(const float* __restrict__ q, const float* __restrict__ k, const f
                 for (int dt = 0; dt < 2; ++dt)
                     *reinterpret_cast<float2*>(dq + base + (size_t)row_b * D + 8 * dt + 2 * t) = make_float2(acc[dt][2] * 0.25f, acc[dt][3] * 0.25f);
             }
-        }
-    }
-    // ---------------- pass B: key tiles; S^T = K Q^T so that P^T / dS^T land in accumulator layout
-    for (int pi = warp; pi < (ntile + 1) / 2; pi += NW) {
-        for (int side = 0; side < 2; ++side) {
-            const int kt = side == 0 ? pi : ntile - 1 - pi;
-            if (side == 1 && kt == pi) break;
+        } else {
+            // ---------------- pass B: key tile; S^T = K Q^T so that P^T / dS^T land in accumulator layout
+            const int kt = item >> 1;
             const int j0 = kt * 16;
             uint32_t ak[2][4], av[2][4];
             load_a16(ak, ks, j0, L, g, t);
@@ -269,7 +295,7 @@ k_attn_bwd_mma(const float* __restrict__ q, const float* __restrict__ k, const f
                     const float lq = (e & 1) ? lqb : lqa, Dq = (e & 1) ? Dqb : Dqa;
                     float pe = 0.f, de = 0.f;
                     if (key <= qi && qi < L && key < L) {
-                        const float p = exp2f((st[e] - lq) * LOG2E);
+                        const float p = ex2((st[e] - lq) * LOG2E);
                         bool kp = true;
                         if (dc.train) {
                             const uint32_t r = rng4(dc.seed, site, ((bhL + qi) * Lp + key) >> 2);

@@ -698,19 +698,22 @@ __global__ void k_reduce_partials(const float* __restrict__ part, int S, int n, 
     for (int i = 0; i < S; ++i) s += p[(size_t)i * n];
     outs.out[blockIdx.y][e] = s;
 }
-// LN partials are [S][256] = (dw[128], db[128]) per tile.  1024 threads: 4 row groups x 256 columns,
-// each group sums its rows in order, then the 4 group sums are added in fixed order (deterministic).
-__global__ void __launch_bounds__(1024)
+// LN partials are [S][256] = (dw[128], db[128]) per tile.  16 CTAs x 256 threads: a CTA owns 16
+// columns, its 16 row groups sum their rows in order, then the group sums are added in fixed order.
+__global__ void __launch_bounds__(256)
 k_reduce_ln(const float* __restrict__ part, int S, float* __restrict__ dw, float* __restrict__ db) {
-    __shared__ float red[4][2 * D];
-    const int e = threadIdx.x & (2 * D - 1), g = threadIdx.x >> 8;
+    __shared__ float red[16][16];
+    const int c = threadIdx.x & 15, g = threadIdx.x >> 4;
+    const int e = blockIdx.x * 16 + c;
     float s = 0.f;
 #pragma unroll 8
-    for (int i = g; i < S; i += 4) s += part[(size_t)i * 2 * D + e];
-    red[g][e] = s;
+    for (int i = g; i < S; i += 16) s += part[(size_t)i * 2 * D + e];
+    red[g][c] = s;
     __syncthreads();
     if (g == 0) {
-        const float t = (red[0][e] + red[1][e]) + (red[2][e] + red[3][e]);
+        float t = red[0][c];
+#pragma unroll
+        for (int k = 1; k < 16; ++k) t += red[k][c];
         if (e < D) dw[e] = t; else db[e - D] = t;
     }
 }
@@ -763,7 +766,7 @@ static int encoder_fwd_impl(const amid_encoder_tensors* P, const float* x0, cons
     if (use_tc) {   // tcgen05 path: the weights are consumed K-major in their natural [out][in] layout
         if (int rc = ensure_smem((const void*)tcenc::k_ln_qkv_tc, tcenc::CHAIN_SMEM)) return rc;
         if (int rc = ensure_smem((const void*)tcenc::k_proj_ffn_tc, tcenc::CHAIN_SMEM)) return rc;
-        const size_t mma_smem = (size_t)3 * L * attn::LDS * sizeof(float);
+        const size_t mma_smem = (size_t)2 * L * attn::LDS * sizeof(float);
         if (int rc = ensure_smem((const void*)attn::k_attn_fwd_mma, mma_smem)) return rc;
         const float* xin = x0;
         for (int i = 0; i < 2; ++i) {
@@ -916,7 +919,7 @@ static int encoder_bwd_impl(const amid_encoder_tensors* P, const float* x0, cons
     k_ln_bwd<<<tiles, NT, 0, stream>>>(d_enc, S->xout[1], S->st3, P->ln3_w, M, dxa, lnp0);
     AMID_LAUNCH_CHECK("k_ln_bwd");
     AMID_K("k_reduce_ln", stream);
-    k_reduce_ln<<<1, 1024, 0, stream>>>(lnp0, tiles, G->ln3_w, G->ln3_b);
+    k_reduce_ln<<<16, 256, 0, stream>>>(lnp0, tiles, G->ln3_w, G->ln3_b);
     AMID_LAUNCH_CHECK("k_reduce_ln");
 
     for (int i = 1; i >= 0; --i) {
@@ -938,13 +941,13 @@ static int encoder_bwd_impl(const amid_encoder_tensors* P, const float* x0, cons
         AMID_LAUNCH_CHECK("k_ffn_bwd");
         }
         AMID_K("k_reduce_ln", stream);
-        k_reduce_ln<<<1, 1024, 0, stream>>>(lnp0, tiles, G->ln2_w[i], G->ln2_b[i]);
+        k_reduce_ln<<<16, 256, 0, stream>>>(lnp0, tiles, G->ln2_w[i], G->ln2_b[i]);
         AMID_LAUNCH_CHECK("k_reduce_ln");
         if (use_tc) {
             const size_t mma_smem = (size_t)(4 * L * attn::LDS + 2 * L) * sizeof(float);
             if (int rc = ensure_smem((const void*)attn::k_attn_bwd_mma, mma_smem)) return rc;
             AMID_K("k_attn_bwd_mma", stream);
-            attn::k_attn_bwd_mma<<<B * H, attn::NW * 32, mma_smem, stream>>>(S->q[i], S->k[i], S->v[i], S->o[i], S->lse[i], dO,
+            attn::k_attn_bwd_mma<<<B * H, attn::NWB * 32, mma_smem, stream>>>(S->q[i], S->k[i], S->v[i], S->o[i], S->lse[i], dO,
                                                                              dq, dk, dv, L, dc, dc.site_base + site_attn(i));
             AMID_LAUNCH_CHECK("k_attn_bwd_mma");
         } else {
@@ -967,7 +970,7 @@ static int encoder_bwd_impl(const amid_encoder_tensors* P, const float* x0, cons
         AMID_LAUNCH_CHECK("k_qkv_bwd");
         }
         AMID_K("k_reduce_ln", stream);
-        k_reduce_ln<<<1, 1024, 0, stream>>>(lnp1, tiles, G->ln1_w[i], G->ln1_b[i]);
+        k_reduce_ln<<<16, 256, 0, stream>>>(lnp1, tiles, G->ln1_w[i], G->ln1_b[i]);
         AMID_LAUNCH_CHECK("k_reduce_ln");
         // weight gradients of the block, one launch: W2, W1, Wo, Wq, Wk, Wv
         WgradJobs wj;

@@ -12,7 +12,8 @@ namespace amid {
 namespace tcenc {
 using namespace tc;
 
-constexpr size_t CHAIN_SMEM = 3 * (size_t)TILE_BYTES + 1024;               // A tile + 2 weight buffers
+constexpr int WSTAGE_FLOATS = 32 * 32;                                     // per-warp transposing stage (4 KB)
+constexpr size_t CHAIN_SMEM = 2 * (size_t)TILE_BYTES + 8 * WSTAGE_FLOATS * 4 + 1024;   // A tile + weight tile + 8 warp stages
 constexpr int ONES_BYTES = 16 * 128 * 4;                                   // [16 rows][128] K-major
 constexpr size_t WGRAD_SMEM = 2 * (size_t)TILE_BYTES + ONES_BYTES + 1024;
 
@@ -24,12 +25,13 @@ struct Shared {
 };
 
 struct Epi {
-    int warp, lane, row, cb;
+    int warp, lane, row, cb, wrow0;
     uint32_t lane_addr;
     __device__ Epi() {
         warp = threadIdx.x >> 5; lane = threadIdx.x & 31;
-        row = 32 * (warp & 3) + lane; cb = 64 * (warp >> 2);
-        lane_addr = (uint32_t)(32 * (warp & 3)) << 16;
+        wrow0 = 32 * (warp & 3);
+        row = wrow0 + lane; cb = 64 * (warp >> 2);
+        lane_addr = (uint32_t)wrow0 << 16;
     }
 };
 
@@ -55,10 +57,9 @@ __device__ __forceinline__ void load_w_async(uint8_t* buf, const float* __restri
     cp_async_commit();
 }
 // make smem operands visible to the tensor core, issue one 128x128x128 GEMM, wait for it
-template <int PENDING>
 __device__ __forceinline__ void run_gemm(Shared& sh, uint32_t acc_col, const uint8_t* A, const uint8_t* W, bool accumulate,
                                          uint32_t& phase) {
-    cp_async_wait<PENDING>();
+    cp_async_wait<0>();
     fence_async_smem();
     fence_before();
     __syncthreads();
@@ -71,6 +72,46 @@ __device__ __forceinline__ void run_gemm(Shared& sh, uint32_t acc_col, const uin
     phase ^= 1;
     fence_after();
 }
+// ---- coalesced global I/O for the thread-per-row epilogues: a 32x32 chunk (this warp's 32 rows x
+// 32 columns) goes through a warp-private swizzled stage so that the global side is 128-byte
+// row segments (4 rows per instruction) while the register side stays one row per thread.
+__device__ __forceinline__ int ws_off(int r, int u) { return r * 32 + ((u ^ (r & 7)) << 2); }
+// registers (lane = row) -> global: g points at (first row of the warp, first column of the chunk)
+__device__ __forceinline__ void warp_store32(float* buf, int lane, const float (&v)[32], float* __restrict__ g, int rows_valid) {
+#pragma unroll
+    for (int u = 0; u < 8; ++u) *reinterpret_cast<float4*>(buf + ws_off(lane, u)) = make_float4(v[4 * u], v[4 * u + 1], v[4 * u + 2], v[4 * u + 3]);
+    __syncwarp();
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+        const int r = it * 4 + (lane >> 3), u = lane & 7;
+        const float4 x = *reinterpret_cast<const float4*>(buf + ws_off(r, u));
+        if (r < rows_valid) *reinterpret_cast<float4*>(g + (size_t)r * D + u * 4) = x;
+    }
+    __syncwarp();
+}
+// global -> registers (lane = row); rows >= rows_valid read as zero
+__device__ __forceinline__ void warp_load32(float* buf, int lane, const float* __restrict__ g, int rows_valid, float (&v)[32]) {
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+        const int r = it * 4 + (lane >> 3), u = lane & 7;
+        float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (r < rows_valid) x = *reinterpret_cast<const float4*>(g + (size_t)r * D + u * 4);
+        *reinterpret_cast<float4*>(buf + ws_off(r, u)) = x;
+    }
+    __syncwarp();
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+        const float4 x = *reinterpret_cast<const float4*>(buf + ws_off(lane, u));
+        v[4 * u] = x.x; v[4 * u + 1] = x.y; v[4 * u + 2] = x.z; v[4 * u + 3] = x.w;
+    }
+    __syncwarp();
+}
+// registers (lane = row) -> the operand tile A, columns [c0, c0+32)
+__device__ __forceinline__ void tile_store32(uint8_t* A, int row, int c0, const float (&v)[32]) {
+#pragma unroll
+    for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(A + tile_off4(row, (c0 + i) >> 2)) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+}
+
 // sum of a per-thread partial over the two threads that share a row (fixed order)
 __device__ __forceinline__ float row_sum(Shared& sh, const Epi& e, int slot, float partial) {
     sh.xch[slot][e.cb >> 6][e.row] = partial;
@@ -109,6 +150,23 @@ __device__ __forceinline__ void flush_ln_partials(Shared& sh, float* __restrict_
 }
 
 // ----------------------------------------------------------------------------------------------
+// Shared structure of the four chain kernels
+//   smem: A (operand tile) | W (weight tile) | 8 warp stages.  The next stage's weight is fetched
+//   with cp.async right after the current MMA has completed, so it overlaps the epilogue.
+// ----------------------------------------------------------------------------------------------
+struct ChainSmem {
+    uint8_t* A;
+    uint8_t* W;
+    float* stage;     // this warp's 32x32 transposing stage
+    __device__ ChainSmem(uint8_t* raw) {
+        A = align1k(raw);
+        W = A + TILE_BYTES;
+        stage = reinterpret_cast<float*>(W + TILE_BYTES) + (threadIdx.x >> 5) * WSTAGE_FLOATS;
+    }
+};
+__device__ __forceinline__ int rows_valid(int row0, const Epi& e, int M) { return max(0, min(32, M - (row0 + e.wrow0))); }
+
+// ----------------------------------------------------------------------------------------------
 // forward 1: k, v from x; LN1 in place; q from LN1(x)
 // ----------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256, 1)
@@ -118,67 +176,67 @@ k_ln_qkv_tc(const float* __restrict__ x, int M, const float* __restrict__ ln_w, 
             float* __restrict__ k, float* __restrict__ v) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ Shared sh;
-    uint8_t* A = align1k(smem_raw);
-    uint8_t* Wb[2] = {A + TILE_BYTES, A + 2 * TILE_BYTES};
+    ChainSmem sm(smem_raw);
     const int row0 = blockIdx.x * 128;
     setup(sh, 128);
-    load_w_async(Wb[0], Wk);
-    fill_tile(A, x, row0, M);
+    load_w_async(sm.W, Wk);
+    fill_tile(sm.A, x, row0, M);
     Epi e;
     const int gr = row0 + e.row;
     const bool valid = gr < M;
+    const int rv = rows_valid(row0, e, M);
+    const size_t wbase = (size_t)(row0 + e.wrow0) * D;
     uint32_t phase = 0;
-    // ---- k and v from the raw tile
     float* outs[2] = {k, v};
 #pragma unroll 1
-    for (int g = 0; g < 2; ++g) {
-        load_w_async(Wb[(g + 1) & 1], g == 0 ? Wv : Wq);
-        run_gemm<1>(sh, 0, A, Wb[g & 1], false, phase);
+    for (int g = 0; g < 2; ++g) {        // k and v from the raw tile
+        run_gemm(sh, 0, sm.A, sm.W, false, phase);
+        load_w_async(sm.W, g == 0 ? Wv : Wq);
         const uint32_t tm = sh.tmem + e.lane_addr;
 #pragma unroll 1
         for (int half = 0; half < 2; ++half) {
             float a[32];
             const int c0 = e.cb + half * 32;
             tmem_ld32(tm + c0, a);
-            if (valid) {
-                float* dst = outs[g] + (size_t)gr * D + c0;
-                const float* bb = in_b + (g + 1) * D + c0;
+            const float* bb = in_b + (g + 1) * D + c0;
 #pragma unroll
-                for (int i = 0; i < 32; i += 4) {
-                    const float4 b4 = __ldg(reinterpret_cast<const float4*>(bb + i));
-                    *reinterpret_cast<float4*>(dst + i) = make_float4(a[i] + b4.x, a[i + 1] + b4.y, a[i + 2] + b4.z, a[i + 3] + b4.w);
-                }
-            }
+            for (int i = 0; i < 32; ++i) a[i] += __ldg(bb + i);
+            warp_store32(sm.stage, e.lane, a, outs[g] + wbase + c0, rv);
         }
     }
-    // ---- LN1 in place on the tile (the v GEMM has completed, the tile is free)
+    // LN1 in place on the tile (the v GEMM has completed, the tile is free)
+    float mean, rstd;
     {
         float s = 0.f;
 #pragma unroll
-        for (int i = 0; i < 64; i += 4) { const float4 t = ld_tile4(A, e.row, e.cb + i); s += (t.x + t.y) + (t.z + t.w); }
-        const float mean = row_sum(sh, e, 0, s) * (1.0f / D);
+        for (int i = 0; i < 64; i += 4) { const float4 t = ld_tile4(sm.A, e.row, e.cb + i); s += (t.x + t.y) + (t.z + t.w); }
+        mean = row_sum(sh, e, 0, s) * (1.0f / D);
         float ss = 0.f;
 #pragma unroll
         for (int i = 0; i < 64; i += 4) {
-            const float4 t = ld_tile4(A, e.row, e.cb + i);
+            const float4 t = ld_tile4(sm.A, e.row, e.cb + i);
             const float a0 = t.x - mean, a1 = t.y - mean, a2 = t.z - mean, a3 = t.w - mean;
             ss += (a0 * a0 + a1 * a1) + (a2 * a2 + a3 * a3);
         }
-        const float rstd = 1.0f / sqrtf(row_sum(sh, e, 1, ss) * (1.0f / D) + LN_EPS);
+        rstd = 1.0f / sqrtf(row_sum(sh, e, 1, ss) * (1.0f / D) + LN_EPS);
+#pragma unroll 1
+        for (int half = 0; half < 2; ++half) {
+            float a[32];
+            const int c0 = e.cb + half * 32;
 #pragma unroll
-        for (int i = 0; i < 64; i += 4) {
-            const float4 t = ld_tile4(A, e.row, e.cb + i);
-            const float4 w4 = __ldg(reinterpret_cast<const float4*>(ln_w + e.cb + i));
-            const float4 b4 = __ldg(reinterpret_cast<const float4*>(ln_b + e.cb + i));
-            const float4 y = make_float4(fmaf((t.x - mean) * rstd, w4.x, b4.x), fmaf((t.y - mean) * rstd, w4.y, b4.y),
-                                         fmaf((t.z - mean) * rstd, w4.z, b4.z), fmaf((t.w - mean) * rstd, w4.w, b4.w));
-            st_tile4(A, e.row, e.cb + i, y);
-            if (valid) *reinterpret_cast<float4*>(qn + (size_t)gr * D + e.cb + i) = y;
+            for (int i = 0; i < 32; i += 4) {
+                const float4 t = ld_tile4(sm.A, e.row, c0 + i);
+                const float4 w4 = __ldg(reinterpret_cast<const float4*>(ln_w + c0 + i));
+                const float4 b4 = __ldg(reinterpret_cast<const float4*>(ln_b + c0 + i));
+                a[i] = fmaf((t.x - mean) * rstd, w4.x, b4.x); a[i + 1] = fmaf((t.y - mean) * rstd, w4.y, b4.y);
+                a[i + 2] = fmaf((t.z - mean) * rstd, w4.z, b4.z); a[i + 3] = fmaf((t.w - mean) * rstd, w4.w, b4.w);
+            }
+            tile_store32(sm.A, e.row, c0, a);
+            warp_store32(sm.stage, e.lane, a, qn + wbase + c0, rv);
         }
         if (valid && e.cb == 0) { st1[(size_t)gr * 2] = mean; st1[(size_t)gr * 2 + 1] = rstd; }
     }
-    // ---- q = 0.25 (LN1(x) Wq^T + bq)
-    run_gemm<0>(sh, 0, A, Wb[0], false, phase);
+    run_gemm(sh, 0, sm.A, sm.W, false, phase);      // q = 0.25 (LN1(x) Wq^T + bq)
     {
         const uint32_t tm = sh.tmem + e.lane_addr;
 #pragma unroll 1
@@ -186,23 +244,16 @@ k_ln_qkv_tc(const float* __restrict__ x, int M, const float* __restrict__ ln_w, 
             float a[32];
             const int c0 = e.cb + half * 32;
             tmem_ld32(tm + c0, a);
-            if (valid) {
-                float* dst = q + (size_t)gr * D + c0;
 #pragma unroll
-                for (int i = 0; i < 32; i += 4) {
-                    const float4 b4 = __ldg(reinterpret_cast<const float4*>(in_b + c0 + i));
-                    *reinterpret_cast<float4*>(dst + i) = make_float4((a[i] + b4.x) * 0.25f, (a[i + 1] + b4.y) * 0.25f,
-                                                                      (a[i + 2] + b4.z) * 0.25f, (a[i + 3] + b4.w) * 0.25f);
-                }
-            }
+            for (int i = 0; i < 32; ++i) a[i] = (a[i] + __ldg(in_b + c0 + i)) * 0.25f;
+            warp_store32(sm.stage, e.lane, a, q + wbase + c0, rv);
         }
     }
     teardown(sh, sh.tmem, 128);
 }
 
-// LayerNorm of a row held as 2 x 32 registers by this thread and 64 more by its partner
-__device__ __forceinline__ void ln_rows64(Shared& sh, const Epi& e, float (&xr)[64], const float* __restrict__ w,
-                                          const float* __restrict__ b, float& mean, float& rstd) {
+// LayerNorm statistics of a row held as 64 registers by this thread and 64 more by its partner
+__device__ __forceinline__ void ln_stats64(Shared& sh, const Epi& e, const float (&xr)[64], float& mean, float& rstd) {
     float s = 0.f;
 #pragma unroll
     for (int i = 0; i < 64; ++i) s += xr[i];
@@ -211,8 +262,6 @@ __device__ __forceinline__ void ln_rows64(Shared& sh, const Epi& e, float (&xr)[
 #pragma unroll
     for (int i = 0; i < 64; ++i) { const float a = xr[i] - mean; ss = fmaf(a, a, ss); }
     rstd = 1.0f / sqrtf(row_sum(sh, e, 1, ss) * (1.0f / D) + LN_EPS);
-#pragma unroll
-    for (int i = 0; i < 64; ++i) xr[i] = fmaf((xr[i] - mean) * rstd, __ldg(w + e.cb + i), __ldg(b + e.cb + i));
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -228,50 +277,54 @@ k_proj_ffn_tc(const float* __restrict__ o, const float* __restrict__ qn, int M, 
               float* __restrict__ enc, float* __restrict__ st3) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ Shared sh;
-    uint8_t* A = align1k(smem_raw);
-    uint8_t* Wb[2] = {A + TILE_BYTES, A + 2 * TILE_BYTES};
+    ChainSmem sm(smem_raw);
     const int row0 = blockIdx.x * 128;
     setup(sh, 128);
-    load_w_async(Wb[0], Wo);
-    fill_tile(A, o, row0, M);
+    load_w_async(sm.W, Wo);
+    fill_tile(sm.A, o, row0, M);
     Epi e;
     const int gr = row0 + e.row;
     const bool valid = gr < M;
+    const int rv = rows_valid(row0, e, M);
+    const size_t wbase = (size_t)(row0 + e.wrow0) * D;
     uint32_t phase = 0;
+    float yr[64];                                   // LN2 output of this thread's half row, kept for the residual
     // ---- x1 = Qn + o Wo^T + bo ; y = LN2(x1)
-    load_w_async(Wb[1], W1);
-    run_gemm<1>(sh, 0, A, Wb[0], false, phase);
+    run_gemm(sh, 0, sm.A, sm.W, false, phase);
+    load_w_async(sm.W, W1);
     {
         const uint32_t tm = sh.tmem + e.lane_addr;
-        float xr[64];
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            float a[32], r[32];
+            const int c0 = e.cb + half * 32;
+            tmem_ld32(tm + c0, a);
+            warp_load32(sm.stage, e.lane, qn + wbase + c0, rv, r);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) a[i] += __ldg(bo + c0 + i) + r[i];
+            warp_store32(sm.stage, e.lane, a, x1 + wbase + c0, rv);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) yr[half * 32 + i] = a[i];
+        }
+        float mean, rstd;
+        ln_stats64(sh, e, yr, mean, rstd);
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
             float a[32];
-            tmem_ld32(tm + e.cb + half * 32, a);
+            const int c0 = e.cb + half * 32;
 #pragma unroll
-            for (int i = 0; i < 32; ++i) xr[half * 32 + i] = a[i];
-        }
-#pragma unroll
-        for (int i = 0; i < 64; i += 4) {
-            const float4 b4 = __ldg(reinterpret_cast<const float4*>(bo + e.cb + i));
-            float4 r4 = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (valid) r4 = __ldg(reinterpret_cast<const float4*>(qn + (size_t)gr * D + e.cb + i));
-            xr[i] += b4.x + r4.x; xr[i + 1] += b4.y + r4.y; xr[i + 2] += b4.z + r4.z; xr[i + 3] += b4.w + r4.w;
-            if (valid) *reinterpret_cast<float4*>(x1 + (size_t)gr * D + e.cb + i) = make_float4(xr[i], xr[i + 1], xr[i + 2], xr[i + 3]);
-        }
-        float mean, rstd;
-        ln_rows64(sh, e, xr, ln2_w, ln2_b, mean, rstd);
-#pragma unroll
-        for (int i = 0; i < 64; i += 4) {
-            const float4 t = make_float4(xr[i], xr[i + 1], xr[i + 2], xr[i + 3]);
-            st_tile4(A, e.row, e.cb + i, t);
-            if (valid) *reinterpret_cast<float4*>(y + (size_t)gr * D + e.cb + i) = t;
+            for (int i = 0; i < 32; ++i) {
+                a[i] = fmaf((yr[half * 32 + i] - mean) * rstd, __ldg(ln2_w + c0 + i), __ldg(ln2_b + c0 + i));
+                yr[half * 32 + i] = a[i];
+            }
+            tile_store32(sm.A, e.row, c0, a);
+            warp_store32(sm.stage, e.lane, a, y + wbase + c0, rv);
         }
         if (valid && e.cb == 0) { st2[(size_t)gr * 2] = mean; st2[(size_t)gr * 2 + 1] = rstd; }
     }
     // ---- h = relu(dropout1(y W1^T + b1))
-    load_w_async(Wb[0], W2);
-    run_gemm<1>(sh, 0, A, Wb[1], false, phase);
+    run_gemm(sh, 0, sm.A, sm.W, false, phase);
+    load_w_async(sm.W, W2);
     {
         const uint32_t tm = sh.tmem + e.lane_addr;
 #pragma unroll 1
@@ -284,17 +337,16 @@ k_proj_ffn_tc(const float* __restrict__ o, const float* __restrict__ qn, int M, 
                 const float4 b4 = __ldg(reinterpret_cast<const float4*>(b1 + c0 + i));
                 float4 t = make_float4(a[i] + b4.x, a[i + 1] + b4.y, a[i + 2] + b4.z, a[i + 3] + b4.w);
                 if (dc.train) t = drop4(t, dc, site1, (uint64_t)gr * D + c0 + i);
-                t = make_float4(fmaxf(t.x, 0.f), fmaxf(t.y, 0.f), fmaxf(t.z, 0.f), fmaxf(t.w, 0.f));
-                st_tile4(A, e.row, c0 + i, t);
-                if (valid) *reinterpret_cast<float4*>(h + (size_t)gr * D + c0 + i) = t;
+                a[i] = fmaxf(t.x, 0.f); a[i + 1] = fmaxf(t.y, 0.f); a[i + 2] = fmaxf(t.z, 0.f); a[i + 3] = fmaxf(t.w, 0.f);
             }
+            tile_store32(sm.A, e.row, c0, a);
+            warp_store32(sm.stage, e.lane, a, h + wbase + c0, rv);
         }
     }
     // ---- xout = (dropout2(h W2^T + b2) + y) * ~tmask  (+ last LayerNorm)
-    run_gemm<0>(sh, 0, A, Wb[0], false, phase);
+    run_gemm(sh, 0, sm.A, sm.W, false, phase);
     {
         const uint32_t tm = sh.tmem + e.lane_addr;
-        float xr[64];
         uint4 tw = make_uint4(0u, 0u, 0u, 0u);
         if (valid) tw = __ldg(reinterpret_cast<const uint4*>(tmask) + gr);
 #pragma unroll
@@ -307,23 +359,26 @@ k_proj_ffn_tc(const float* __restrict__ o, const float* __restrict__ qn, int M, 
                 const float4 b4 = __ldg(reinterpret_cast<const float4*>(b2 + c0 + i));
                 float4 t = make_float4(a[i] + b4.x, a[i + 1] + b4.y, a[i + 2] + b4.z, a[i + 3] + b4.w);
                 if (dc.train) t = drop4(t, dc, site2, (uint64_t)gr * D + c0 + i);
-                float4 yy = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (valid) yy = *reinterpret_cast<const float4*>(y + (size_t)gr * D + c0 + i);
-                t = make_float4(t.x + yy.x, t.y + yy.y, t.z + yy.z, t.w + yy.w);
+                t = make_float4(t.x + yr[half * 32 + i], t.y + yr[half * 32 + i + 1], t.z + yr[half * 32 + i + 2], t.w + yr[half * 32 + i + 3]);
                 t = apply_tmask(t, tw, (c0 + i) >> 2);
-                if (valid) *reinterpret_cast<float4*>(xout + (size_t)gr * D + c0 + i) = t;
-                xr[half * 32 + i] = t.x; xr[half * 32 + i + 1] = t.y; xr[half * 32 + i + 2] = t.z; xr[half * 32 + i + 3] = t.w;
+                a[i] = t.x; a[i + 1] = t.y; a[i + 2] = t.z; a[i + 3] = t.w;
             }
-        }
-        if (enc) {   // uniform
-            float mean, rstd;
-            ln_rows64(sh, e, xr, ln3_w, ln3_b, mean, rstd);
-            if (valid) {
+            warp_store32(sm.stage, e.lane, a, xout + wbase + c0, rv);
 #pragma unroll
-                for (int i = 0; i < 64; i += 4)
-                    *reinterpret_cast<float4*>(enc + (size_t)gr * D + e.cb + i) = make_float4(xr[i], xr[i + 1], xr[i + 2], xr[i + 3]);
-                if (e.cb == 0) { st3[(size_t)gr * 2] = mean; st3[(size_t)gr * 2 + 1] = rstd; }
+            for (int i = 0; i < 32; ++i) yr[half * 32 + i] = a[i];
+        }
+        if (enc) {   // uniform: last_layernorm (model_seq.py:385)
+            float mean, rstd;
+            ln_stats64(sh, e, yr, mean, rstd);
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                float a[32];
+                const int c0 = e.cb + half * 32;
+#pragma unroll
+                for (int i = 0; i < 32; ++i) a[i] = fmaf((yr[half * 32 + i] - mean) * rstd, __ldg(ln3_w + c0 + i), __ldg(ln3_b + c0 + i));
+                warp_store32(sm.stage, e.lane, a, enc + wbase + c0, rv);
             }
+            if (valid && e.cb == 0) { st3[(size_t)gr * 2] = mean; st3[(size_t)gr * 2 + 1] = rstd; }
         }
     }
     teardown(sh, sh.tmem, 128);
@@ -340,12 +395,11 @@ k_ffn_bwd_tc(const float* __restrict__ dxo, const float* __restrict__ h, const f
              float* __restrict__ dO, float* __restrict__ ln_part) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ Shared sh;
-    uint8_t* A = align1k(smem_raw);
-    uint8_t* Wb[2] = {A + TILE_BYTES, A + 2 * TILE_BYTES};
+    ChainSmem sm(smem_raw);
     const int row0 = blockIdx.x * 128;
     setup(sh, 128);
-    load_w_async(Wb[0], W2t);
-    // A = do2 = dropout2-mask * (dxo * ~tmask)
+    load_w_async(sm.W, W2t);
+    // A = do2 = dropout2-mask * (dxo * ~tmask)   (warp per row: coalesced)
 #pragma unroll 2
     for (int idx = threadIdx.x; idx < 128 * 32; idx += 256) {
         const int r = idx >> 5, c4 = idx & 31, grr = row0 + r;
@@ -356,98 +410,89 @@ k_ffn_bwd_tc(const float* __restrict__ dxo, const float* __restrict__ h, const f
             if (dc.train) g = drop4(g, dc, site2, (uint64_t)grr * D + c4 * 4);
             *(reinterpret_cast<float4*>(do2 + (size_t)grr * D) + c4) = g;
         }
-        *reinterpret_cast<float4*>(A + tile_off4(r, c4)) = g;
+        *reinterpret_cast<float4*>(sm.A + tile_off4(r, c4)) = g;
     }
     Epi e;
     const int gr = row0 + e.row;
     const bool valid = gr < M;
+    const int rv = rows_valid(row0, e, M);
+    const size_t wbase = (size_t)(row0 + e.wrow0) * D;
     uint32_t phase = 0;
     const float sc = dc.train ? dc.scale : 1.0f;
     // ---- dhpre = (do2 W2) * scale * [h > 0]
-    load_w_async(Wb[1], W1t);
-    run_gemm<1>(sh, 0, A, Wb[0], false, phase);
+    run_gemm(sh, 0, sm.A, sm.W, false, phase);
+    load_w_async(sm.W, W1t);
     {
         const uint32_t tm = sh.tmem + e.lane_addr;
 #pragma unroll 1
         for (int half = 0; half < 2; ++half) {
-            float a[32];
+            float a[32], hh[32];
             const int c0 = e.cb + half * 32;
             tmem_ld32(tm + c0, a);
+            warp_load32(sm.stage, e.lane, h + wbase + c0, rv, hh);
 #pragma unroll
-            for (int i = 0; i < 32; i += 4) {
-                float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (valid) {
-                    const float4 hh = __ldg(reinterpret_cast<const float4*>(h + (size_t)gr * D + c0 + i));
-                    t = make_float4(hh.x > 0.f ? a[i] * sc : 0.f, hh.y > 0.f ? a[i + 1] * sc : 0.f,
-                                    hh.z > 0.f ? a[i + 2] * sc : 0.f, hh.w > 0.f ? a[i + 3] * sc : 0.f);
-                    *reinterpret_cast<float4*>(dhpre + (size_t)gr * D + c0 + i) = t;
-                }
-                st_tile4(A, e.row, c0 + i, t);
-            }
+            for (int i = 0; i < 32; ++i) a[i] = hh[i] > 0.f ? a[i] * sc : 0.f;
+            tile_store32(sm.A, e.row, c0, a);
+            warp_store32(sm.stage, e.lane, a, dhpre + wbase + c0, rv);
         }
     }
     // ---- dy = dhpre W1 + g ; LN2 backward -> dx1
-    load_w_async(Wb[0], Wot);
-    run_gemm<1>(sh, 0, A, Wb[1], false, phase);
+    run_gemm(sh, 0, sm.A, sm.W, false, phase);
+    load_w_async(sm.W, Wot);
     {
         const uint32_t tm = sh.tmem + e.lane_addr;
         float mean = 0.f, rstd = 0.f;
         uint4 tw = make_uint4(0u, 0u, 0u, 0u);
         if (valid) { mean = st2[(size_t)gr * 2]; rstd = st2[(size_t)gr * 2 + 1]; tw = __ldg(reinterpret_cast<const uint4*>(tmask) + gr); }
+        float dy[64], xh[64];
         float p1 = 0.f, p2 = 0.f;
-#pragma unroll 1
-        for (int half = 0; half < 2; ++half) {     // pass 1: row reductions
-            float a[32];
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            float a[32], g[32], xv[32];
             const int c0 = e.cb + half * 32;
             tmem_ld32(tm + c0, a);
-            if (valid) {
+            warp_load32(sm.stage, e.lane, dxo + wbase + c0, rv, g);
+            warp_load32(sm.stage, e.lane, x1 + wbase + c0, rv, xv);
 #pragma unroll
-                for (int i = 0; i < 32; i += 4) {
-                    float4 g = __ldg(reinterpret_cast<const float4*>(dxo + (size_t)gr * D + c0 + i));
-                    g = apply_tmask(g, tw, (c0 + i) >> 2);
-                    const float4 xv = __ldg(reinterpret_cast<const float4*>(x1 + (size_t)gr * D + c0 + i));
-                    const float4 w4 = __ldg(reinterpret_cast<const float4*>(ln2_w + c0 + i));
-                    const float d0 = (a[i] + g.x) * w4.x, d1 = (a[i + 1] + g.y) * w4.y, d2 = (a[i + 2] + g.z) * w4.z, d3 = (a[i + 3] + g.w) * w4.w;
-                    p1 += (d0 + d1) + (d2 + d3);
-                    p2 += d0 * ((xv.x - mean) * rstd) + d1 * ((xv.y - mean) * rstd) + d2 * ((xv.z - mean) * rstd) + d3 * ((xv.w - mean) * rstd);
+            for (int i = 0; i < 32; i += 4) {
+                const float4 gm = apply_tmask(make_float4(g[i], g[i + 1], g[i + 2], g[i + 3]), tw, (c0 + i) >> 2);
+                const float gg[4] = {gm.x, gm.y, gm.z, gm.w};
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const float d = a[i + u] + gg[u];
+                    const float xx = valid ? (xv[i + u] - mean) * rstd : 0.f;
+                    const float dw = d * __ldg(ln2_w + c0 + i + u);
+                    dy[half * 32 + i + u] = d;
+                    xh[half * 32 + i + u] = xx;
+                    p1 += dw;
+                    p2 = fmaf(dw, xx, p2);
                 }
             }
         }
         const float c1 = row_sum(sh, e, 0, p1) * (1.0f / D);
         const float c2 = row_sum(sh, e, 1, p2) * (1.0f / D);
-#pragma unroll 1
-        for (int half = 0; half < 2; ++half) {     // pass 2: dx1 and the LN parameter partials
-            float a[32], pw[32];
-            const int c0 = e.cb + half * 32;
-            tmem_ld32(tm + c0, a);
 #pragma unroll
-            for (int i = 0; i < 32; i += 4) {
-                float4 dx = make_float4(0.f, 0.f, 0.f, 0.f);
-                float4 dyv = dx, xh = dx;
-                if (valid) {
-                    float4 g = __ldg(reinterpret_cast<const float4*>(dxo + (size_t)gr * D + c0 + i));
-                    g = apply_tmask(g, tw, (c0 + i) >> 2);
-                    const float4 xv = __ldg(reinterpret_cast<const float4*>(x1 + (size_t)gr * D + c0 + i));
-                    const float4 w4 = __ldg(reinterpret_cast<const float4*>(ln2_w + c0 + i));
-                    dyv = make_float4(a[i] + g.x, a[i + 1] + g.y, a[i + 2] + g.z, a[i + 3] + g.w);
-                    xh = make_float4((xv.x - mean) * rstd, (xv.y - mean) * rstd, (xv.z - mean) * rstd, (xv.w - mean) * rstd);
-                    dx = make_float4(rstd * (dyv.x * w4.x - c1 - xh.x * c2), rstd * (dyv.y * w4.y - c1 - xh.y * c2),
-                                     rstd * (dyv.z * w4.z - c1 - xh.z * c2), rstd * (dyv.w * w4.w - c1 - xh.w * c2));
-                    *reinterpret_cast<float4*>(dx1 + (size_t)gr * D + c0 + i) = dx;
-                }
-                st_tile4(A, e.row, c0 + i, dx);
-                a[i] = dyv.x; a[i + 1] = dyv.y; a[i + 2] = dyv.z; a[i + 3] = dyv.w;                 // db terms
-                pw[i] = dyv.x * xh.x; pw[i + 1] = dyv.y * xh.y; pw[i + 2] = dyv.z * xh.z; pw[i + 3] = dyv.w * xh.w;   // dw terms
+        for (int half = 0; half < 2; ++half) {
+            float a[32], pw[32], pb[32];
+            const int c0 = e.cb + half * 32;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                const float d = dy[half * 32 + i], xx = xh[half * 32 + i];
+                a[i] = valid ? rstd * (d * __ldg(ln2_w + c0 + i) - c1 - xx * c2) : 0.f;
+                pw[i] = d * xx;
+                pb[i] = d;
             }
+            tile_store32(sm.A, e.row, c0, a);
+            warp_store32(sm.stage, e.lane, a, dx1 + wbase + c0, rv);
             const float sw = warp_colsum32(pw, e.lane);
-            const float sb = warp_colsum32(a, e.lane);
+            const float sb = warp_colsum32(pb, e.lane);
             sh.lnacc[e.warp][0][half * 32 + e.lane] = sw;
             sh.lnacc[e.warp][1][half * 32 + e.lane] = sb;
         }
         flush_ln_partials(sh, ln_part + (size_t)blockIdx.x * 2 * D);
     }
     // ---- dO = dx1 Wo
-    run_gemm<0>(sh, 0, A, Wb[0], false, phase);
+    run_gemm(sh, 0, sm.A, sm.W, false, phase);
     {
         const uint32_t tm = sh.tmem + e.lane_addr;
 #pragma unroll 1
@@ -455,11 +500,7 @@ k_ffn_bwd_tc(const float* __restrict__ dxo, const float* __restrict__ h, const f
             float a[32];
             const int c0 = e.cb + half * 32;
             tmem_ld32(tm + c0, a);
-            if (valid) {
-#pragma unroll
-                for (int i = 0; i < 32; i += 4)
-                    *reinterpret_cast<float4*>(dO + (size_t)gr * D + c0 + i) = make_float4(a[i], a[i + 1], a[i + 2], a[i + 3]);
-            }
+            warp_store32(sm.stage, e.lane, a, dO + wbase + c0, rv);
         }
     }
     teardown(sh, sh.tmem, 128);
@@ -476,71 +517,65 @@ k_qkv_bwd_tc(const float* __restrict__ dq, const float* __restrict__ dk, const f
              const float* __restrict__ ln1_w, float* __restrict__ dxin, float* __restrict__ ln_part) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ Shared sh;
-    uint8_t* A = align1k(smem_raw);
-    uint8_t* Wb[2] = {A + TILE_BYTES, A + 2 * TILE_BYTES};
+    ChainSmem sm(smem_raw);
     const int row0 = blockIdx.x * 128;
     setup(sh, 256);
-    load_w_async(Wb[0], Wqt);
-    fill_tile(A, dq, row0, M);
+    load_w_async(sm.W, Wqt);
+    fill_tile(sm.A, dq, row0, M);
     Epi e;
     const int gr = row0 + e.row;
     const bool valid = gr < M;
+    const int rv = rows_valid(row0, e, M);
+    const size_t wbase = (size_t)(row0 + e.wrow0) * D;
     uint32_t phase = 0;
-    load_w_async(Wb[1], Wkt);
-    run_gemm<1>(sh, 0, A, Wb[0], false, phase);
-    fill_tile(A, dk, row0, M);
-    load_w_async(Wb[0], Wvt);
-    run_gemm<1>(sh, 128, A, Wb[1], false, phase);
-    fill_tile(A, dv, row0, M);
-    run_gemm<0>(sh, 128, A, Wb[0], true, phase);
+    run_gemm(sh, 0, sm.A, sm.W, false, phase);
+    load_w_async(sm.W, Wkt);
+    fill_tile(sm.A, dk, row0, M);
+    run_gemm(sh, 128, sm.A, sm.W, false, phase);
+    load_w_async(sm.W, Wvt);
+    fill_tile(sm.A, dv, row0, M);
+    run_gemm(sh, 128, sm.A, sm.W, true, phase);
     {
         const uint32_t tm = sh.tmem + e.lane_addr;
         float mean = 0.f, rstd = 0.f;
         if (valid) { mean = st1[(size_t)gr * 2]; rstd = st1[(size_t)gr * 2 + 1]; }
+        float dy[64], xh[64];
         float p1 = 0.f, p2 = 0.f;
-#pragma unroll 1
+#pragma unroll
         for (int half = 0; half < 2; ++half) {
-            float a[32];
+            float a[32], r[32], xv[32];
             const int c0 = e.cb + half * 32;
             tmem_ld32(tm + c0, a);
-            if (valid) {
+            warp_load32(sm.stage, e.lane, dx1 + wbase + c0, rv, r);
+            warp_load32(sm.stage, e.lane, xin + wbase + c0, rv, xv);
 #pragma unroll
-                for (int i = 0; i < 32; i += 4) {
-                    const float4 r4 = __ldg(reinterpret_cast<const float4*>(dx1 + (size_t)gr * D + c0 + i));
-                    const float4 xv = __ldg(reinterpret_cast<const float4*>(xin + (size_t)gr * D + c0 + i));
-                    const float4 w4 = __ldg(reinterpret_cast<const float4*>(ln1_w + c0 + i));
-                    const float d0 = (a[i] + r4.x) * w4.x, d1 = (a[i + 1] + r4.y) * w4.y, d2 = (a[i + 2] + r4.z) * w4.z, d3 = (a[i + 3] + r4.w) * w4.w;
-                    p1 += (d0 + d1) + (d2 + d3);
-                    p2 += d0 * ((xv.x - mean) * rstd) + d1 * ((xv.y - mean) * rstd) + d2 * ((xv.z - mean) * rstd) + d3 * ((xv.w - mean) * rstd);
-                }
+            for (int i = 0; i < 32; ++i) {
+                const float d = a[i] + r[i];
+                const float xx = valid ? (xv[i] - mean) * rstd : 0.f;
+                const float dw = d * __ldg(ln1_w + c0 + i);
+                dy[half * 32 + i] = d;
+                xh[half * 32 + i] = xx;
+                p1 += dw;
+                p2 = fmaf(dw, xx, p2);
             }
         }
         const float c1 = row_sum(sh, e, 0, p1) * (1.0f / D);
         const float c2 = row_sum(sh, e, 1, p2) * (1.0f / D);
-#pragma unroll 1
-        for (int half = 0; half < 2; ++half) {
-            float a[32], pw[32], base[32];
-            const int c0 = e.cb + half * 32;
-            tmem_ld32(tm + c0, a);
-            tmem_ld32(tm + 128 + c0, base);
 #pragma unroll
-            for (int i = 0; i < 32; i += 4) {
-                float4 dyv = make_float4(0.f, 0.f, 0.f, 0.f), xh = dyv;
-                if (valid) {
-                    const float4 r4 = __ldg(reinterpret_cast<const float4*>(dx1 + (size_t)gr * D + c0 + i));
-                    const float4 xv = __ldg(reinterpret_cast<const float4*>(xin + (size_t)gr * D + c0 + i));
-                    const float4 w4 = __ldg(reinterpret_cast<const float4*>(ln1_w + c0 + i));
-                    dyv = make_float4(a[i] + r4.x, a[i + 1] + r4.y, a[i + 2] + r4.z, a[i + 3] + r4.w);
-                    xh = make_float4((xv.x - mean) * rstd, (xv.y - mean) * rstd, (xv.z - mean) * rstd, (xv.w - mean) * rstd);
-                    *reinterpret_cast<float4*>(dxin + (size_t)gr * D + c0 + i) =
-                        make_float4(base[i] + rstd * (dyv.x * w4.x - c1 - xh.x * c2), base[i + 1] + rstd * (dyv.y * w4.y - c1 - xh.y * c2),
-                                    base[i + 2] + rstd * (dyv.z * w4.z - c1 - xh.z * c2), base[i + 3] + rstd * (dyv.w * w4.w - c1 - xh.w * c2));
-                }
-                a[i] = dyv.x; a[i + 1] = dyv.y; a[i + 2] = dyv.z; a[i + 3] = dyv.w;
-                pw[i] = dyv.x * xh.x; pw[i + 1] = dyv.y * xh.y; pw[i + 2] = dyv.z * xh.z; pw[i + 3] = dyv.w * xh.w;
+        for (int half = 0; half < 2; ++half) {
+            float a[32], pw[32], pb[32];
+            const int c0 = e.cb + half * 32;
+            tmem_ld32(tm + 128 + c0, a);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                const float d = dy[half * 32 + i], xx = xh[half * 32 + i];
+                a[i] += valid ? rstd * (d * __ldg(ln1_w + c0 + i) - c1 - xx * c2) : 0.f;
+                pw[i] = d * xx;
+                pb[i] = d;
             }
+            warp_store32(sm.stage, e.lane, a, dxin + wbase + c0, rv);
             const float sw = warp_colsum32(pw, e.lane);
-            const float sb = warp_colsum32(a, e.lane);
+            const float sb = warp_colsum32(pb, e.lane);
             sh.lnacc[e.warp][0][half * 32 + e.lane] = sw;
             sh.lnacc[e.warp][1][half * 32 + e.lane] = sb;
         }

@@ -6,8 +6,9 @@
 // 16-byte units XOR-ed with row%8).  The SAME bytes are
 //   * a K-major operand  (rows = M/N index, columns = K)    -> Y = X W^T, dX = dY W
 //   * an MN-major operand (columns = M/N index, rows = K)   -> dW = dY^T X
-// so a tile written once by an epilogue feeds both kinds of GEMM.  kind::tf32 reads the fp32
-// bit patterns directly (10-bit mantissa), accumulators are fp32 in TMEM.
+// (the MN-major view needs the SWIZZLE_128B_BASE32B layout for 32-bit operands, so the weight-gradient
+// kernel stages transposed K-major tiles instead).  kind::tf32 reads the fp32 bit patterns directly
+// (10-bit mantissa), accumulators are fp32 in TMEM.
 #pragma once
 #include "common.cuh"
 

@@ -1,6 +1,5 @@
 // Bring-up / unit-test entry points of the tcgen05 tile pipeline (tc.cuh): a plain linear layer
-// (K-major operands) and a weight-gradient accumulation (MN-major operands, TMEM-resident
-// accumulator across tiles).  The fused encoder kernels are built from the same pieces.
+// (K-major operands).  The fused encoder kernels are built from the same pieces.
 #include "tc.cuh"
 
 namespace amid {
@@ -55,61 +54,6 @@ k_tc_linear(const float* __restrict__ x, const float* __restrict__ w, const floa
     if (warp == 0) tmem_dealloc(tmem, 128);
 }
 
-// part[cta][n][k] = sum over this CTA's token tiles of dy[m][n] * x[m][k]
-__global__ void __launch_bounds__(256, 1)
-k_tc_wgrad(const float* __restrict__ dy, const float* __restrict__ x, int M, float* __restrict__ part) {
-    extern __shared__ uint8_t smem_raw[];
-    __shared__ uint64_t bar;
-    __shared__ uint32_t tmem_base_s;
-    uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint8_t* At = base;
-    uint8_t* Bt = base + TILE_BYTES;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (warp == 0) tmem_alloc(&tmem_base_s, 128);
-    if (threadIdx.x == 0) { mbar_init(&bar, 1); fence_barrier_init(); }
-    fence_before();
-    __syncthreads();
-    fence_after();
-    const uint32_t tmem = tmem_base_s;
-    const int tiles = (M + 127) / 128;
-    uint32_t phase = 0;
-    bool first = true;
-    for (int t = blockIdx.x; t < tiles; t += gridDim.x) {
-        fill_tile(At, dy, t * 128, M);      // rows >= M are zero: they add nothing
-        fill_tile(Bt, x, t * 128, M);
-        fence_async_smem();
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            fence_after();
-            issue_gemm_mn(tmem, smem_u32(At), smem_u32(Bt), 128, !first);
-            mma_commit(&bar);
-        }
-        mbar_wait(&bar, phase);             // operands may be overwritten once the MMAs have completed
-        phase ^= 1;
-        first = false;
-    }
-    fence_after();
-    const int row = 32 * (warp & 3) + lane;
-    const int cb = 64 * (warp >> 2);
-    float* out = part + (size_t)blockIdx.x * D * D;
-#pragma unroll 1
-    for (int half = 0; half < 2; ++half) {
-        float v[32];
-        if (!first) {
-            tmem_ld32(tmem + ((uint32_t)(32 * (warp & 3)) << 16) + cb + half * 32, v);
-        } else {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = 0.f;
-        }
-        float* dst = out + (size_t)row * D + cb + half * 32;
-#pragma unroll
-        for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(dst + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-    }
-    fence_before();
-    __syncthreads();
-    if (warp == 0) tmem_dealloc(tmem, 128);
-}
-
 }  // namespace amid
 
 using namespace amid;
@@ -121,15 +65,5 @@ extern "C" int amid_tc_linear_test(const float* x, const float* w, const float* 
     AMID_K("k_tc_linear", s_);
     k_tc_linear<<<(M + 127) / 128, 256, TC_TEST_SMEM, (cudaStream_t)s_>>>(x, w, b, M, y);
     AMID_LAUNCH_CHECK("k_tc_linear");
-    return 0;
-}
-
-extern "C" int amid_tc_wgrad_test(const float* dy, const float* x, int32_t M, float* part, int32_t n_ctas, amid_stream_t s_) {
-    AMID_REQUIRE(dy && x && part && M > 0 && n_ctas > 0, "tc_wgrad_test: bad argument");
-    cudaError_t e = cudaFuncSetAttribute((const void*)k_tc_wgrad, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_TEST_SMEM);
-    if (e != cudaSuccess) return set_error(-3, "tc_wgrad_test: smem attribute: %s", cudaGetErrorString(e));
-    AMID_K("k_tc_wgrad", s_);
-    k_tc_wgrad<<<n_ctas, 256, TC_TEST_SMEM, (cudaStream_t)s_>>>(dy, x, M, part);
-    AMID_LAUNCH_CHECK("k_tc_wgrad");
     return 0;
 }

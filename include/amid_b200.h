@@ -236,8 +236,6 @@ int amid_dropout_mask_attn(const amid_dropout* drop, uint32_t site, int32_t B, i
 /* ---- tcgen05 bring-up / unit-test entry points (TF32 operands, fp32 accumulate in TMEM) ------ */
 /* y[M,128] = x[M,128] w[128,128]^T + b   (what nn.Linear / Conv1d(k=1) compute on the path) */
 int amid_tc_linear_test(const float* x, const float* w, const float* b, int32_t M, float* y, amid_stream_t stream);
-/* part[cta][n][k] = sum over the CTA's 128-token tiles of dy[m][n] x[m][k]; sum over cta = dy^T x */
-int amid_tc_wgrad_test(const float* dy, const float* x, int32_t M, float* part, int32_t n_ctas, amid_stream_t stream);
 
 #ifdef __cplusplus
 }
