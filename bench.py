@@ -192,6 +192,38 @@ def kernel_work(name, B, L, C):
     return table.get(name)
 
 
+def eval_users_per_sec(a, n_batches=20):
+    """BASELINE metric 3 ("eval users/sec"): the C1 evaluation shape of run.sh -- 256 users per batch,
+    1 + 999 candidates, L = 20 -- scored in eval mode and ranked on the device (test() of train_sr.py:31-128).
+    One GPU (rank 0), batches resident in HBM, includes the D2H of the rank counts and the metric reduce."""
+    from amid_b200 import evaluate
+    from amid_b200.engine import Trainer
+    from amid_b200.model_seq import SASRec
+    B, L, C = 256, 20, 1000
+    torch.manual_seed(1)
+    m = SASRec(0, D, V_ITEMS, D, L, HID, B, False, True, 0.5, 0.4, isDR=False).cuda().eval()
+    m.cfg.precision = a.precision
+    tr = Trainer(m)
+    rng = np.random.default_rng(7)
+    bs = [tr.to_device(synth_batch(rng, B, L, C, V_ITEMS)) for _ in range(4)]
+
+    def one(i):
+        b = bs[i % 4]
+        probs = tr.scores(b)
+        return evaluate.evaluate_lists(probs[0, 0], probs[0, 1], b["domain_id"])
+
+    for i in range(3):
+        one(i)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for i in range(n_batches):
+        one(i)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    return {"metric": "eval_users_per_sec", "value": n_batches * B / dt, "unit": "users/s", "ms_per_batch": 1e3 * dt / n_batches,
+            "config": f"{B} users x {C} candidates per batch, L={L}, SASRec+ItC, device ranking + HR/NDCG/MRR, 1 GPU"}
+
+
 def run_ours(a):
     from amid_b200 import _abi
     from amid_b200.engine import Trainer
@@ -317,6 +349,10 @@ def run_ours(a):
         "kernel_breakdown": breakdown[:12],
         "final_loss": final_loss,
     }
+    try:
+        line["eval"] = eval_users_per_sec(a)
+    except Exception as e:
+        line["eval"] = {"value": None, "error": repr(e)}
     if world == 1 and not a.no_cpu_baseline:
         try:
             v, ms, cores = cpu_reference_steps(a, 2, 1, a.cpu_sample)

@@ -1,0 +1,75 @@
+"""Run under torchrun with N >= 2 GPUs: batch-sharded DP training steps must reproduce the
+single-GPU result on the same global batch.  Used by test_gpu_dp.py."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "tests", "golden")):
+    sys.path.insert(0, p)
+
+from common import make_params  # noqa: E402
+from helpers import random_batch  # noqa: E402
+
+
+def main():
+    from amid_b200.engine import Trainer
+    from amid_b200.hotpath import DistCtx
+    from amid_b200.model_seq import SASRec
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
+    dist.init_process_group("nccl")
+    Bl, L, C, V = 4, 12, 2, 64
+    Bg = Bl * world
+    P = make_params(9, V, 128, L, 32, Bg)
+
+    def build():
+        m = SASRec(10, 128, V, 128, L, 32, Bg, False, True, 0.5, 0.3)
+        m.load_state_dict(P)
+        m.cfg.drop_p = 0.0
+        return m.cuda().train()
+
+    rng = np.random.default_rng(3)
+    batches = [random_batch(rng, Bg, L, C, V) for _ in range(3)]
+    tr = Trainer(build(), lr=1e-3, dist=DistCtx())
+    losses = []
+    for b in batches:
+        shard = {k: v[rank * Bl:(rank + 1) * Bl].cuda().contiguous() for k, v in b.items()}
+        losses.append(tr.step(shard).clone())
+    tr.flush()
+    torch.cuda.synchronize()
+    ok = True
+    if rank == 0:
+        ref = Trainer(build(), lr=1e-3)
+        for i, b in enumerate(batches):
+            l = ref.step({k: v.cuda().contiguous() for k, v in b.items()})
+            if abs(l[0].item() - losses[i][0].item()) > 2e-6 * max(1.0, abs(l[0].item())):
+                print(f"loss mismatch step {i}: dp {losses[i][0].item()} single {l[0].item()}")
+                ok = False
+        ref.flush()
+        pd, ps = dict(tr.model.named_parameters()), dict(ref.model.named_parameters())
+        for n in pd:
+            err = (pd[n].detach() - ps[n].detach()).abs().max().item()
+            if err > 2e-6:
+                print(f"param mismatch {n}: {err}")
+                ok = False
+    # all replicas must hold identical parameters
+    for n, p in tr.model.named_parameters():
+        t = p.detach().clone()
+        dist.broadcast(t, 0)
+        if not torch.equal(t, p.detach()):
+            print(f"rank {rank}: replica diverged on {n}: {(t - p.detach()).abs().max().item()}")
+            ok = False
+    flag = torch.tensor([0 if ok else 1], device="cuda")
+    dist.all_reduce(flag)
+    dist.destroy_process_group()
+    if rank == 0:
+        print("DP_CHECK_OK" if flag.item() == 0 else "DP_CHECK_FAILED")
+    sys.exit(0 if flag.item() == 0 else 1)
+
+
+if __name__ == "__main__":
+    main()

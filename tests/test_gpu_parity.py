@@ -196,6 +196,44 @@ def test_train_p0_grads_and_trajectory_golden():
                 assert_close(named[k[7:]], z[k], 0, 3e-5, f"{k} sparse={sparse}")
 
 
+def test_dropin_unchanged_driver_loop_with_torch_adam():
+    """The reference training loop body (train_sr.py:191-215) driving the drop-in module with
+    torch.optim.Adam over model.parameters(): 3 steps must land on the reference's parameters."""
+    z = load("train_p0.npz")
+    V = int(z["V"])
+    model = build_model(make_params(18, V, D, 20, HID, 16), V, 20, 16, ts2=0.07, drop_p=0.0)
+    optimizer = torch.optim.Adam(model.parameters(), lr=5e-4)            # train_sr.py:480
+    criterion_cls = torch.nn.BCELoss(reduction="none")                   # train_sr.py:184
+    model.train()
+    for step in range(3):
+        sample = {k[len(f"b{step}_"):]: T(z[k]) for k in z if k.startswith(f"b{step}_")}
+        u_node = sample["user_node"].long().cuda()
+        i_node = sample["i_node"].long().cuda()
+        neg_samples = sample["neg_samples"].long().cuda()
+        seq_d1 = sample["seq_d1"].long().cuda()
+        seq_d2 = sample["seq_d2"].long().cuda()
+        lt1 = sample["long_tail_mask_d1"].long().cuda()
+        lt2 = sample["long_tail_mask_d2"].long().cuda()
+        domain_id = sample["domain_id"].long().cuda()
+        labels = sample["label"].long().cuda().float()
+        predict_d1, predict_d2 = model(u_node, i_node, neg_samples, seq_d1, seq_d2, lt1, lt2)
+        predict_d1, predict_d2 = predict_d1.squeeze(), predict_d2.squeeze()
+        mask_d1 = (torch.ones_like(domain_id) - domain_id)
+        mask_d2 = domain_id
+        loss_cls = criterion_cls(predict_d1, labels) * mask_d1.unsqueeze(1) + criterion_cls(predict_d2, labels) * mask_d2.unsqueeze(1)
+        loss = torch.mean(loss_cls)
+        optimizer.zero_grad()
+        loss.backward()
+        optimizer.step()
+        assert_close(loss, z[f"loss_step{step}"], 5e-5, 0, f"step {step}")
+    named = dict(model.named_parameters())
+    for k in z:
+        if k.startswith("after3/"):
+            assert_close(named[k[7:]], z[k], 0, 3e-5, k)
+    sd = model.state_dict()
+    assert sd["item_emb_layer.emb_item.weight"].shape == (V, D)
+
+
 # ------------------------------------------------------------------ train mode WITH dropout: oracle + our masks
 @pytest.mark.parametrize("B,L,C,isDR", [(6, 9, 2, False), (5, 20, 3, True)])
 def test_train_dropout_vs_oracle_with_exported_masks(B, L, C, isDR):
