@@ -45,7 +45,8 @@ class Trainer:
     """Fused train step for an ``amid_b200.model_seq.SASRec`` on the current CUDA device."""
 
     def __init__(self, model, lr: float = 5e-4, lr2: float = 1.0, dr_e_w: float = 0.01, betas=(0.9, 0.999),
-                 eps: float = 1e-8, dist: Optional[hotpath.DistCtx] = None, sparse_table: bool = True):
+                 eps: float = 1e-8, dist: Optional[hotpath.DistCtx] = None, sparse_table: bool = True,
+                 table_sync: str = "auto", rows_per_step_hint: Optional[int] = None):
         self.model, self.cfg, self.dist = model, model.cfg, dist
         self.lr, self.lr2, self.dr_e_w, self.betas, self.eps = lr, lr * lr2, dr_e_w, betas, eps   # train_sr_dr.py:668-669
         self.sparse_table = sparse_table
@@ -70,11 +71,37 @@ class Trainer:
             off += (k + 3) // 4 * 4
         self.P = {n: p.data for n, p in model.named_parameters()}
         self.V = self.table.shape[0]
-        self.opt = [_AdamState(total, self.V, dev)]
-        if self.cfg.isDR:
-            self.opt.append(_AdamState(total, self.V, dev))     # optimizer2 (train_sr_dr.py:669)
-        self.active_opt = 0
         self.world = dist.world if dist is not None else 1
+        # How replicas keep the replicated table identical under data parallelism:
+        #  "sparse": all-gather the locally pre-reduced (row id, gradient row) lists, reduce again, row-sparse Adam
+        #            (right when a step touches few distinct rows: real data, pad-heavy histories);
+        #  "dense" : scatter into a dense [V,128] gradient, reduce-scatter it, dense Adam on this rank's row shard
+        #            (Adam state sharded 1/N), all-gather the updated shard (right when most of the table is touched).
+        if table_sync == "auto":
+            rows = rows_per_step_hint if rows_per_step_hint is not None else 0
+            table_sync = "dense" if (self.world > 1 and rows * self.world * 2 >= self.V) else "sparse"
+        self.table_sync = table_sync if self.world > 1 else "local"
+        n_opt = 2 if self.cfg.isDR else 1                        # optimizer2 (train_sr_dr.py:669)
+        if self.table_sync == "dense":
+            self.Vs = (self.V + self.world - 1) // self.world     # rows per shard
+            self.Vp = self.Vs * self.world
+            padded = torch.zeros(self.Vp, D, device=dev, dtype=torch.float32)
+            padded[:self.V].copy_(self.table.data)
+            self.table_padded = padded
+            self.table.data = padded[:self.V]                     # the parameter stays a [V,128] view
+            self.dense_g = torch.zeros(self.Vp, D, device=dev, dtype=torch.float32)
+            self.shard_g = torch.empty(self.Vs, D, device=dev, dtype=torch.float32)
+            self.shard_p = torch.empty(self.Vs, D, device=dev, dtype=torch.float32)
+            self.opt = [_AdamState(total, 1, dev) for _ in range(n_opt)]
+            for st in self.opt:
+                st.tm = torch.zeros(self.Vs, D, device=dev, dtype=torch.float32)
+                st.tv = torch.zeros(self.Vs, D, device=dev, dtype=torch.float32)
+            self.sparse_table = False
+        else:
+            self.opt = [_AdamState(total, self.V, dev) for _ in range(n_opt)]
+        self.P = {n: p.data for n, p in model.named_parameters()}   # (re)bind after any re-pointing above
+        self.table = self.P[TABLE]
+        self.active_opt = 0
         self.last_losses = None
         self._seed = 0
 
@@ -129,8 +156,15 @@ class Trainer:
         uid, ug, nu = hotpath.segreduce(ids_all, rows_all, self.V)
         if self.world > 1:
             self.dist.all_reduce(self.flat_g)                      # dense grads: one NCCL call
-            uid, ug, nu = self._exchange_table_grads(uid, ug, nu)
             self.dist.all_reduce(losses)
+            if self.table_sync == "dense":
+                st.step += 1
+                call("amid_adam_dense", _ptr(self.flat_p), _ptr(self.flat_g), _ptr(st.m), _ptr(st.v),
+                     self.flat_p.numel(), st.step, lr, self.betas[0], self.betas[1], self.eps, _stream())
+                self._dense_table_step(st, uid, ug, nu, lr)
+                self.last_losses = losses
+                return losses
+            uid, ug, nu = self._exchange_table_grads(uid, ug, nu)
         st.step += 1
         call("amid_adam_dense", _ptr(self.flat_p), _ptr(self.flat_g), _ptr(st.m), _ptr(st.v), self.flat_p.numel(),
              st.step, lr, self.betas[0], self.betas[1], self.eps, _stream())
@@ -142,6 +176,20 @@ class Trainer:
                  st.step, lr, self.betas[0], self.betas[1], self.eps, _stream())
         self.last_losses = losses
         return losses
+
+    def _dense_table_step(self, st, uid, ug, nu, lr):
+        """Replicated table, most rows touched: dense gradient -> reduce-scatter -> Adam on this rank's
+        row shard -> all-gather of the updated rows.  Exactly torch.optim.Adam's dense semantics."""
+        import torch.distributed as tdist
+        self.dense_g.zero_()
+        call("amid_embgrad_scatter_dense", _ptr(uid), _ptr(ug), _ptr(nu), uid.numel(), _ptr(self.dense_g), self.V,
+             _stream())
+        tdist.reduce_scatter_tensor(self.shard_g, self.dense_g, group=self.dist.group)
+        r = self.dist.rank
+        self.shard_p.copy_(self.table_padded[r * self.Vs:(r + 1) * self.Vs])
+        call("amid_adam_dense", _ptr(self.shard_p), _ptr(self.shard_g), _ptr(st.tm), _ptr(st.tv), self.shard_p.numel(),
+             st.step, lr, self.betas[0], self.betas[1], self.eps, _stream())
+        tdist.all_gather_into_tensor(self.table_padded, self.shard_p, group=self.dist.group)
 
     def _exchange_table_grads(self, uid, ug, nu):
         """Replicated table under DP: all-gather every rank's pre-reduced (row id, gradient row)

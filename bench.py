@@ -240,6 +240,8 @@ def run_ours(a):
     torch.cuda.set_device(local)
     dctx = None
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"          # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
         dctx = DistCtx()
     B, L, C = a.batch, a.seq_len, 1 + a.neg
@@ -248,7 +250,7 @@ def run_ours(a):
     model = SASRec(user_length=0, user_emb_dim=D, item_length=V_ITEMS, item_emb_dim=D, seq_len=L, hid_dim=HID, bs=Bg,
                    isInC=False, isItC=True, threshold1=0.5, threshold2=0.4, isDR=a.dr).cuda().train()
     model.cfg.precision = a.precision
-    tr = Trainer(model, lr=5e-4, dist=dctx, sparse_table=not a.dense_table)
+    tr = Trainer(model, lr=5e-4, dist=dctx, sparse_table=not a.dense_table, rows_per_step_hint=B * (2 * L + C))
     rng = np.random.default_rng(100 + rank)
     n_pool = 4
     host = [{k: v.pin_memory() for k, v in synth_batch(rng, B, L, C, V_ITEMS).items()} for _ in range(n_pool)]
@@ -337,7 +339,8 @@ def run_ours(a):
         "vs_baseline": None, "dtype": "tf32" if a.precision == "tf32" else "f32", "data": "synthetic",
         "config": {"workload": workload_name(a), "global_batch": Bg, "seq_len": L, "parallelism": f"dp{world}",
                    "l2": "no explicit flush: each step streams ~8 GB of activations, far larger than the 126 MB L2",
-                   "table_update": "dense" if a.dense_table else "row-sparse lazy Adam (exact dense semantics)"},
+                   "table_update": ("dense" if a.dense_table else "row-sparse lazy Adam (exact dense semantics)") if world == 1
+                   else f"table_sync={tr.table_sync}"},
         "clocks": clk,
         "e2e": {"value": Bg / (ms_e2e / a.steps / 1e3), "unit": "seq/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": 12, "ms_per_step": ms_e2e / a.steps},

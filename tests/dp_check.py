@@ -34,7 +34,8 @@ def main():
 
     rng = np.random.default_rng(3)
     batches = [random_batch(rng, Bg, L, C, V) for _ in range(3)]
-    tr = Trainer(build(), lr=1e-3, dist=DistCtx())
+    mode = os.environ.get("AMID_TABLE_SYNC", "sparse")
+    tr = Trainer(build(), lr=1e-3, dist=DistCtx(), table_sync=mode)
     losses = []
     for b in batches:
         shard = {k: v[rank * Bl:(rank + 1) * Bl].cuda().contiguous() for k, v in b.items()}
@@ -46,14 +47,14 @@ def main():
         ref = Trainer(build(), lr=1e-3)
         for i, b in enumerate(batches):
             l = ref.step({k: v.cuda().contiguous() for k, v in b.items()})
-            if abs(l[0].item() - losses[i][0].item()) > 2e-6 * max(1.0, abs(l[0].item())):
+            if abs(l[0].item() - losses[i][0].item()) > 1e-5 * max(1.0, abs(l[0].item())):
                 print(f"loss mismatch step {i}: dp {losses[i][0].item()} single {l[0].item()}")
                 ok = False
         ref.flush()
         pd, ps = dict(tr.model.named_parameters()), dict(ref.model.named_parameters())
         for n in pd:
             err = (pd[n].detach() - ps[n].detach()).abs().max().item()
-            if err > 2e-6:
+            if err > 2e-5:
                 print(f"param mismatch {n}: {err}")
                 ok = False
     # all replicas must hold identical parameters
