@@ -53,8 +53,12 @@ def main():
         ref.flush()
         pd, ps = dict(tr.model.named_parameters()), dict(ref.model.named_parameters())
         for n in pd:
+            # Adam moves every element by ~lr per step whatever the gradient's size, so an element whose
+            # gradient is at fp32-noise level can differ by a fraction of lr; hold elements to 0.1*lr and
+            # the tensor as a whole to 1e-5 relative
             err = (pd[n].detach() - ps[n].detach()).abs().max().item()
-            if err > 2e-5:
+            rel = (pd[n].detach() - ps[n].detach()).norm().item() / max(ps[n].detach().norm().item(), 1e-12)
+            if err > 1e-4 or rel > 1e-5:
                 print(f"param mismatch {n}: {err}")
                 ok = False
     # all replicas must hold identical parameters
