@@ -63,6 +63,10 @@ _SIGS = {
                                       POINTER(EncoderSaved), P, P, c_int64, P]),
     "amid_encoder_bwd_tc": (c_int32, [POINTER(EncoderTensors), P, P, c_int32, c_int32, POINTER(Dropout),
                                       POINTER(EncoderSaved), P, P, POINTER(EncoderTensors), P, P, c_int64, P]),
+    "amid_encoder_fwd_bf16": (c_int32, [POINTER(EncoderTensors), P, P, c_int32, c_int32, POINTER(Dropout),
+                                        POINTER(EncoderSaved), P, P, c_int64, P]),
+    "amid_encoder_bwd_bf16": (c_int32, [POINTER(EncoderTensors), P, P, c_int32, c_int32, POINTER(Dropout),
+                                        POINTER(EncoderSaved), P, P, POINTER(EncoderTensors), P, P, c_int64, P]),
     "amid_mim_scores": (c_int32, [P, P, c_int32, c_int32, P, P]),
     "amid_mim_gate": (c_int32, [P, P, c_int32, c_float, P, P, P, P, P, P, P]),
     "amid_mim_aggregate": (c_int32, [P, P, P, P, c_int32, c_int32, c_int32, P, P]),
@@ -84,6 +88,8 @@ _SIGS = {
     "amid_adam_rows_flush": (c_int32, [P, P, P, P, c_int64, c_int32, c_float, c_float, c_float, c_float, P]),
     "amid_rank_counts": (c_int32, [P, c_int64, c_int32, c_float, P, P, P]),
     "amid_tc_linear_test": (c_int32, [P, P, P, c_int32, P, P]),
+    "amid_tc_linear16_test": (c_int32, [P, P, P, c_int32, P, P]),
+    "amid_tc_wgrad16_test": (c_int32, [P, P, c_int32, P, c_int32, P]),
     "amid_dropout_mask_feature": (c_int32, [POINTER(Dropout), c_uint32, c_int64, P, P]),
     "amid_dropout_mask_attn": (c_int32, [POINTER(Dropout), c_uint32, c_int32, c_int32, P, P]),
 }

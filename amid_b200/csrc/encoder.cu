@@ -11,6 +11,7 @@
 #include "tile.cuh"
 #include "encoder_tc.cuh"
 #include "attn_mma.cuh"
+#include "encoder_tc16.cuh"
 
 namespace amid {
 
@@ -751,7 +752,8 @@ extern "C" int64_t amid_encoder_fwd_workspace_bytes(int32_t, int32_t) { return (
 
 static int encoder_fwd_impl(const amid_encoder_tensors* P, const float* x0, const uint32_t* tmask, int32_t B,
                             int32_t L, const amid_dropout* drop, amid_encoder_saved* S, float* enc_out,
-                            void* workspace, int64_t workspace_bytes, amid_stream_t stream_, bool use_tc) {
+                            void* workspace, int64_t workspace_bytes, amid_stream_t stream_, int mode) {
+    const bool use_tc = mode != 0;
     cudaStream_t stream = (cudaStream_t)stream_;
     if (int rc = check_encoder_args(B, L)) return rc;
     AMID_REQUIRE(P && S && x0 && tmask && enc_out && workspace, "encoder_fwd: null argument");
@@ -763,6 +765,48 @@ static int encoder_fwd_impl(const amid_encoder_tensors* P, const float* x0, cons
     const size_t attn_smem = (size_t)2 * L * DH * sizeof(float);
     if (int rc = ensure_smem((const void*)k_attn_fwd, attn_smem)) return rc;
     const int attn_threads = (int)round_up((L + 1) / 2, 32);
+    if (mode == 2) {   // BF16 operands: convert the 12 weight matrices once, then 2 CTAs/SM chain kernels
+        if (int rc = ensure_smem((const void*)tc16::k_ln_qkv_16, tc16::CHAIN16_SMEM)) return rc;
+        if (int rc = ensure_smem((const void*)tc16::k_proj_ffn_16, tc16::CHAIN16_SMEM)) return rc;
+        const size_t mma_smem = (size_t)2 * L * attn::LDS * sizeof(float);
+        if (int rc = ensure_smem((const void*)attn::k_attn_fwd_mma, mma_smem)) return rc;
+        uint16_t* w16 = (uint16_t*)workspace;
+        tc16::PrepJobs pj;
+        for (int i = 0; i < 2; ++i) {
+            pj.src[i * 6 + 0] = P->in_w[i];
+            pj.src[i * 6 + 1] = P->in_w[i] + D * D;
+            pj.src[i * 6 + 2] = P->in_w[i] + 2 * D * D;
+            pj.src[i * 6 + 3] = P->out_w[i];
+            pj.src[i * 6 + 4] = P->c1_w[i];
+            pj.src[i * 6 + 5] = P->c2_w[i];
+        }
+        AMID_K("k_prep_w16", stream);
+        tc16::k_prep_w16<<<dim3(4, 4, 12), dim3(32, 8), 0, stream>>>(pj, w16, 0);
+        AMID_LAUNCH_CHECK("k_prep_w16");
+        const float* xin = x0;
+        for (int i = 0; i < 2; ++i) {
+            const uint16_t* W = w16 + (size_t)i * 6 * D * D;
+            AMID_K("k_ln_qkv_16", stream);
+            tc16::k_ln_qkv_16<<<tiles, 256, tc16::CHAIN16_SMEM, stream>>>(xin, M, P->ln1_w[i], P->ln1_b[i], W, W + D * D,
+                                                                         W + 2 * D * D, P->in_b[i], S->qn[i], S->st1[i],
+                                                                         S->q[i], S->k[i], S->v[i]);
+            AMID_LAUNCH_CHECK("k_ln_qkv_16");
+            AMID_K("k_attn_fwd_mma", stream);
+            attn::k_attn_fwd_mma<<<B * H, attn::NW * 32, mma_smem, stream>>>(S->q[i], S->k[i], S->v[i], S->o[i], S->lse[i], L,
+                                                                             dc, dc.site_base + site_attn(i));
+            AMID_LAUNCH_CHECK("k_attn_fwd_mma");
+            const bool last = i == 1;
+            AMID_K("k_proj_ffn_16", stream);
+            tc16::k_proj_ffn_16<<<tiles, 256, tc16::CHAIN16_SMEM, stream>>>(
+                S->o[i], S->qn[i], M, W + 3 * D * D, P->out_b[i], P->ln2_w[i], P->ln2_b[i], W + 4 * D * D, P->c1_b[i],
+                W + 5 * D * D, P->c2_b[i], tmask, dc, dc.site_base + site_ffn1(i), dc.site_base + site_ffn2(i), S->x1[i],
+                S->st2[i], S->y[i], S->h[i], S->xout[i], last ? P->ln3_w : nullptr, last ? P->ln3_b : nullptr,
+                last ? enc_out : nullptr, last ? S->st3 : nullptr);
+            AMID_LAUNCH_CHECK("k_proj_ffn_16");
+            xin = S->xout[i];
+        }
+        return 0;
+    }
     if (use_tc) {   // tcgen05 path: the weights are consumed K-major in their natural [out][in] layout
         if (int rc = ensure_smem((const void*)tcenc::k_ln_qkv_tc, tcenc::CHAIN_SMEM)) return rc;
         if (int rc = ensure_smem((const void*)tcenc::k_proj_ffn_tc, tcenc::CHAIN_SMEM)) return rc;
@@ -833,12 +877,17 @@ static int encoder_fwd_impl(const amid_encoder_tensors* P, const float* x0, cons
 extern "C" int amid_encoder_fwd(const amid_encoder_tensors* P, const float* x0, const uint32_t* tmask, int32_t B,
                                 int32_t L, const amid_dropout* drop, amid_encoder_saved* S, float* enc_out,
                                 void* workspace, int64_t workspace_bytes, amid_stream_t stream) {
-    return encoder_fwd_impl(P, x0, tmask, B, L, drop, S, enc_out, workspace, workspace_bytes, stream, false);
+    return encoder_fwd_impl(P, x0, tmask, B, L, drop, S, enc_out, workspace, workspace_bytes, stream, 0);
 }
 extern "C" int amid_encoder_fwd_tc(const amid_encoder_tensors* P, const float* x0, const uint32_t* tmask, int32_t B,
                                    int32_t L, const amid_dropout* drop, amid_encoder_saved* S, float* enc_out,
                                    void* workspace, int64_t workspace_bytes, amid_stream_t stream) {
-    return encoder_fwd_impl(P, x0, tmask, B, L, drop, S, enc_out, workspace, workspace_bytes, stream, true);
+    return encoder_fwd_impl(P, x0, tmask, B, L, drop, S, enc_out, workspace, workspace_bytes, stream, 1);
+}
+extern "C" int amid_encoder_fwd_bf16(const amid_encoder_tensors* P, const float* x0, const uint32_t* tmask, int32_t B,
+                                     int32_t L, const amid_dropout* drop, amid_encoder_saved* S, float* enc_out,
+                                     void* workspace, int64_t workspace_bytes, amid_stream_t stream) {
+    return encoder_fwd_impl(P, x0, tmask, B, L, drop, S, enc_out, workspace, workspace_bytes, stream, 2);
 }
 
 constexpr int WG_TC_S = 24;   // CTAs per weight-gradient job on the tensor-core path (6 jobs -> 144 CTAs)
@@ -848,7 +897,7 @@ extern "C" int64_t amid_encoder_bwd_workspace_bytes(int32_t B, int32_t L) {
     const int64_t tiles = (M + TM - 1) / TM;
     int rp;
     int S = wgrad_chunks((int)M, &rp);
-    if (S < WG_TC_S) S = WG_TC_S;
+    if (S < 2 * WG_TC_S) S = 2 * WG_TC_S;
     int64_t fl = 9 * M * D;                  // dxa, dxb, do2, dhpre, dx1, dO, dq, dk, dv
     fl += (int64_t)6 * S * (D * D + D);      // weight / bias partials
     fl += 2 * tiles * 2 * D;                 // LN partials (two in flight)
@@ -859,7 +908,8 @@ extern "C" int64_t amid_encoder_bwd_workspace_bytes(int32_t B, int32_t L) {
 static int encoder_bwd_impl(const amid_encoder_tensors* P, const float* x0, const uint32_t* tmask, int32_t B,
                             int32_t L, const amid_dropout* drop, const amid_encoder_saved* S, const float* enc_out,
                             const float* d_enc, amid_encoder_tensors* G, float* dx0, void* workspace,
-                            int64_t workspace_bytes, amid_stream_t stream_, bool use_tc) {
+                            int64_t workspace_bytes, amid_stream_t stream_, int mode) {
+    const bool use_tc = mode != 0;
     (void)enc_out;
     cudaStream_t stream = (cudaStream_t)stream_;
     if (int rc = check_encoder_args(B, L)) return rc;
@@ -871,8 +921,9 @@ static int encoder_bwd_impl(const amid_encoder_tensors* P, const float* x0, cons
     const DropCfg dc = make_drop(drop);
     int rp;
     int SW = wgrad_chunks(M, &rp);
-    const int SWmax = SW < WG_TC_S ? WG_TC_S : SW;
+    const int SWmax = SW < 2 * WG_TC_S ? 2 * WG_TC_S : SW;
     if (use_tc) SW = tiles < WG_TC_S ? tiles : WG_TC_S;
+    if (mode == 2) SW = tiles < 2 * WG_TC_S ? tiles : 2 * WG_TC_S;   // 2 CTAs/SM -> 48 x 6 CTAs
     float* w = (float*)workspace;
     const size_t MD = (size_t)M * D;
     float* dxa = w;            // gradient of the current block output
@@ -889,7 +940,23 @@ static int encoder_bwd_impl(const amid_encoder_tensors* P, const float* x0, cons
     float* lnp0 = bpart + (size_t)6 * SWmax * D;
     float* lnp1 = lnp0 + (size_t)tiles * 2 * D;
     float* wtr = lnp1 + (size_t)tiles * 2 * D;   // 12 transposed weights: per block W2t, W1t, Wot, Wqt, Wkt, Wvt
-    if (use_tc) {
+    if (mode == 2) {
+        if (int rc = ensure_smem((const void*)tc16::k_ffn_bwd_16, tc16::CHAIN16_SMEM)) return rc;
+        if (int rc = ensure_smem((const void*)tc16::k_qkv_bwd_16, tc16::CHAIN16_SMEM)) return rc;
+        if (int rc = ensure_smem((const void*)tc16::k_wgrad_16, tc16::WGRAD16_SMEM)) return rc;
+        tc16::PrepJobs pj;
+        for (int i = 0; i < 2; ++i) {
+            pj.src[i * 6 + 0] = P->c2_w[i];
+            pj.src[i * 6 + 1] = P->c1_w[i];
+            pj.src[i * 6 + 2] = P->out_w[i];
+            pj.src[i * 6 + 3] = P->in_w[i];
+            pj.src[i * 6 + 4] = P->in_w[i] + D * D;
+            pj.src[i * 6 + 5] = P->in_w[i] + 2 * D * D;
+        }
+        AMID_K("k_prep_w16", stream);
+        tc16::k_prep_w16<<<dim3(4, 4, 12), dim3(32, 8), 0, stream>>>(pj, (uint16_t*)wtr, 1);
+        AMID_LAUNCH_CHECK("k_prep_w16");
+    } else if (use_tc) {
         if (int rc = ensure_smem((const void*)tcenc::k_ffn_bwd_tc, tcenc::CHAIN_SMEM)) return rc;
         if (int rc = ensure_smem((const void*)tcenc::k_qkv_bwd_tc, tcenc::CHAIN_SMEM)) return rc;
         if (int rc = ensure_smem((const void*)tcenc::k_wgrad_tc, tcenc::WGRAD_SMEM)) return rc;
@@ -926,7 +993,14 @@ static int encoder_bwd_impl(const amid_encoder_tensors* P, const float* x0, cons
         const float* xin = i == 0 ? x0 : S->xout[0];
         float* dxin = i == 0 ? dx0 : dxb;
         const float* Wt = wtr + (size_t)i * 6 * D * D;
-        if (use_tc) {
+        if (mode == 2) {
+            const uint16_t* W16 = (const uint16_t*)wtr + (size_t)i * 6 * D * D;
+            AMID_K("k_ffn_bwd_16", stream);
+            tc16::k_ffn_bwd_16<<<tiles, 256, tc16::CHAIN16_SMEM, stream>>>(
+                dxa, S->h[i], S->x1[i], S->st2[i], tmask, M, W16, W16 + D * D, W16 + 2 * D * D, P->ln2_w[i], dc,
+                dc.site_base + site_ffn1(i), dc.site_base + site_ffn2(i), do2, dhp, dx1, dO, lnp0);
+            AMID_LAUNCH_CHECK("k_ffn_bwd_16");
+        } else if (use_tc) {
             AMID_K("k_ffn_bwd_tc", stream);
             tcenc::k_ffn_bwd_tc<<<tiles, 256, tcenc::CHAIN_SMEM, stream>>>(
                 dxa, S->h[i], S->x1[i], S->st2[i], tmask, M, Wt, Wt + D * D, Wt + 2 * D * D, P->ln2_w[i], dc,
@@ -956,7 +1030,14 @@ static int encoder_bwd_impl(const amid_encoder_tensors* P, const float* x0, cons
                                                                dv, L, dc, dc.site_base + site_attn(i));
         AMID_LAUNCH_CHECK("k_attn_bwd");
         }
-        if (use_tc) {
+        if (mode == 2) {
+            const uint16_t* W16 = (const uint16_t*)wtr + (size_t)i * 6 * D * D;
+            AMID_K("k_qkv_bwd_16", stream);
+            tc16::k_qkv_bwd_16<<<tiles, 256, tc16::CHAIN16_SMEM, stream>>>(dq, dk, dv, dx1, xin, S->st1[i], M, W16 + 3 * D * D,
+                                                                          W16 + 4 * D * D, W16 + 5 * D * D, P->ln1_w[i], dxin,
+                                                                          lnp1);
+            AMID_LAUNCH_CHECK("k_qkv_bwd_16");
+        } else if (use_tc) {
             AMID_K("k_qkv_bwd_tc", stream);
             tcenc::k_qkv_bwd_tc<<<tiles, 256, tcenc::CHAIN_SMEM, stream>>>(dq, dk, dv, dx1, xin, S->st1[i], M, Wt + 3 * D * D,
                                                                           Wt + 4 * D * D, Wt + 5 * D * D, P->ln1_w[i], dxin,
@@ -980,7 +1061,13 @@ static int encoder_bwd_impl(const amid_encoder_tensors* P, const float* x0, cons
         wj.dY[3] = dq;  wj.X[3] = S->qn[i];
         wj.dY[4] = dk;  wj.X[4] = xin;
         wj.dY[5] = dv;  wj.X[5] = xin;
-        if (use_tc) {
+        if (mode == 2) {
+            tc16::WgradJobs16 w16;
+            for (int j = 0; j < 6; ++j) { w16.dY[j] = wj.dY[j]; w16.X[j] = wj.X[j]; }
+            AMID_K("k_wgrad_16", stream);
+            tc16::k_wgrad_16<<<dim3(SW, 6), 256, tc16::WGRAD16_SMEM, stream>>>(w16, M, wpart, bpart);
+            AMID_LAUNCH_CHECK("k_wgrad_16");
+        } else if (use_tc) {
             tcenc::WgradJobsTc wt6;
             for (int j = 0; j < 6; ++j) { wt6.dY[j] = wj.dY[j]; wt6.X[j] = wj.X[j]; }
             AMID_K("k_wgrad_tc", stream);
@@ -1016,11 +1103,17 @@ extern "C" int amid_encoder_bwd(const amid_encoder_tensors* P, const float* x0, 
                                 int32_t L, const amid_dropout* drop, const amid_encoder_saved* S, const float* enc_out,
                                 const float* d_enc, amid_encoder_tensors* G, float* dx0, void* workspace,
                                 int64_t workspace_bytes, amid_stream_t stream) {
-    return encoder_bwd_impl(P, x0, tmask, B, L, drop, S, enc_out, d_enc, G, dx0, workspace, workspace_bytes, stream, false);
+    return encoder_bwd_impl(P, x0, tmask, B, L, drop, S, enc_out, d_enc, G, dx0, workspace, workspace_bytes, stream, 0);
 }
 extern "C" int amid_encoder_bwd_tc(const amid_encoder_tensors* P, const float* x0, const uint32_t* tmask, int32_t B,
                                    int32_t L, const amid_dropout* drop, const amid_encoder_saved* S, const float* enc_out,
                                    const float* d_enc, amid_encoder_tensors* G, float* dx0, void* workspace,
                                    int64_t workspace_bytes, amid_stream_t stream) {
-    return encoder_bwd_impl(P, x0, tmask, B, L, drop, S, enc_out, d_enc, G, dx0, workspace, workspace_bytes, stream, true);
+    return encoder_bwd_impl(P, x0, tmask, B, L, drop, S, enc_out, d_enc, G, dx0, workspace, workspace_bytes, stream, 1);
+}
+extern "C" int amid_encoder_bwd_bf16(const amid_encoder_tensors* P, const float* x0, const uint32_t* tmask, int32_t B,
+                                     int32_t L, const amid_dropout* drop, const amid_encoder_saved* S, const float* enc_out,
+                                     const float* d_enc, amid_encoder_tensors* G, float* dx0, void* workspace,
+                                     int64_t workspace_bytes, amid_stream_t stream) {
+    return encoder_bwd_impl(P, x0, tmask, B, L, drop, S, enc_out, d_enc, G, dx0, workspace, workspace_bytes, stream, 2);
 }

@@ -106,6 +106,23 @@ __device__ __forceinline__ void warp_load32(float* buf, int lane, const float* _
     }
     __syncwarp();
 }
+// the same for data written earlier in this kernel by other threads (coherent L2 loads)
+__device__ __forceinline__ void warp_load32_cg(float* buf, int lane, const float* g, int rows_valid, float (&v)[32]) {
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+        const int r = it * 4 + (lane >> 3), u = lane & 7;
+        float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (r < rows_valid) x = __ldcg(reinterpret_cast<const float4*>(g + (size_t)r * D + u * 4));
+        *reinterpret_cast<float4*>(buf + ws_off(r, u)) = x;
+    }
+    __syncwarp();
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+        const float4 x = *reinterpret_cast<const float4*>(buf + ws_off(lane, u));
+        v[4 * u] = x.x; v[4 * u + 1] = x.y; v[4 * u + 2] = x.z; v[4 * u + 3] = x.w;
+    }
+    __syncwarp();
+}
 // registers (lane = row) -> the operand tile A, columns [c0, c0+32)
 __device__ __forceinline__ void tile_store32(uint8_t* A, int row, int c0, const float (&v)[32]) {
 #pragma unroll

@@ -136,5 +136,69 @@ __device__ __forceinline__ void fill_tile(uint8_t* tile, const float* __restrict
     }
 }
 
+
+// ================================================================================================
+// BF16 operand tiles: [128 rows][128 bf16] = 2 column chunks of 64 bf16 (128 B); chunk = [128 rows x
+// 128 B] SWIZZLE_128B (32 KB per tile).  kind::f16 with BF16 inputs, fp32 accumulation, K = 16 per MMA.
+// The same bytes serve as a K-major operand (rows = M/N) and as an MN-major operand (columns = M/N,
+// rows = K): for 16-bit types the MN-major SWIZZLE_128B atom is 64 elements x 8 rows = one 1024 B group.
+// ================================================================================================
+constexpr int TILE16_BYTES = 128 * 128 * 2;
+constexpr int CHUNK16_BYTES = 128 * 128;
+
+// byte offset of the 16-byte unit holding columns [8*u, 8*u+8) of row r
+__device__ __forceinline__ uint32_t tile16_off8(int r, int u) {
+    return (uint32_t)((u >> 3) * CHUNK16_BYTES + (r >> 3) * 1024 + (r & 7) * 128 + (((u & 7) ^ (r & 7)) << 4));
+}
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+    uint32_t r;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));   // low half = a, high half = b
+    return r;
+}
+__host__ __device__ constexpr uint32_t idesc_bf16(int n, bool a_mn, bool b_mn) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
+           ((uint32_t)(n >> 3) << 17) | ((128u >> 4) << 24);
+}
+__device__ __forceinline__ void mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+    asm volatile(
+        "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
+}
+// K-major view: k-step ks (16 bf16 = 32 B) of chunk c
+__device__ __forceinline__ uint64_t desc16_k(uint32_t tile_addr, int c, int ks) {
+    return make_desc(tile_addr + c * CHUNK16_BYTES + ks * 32, 16, 1024);
+}
+// MN-major view: k-step = 16 rows = two 1024 B groups (SBO apart); the 2 chunks are the MN atoms (LBO apart)
+__device__ __forceinline__ uint64_t desc16_mn(uint32_t tile_addr, int kstep) {
+    return make_desc(tile_addr + kstep * 2048, CHUNK16_BYTES, 1024);
+}
+// D[128 x 128] (+)= A * B^T, both K-major bf16 tiles (K = 128 = 2 chunks x 4 k-steps)
+__device__ __forceinline__ void issue_gemm16_kk(uint32_t tmem_d, uint32_t a_addr, uint32_t b_addr, bool accumulate) {
+    constexpr uint32_t id = idesc_bf16(128, false, false);
+#pragma unroll
+    for (int c = 0; c < 2; ++c)
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks)
+            mma_bf16(tmem_d, desc16_k(a_addr, c, ks), desc16_k(b_addr, c, ks), id, (accumulate || c || ks) ? 1u : 0u);
+}
+// global fp32 [M,128] rows row0.. -> bf16 tile (warp per row; rows >= M zero)
+__device__ __forceinline__ void fill_tile16(uint8_t* tile, const float* __restrict__ g, int row0, int M) {
+#pragma unroll 4
+    for (int idx = threadIdx.x; idx < 128 * 32; idx += 256) {
+        const int r = idx >> 5, c4 = idx & 31;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (row0 + r < M) v = __ldg(reinterpret_cast<const float4*>(g + (size_t)(row0 + r) * D) + c4);
+        *reinterpret_cast<uint2*>(tile + tile16_off8(r, c4 >> 1) + (c4 & 1) * 8) = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
+    }
+}
+// registers (one row, 32 consecutive fp32 columns starting at c0, c0 % 32 == 0) -> bf16 tile
+__device__ __forceinline__ void tile16_store32(uint8_t* tile, int row, int c0, const float (&v)[32]) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+        *reinterpret_cast<uint4*>(tile + tile16_off8(row, (c0 >> 3) + j)) =
+            make_uint4(pack_bf16(v[8 * j], v[8 * j + 1]), pack_bf16(v[8 * j + 2], v[8 * j + 3]),
+                       pack_bf16(v[8 * j + 4], v[8 * j + 5]), pack_bf16(v[8 * j + 6], v[8 * j + 7]));
+}
+
 }  // namespace tc
 }  // namespace amid

@@ -32,7 +32,7 @@ class Config:
     ts2: float
     isDR: bool
     drop_p: float = 0.5          # model_seq.py:335,350,355 (hard-coded in the reference)
-    precision: str = "fp32"      # "fp32": exact CUDA-core tiles; "tf32": tcgen05 tensor-core tiles (fp32 accumulate)
+    precision: str = "fp32"      # GEMM stages: "fp32" exact CUDA-core tiles | "tf32" / "bf16" tcgen05 tiles, fp32 accumulate
 
     @property
     def enc_len(self) -> int:    # model_seq.py:399-400
@@ -41,6 +41,10 @@ class Config:
     @property
     def head_names(self):
         return ["predictModule"] + (["predict_ips", "predict_gfunc"] if self.isDR else [])
+
+
+_ENC_FWD = {"fp32": "amid_encoder_fwd", "tf32": "amid_encoder_fwd_tc", "bf16": "amid_encoder_fwd_bf16"}
+_ENC_BWD = {"fp32": "amid_encoder_bwd", "tf32": "amid_encoder_bwd_tc", "bf16": "amid_encoder_bwd_bf16"}
 
 
 class DistCtx:
@@ -265,7 +269,7 @@ def forward(P: Dict[str, torch.Tensor], cfg: Config, i_node, neg_samples, seq_d1
         ws_bytes = _abi.lib().amid_encoder_fwd_workspace_bytes(B, Le)
         ws = torch.empty(ws_bytes, device=dev, dtype=torch.uint8)
         es = encoder_struct(P, sac)
-        call("amid_encoder_fwd_tc" if cfg.precision == "tf32" else "amid_encoder_fwd", C.byref(es), _ptr(x0), _ptr(tm), B, Le, C.byref(drop), C.byref(sv.struct), _ptr(enc),
+        call(_ENC_FWD[cfg.precision], C.byref(es), _ptr(x0), _ptr(tm), B, Le, C.byref(drop), C.byref(sv.struct), _ptr(enc),
              _ptr(ws), ws_bytes, s)
         encs.append(enc); x0s.append(x0); tms.append(tm); saveds.append(sv)
     ctx.encs, ctx.x0s, ctx.tms, ctx.saveds, ctx.incs, ctx.raws = encs, x0s, tms, saveds, incs, raws
@@ -362,7 +366,7 @@ def backward(P: Dict[str, torch.Tensor], cfg: Config, ctx: Ctx, dprobs: torch.Te
         es = encoder_struct(P, sac)
         gstruct = encoder_struct(G, sac)
         dx0 = f(B * Le, D) if cfg.isInC else dseq[k]
-        call("amid_encoder_bwd_tc" if cfg.precision == "tf32" else "amid_encoder_bwd", C.byref(es), _ptr(ctx.x0s[k]), _ptr(ctx.tms[k]), B, Le, C.byref(drop),
+        call(_ENC_BWD[cfg.precision], C.byref(es), _ptr(ctx.x0s[k]), _ptr(ctx.tms[k]), B, Le, C.byref(drop),
              C.byref(ctx.saveds[k].struct), _ptr(ctx.encs[k]), _ptr(d_encs[k]), C.byref(gstruct), _ptr(dx0), _ptr(ws),
              wsb, s)
         gpos = G[sac + "pos_emb.weight"]

@@ -44,7 +44,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample", type=int, default=32, help="sequences per CPU-baseline step (bounded sample)")
     ap.add_argument("--dense-table", action="store_true", help="dense Adam over the whole table (reference-style)")
-    ap.add_argument("--precision", default="tf32", choices=["fp32", "tf32"],
+    ap.add_argument("--precision", default="tf32", choices=["fp32", "tf32", "bf16"],
                     help="encoder GEMM stages: tf32 = tcgen05 tensor cores (fp32 accumulate), fp32 = exact CUDA-core tiles")
     return ap.parse_args()
 
@@ -52,7 +52,7 @@ def parse():
 def workload_name(a):
     return (f"C3 synthetic train step: per-GPU batch {a.batch}, L={a.seq_len}, d={D}, hid={HID}, C={1 + a.neg}, "
             f"V={V_ITEMS}, SASRec+ItC(ts2=0.4){'+DR' if a.dr else ''}, dropout 0.5, uniform ids (roofline variant), "
-            f"{'tcgen05 TF32 GEMM stages, fp32 accumulate/storage' if a.precision == 'tf32' else 'exact-fp32 path'}")
+            f"{'exact-fp32 path' if a.precision == 'fp32' else 'tcgen05 ' + a.precision.upper() + ' GEMM stages, fp32 accumulate/storage'}")
 
 
 def synth_batch(rng, B, L, C, V):
@@ -184,6 +184,8 @@ def kernel_work(name, B, L, C):
         "k_qkv_bwd": ("flop", 3 * gemm), "k_wgrad": ("flop", 6 * gemm),
         "k_ln_qkv_tc": ("flop", 3 * gemm), "k_proj_ffn_tc": ("flop", 3 * gemm), "k_ffn_bwd_tc": ("flop", 3 * gemm),
         "k_qkv_bwd_tc": ("flop", 3 * gemm), "k_wgrad_tc": ("flop", 6 * gemm),
+        "k_ln_qkv_16": ("flop", 3 * gemm), "k_proj_ffn_16": ("flop", 3 * gemm), "k_ffn_bwd_16": ("flop", 3 * gemm),
+        "k_qkv_bwd_16": ("flop", 3 * gemm), "k_wgrad_16": ("flop", 6 * gemm),
         "k_attn_fwd": ("flop", attn_full), "k_attn_bwd": ("flop", 2.5 * attn_full),
         "k_attn_fwd_mma": ("flop", attn_full), "k_attn_bwd_mma": ("flop", 2.5 * attn_full),
         "k_seq_embed": ("byte", rows_seq * (2 * D * 4 + 8)), "k_gather": ("byte", rows_items * (2 * D * 4 + 8)),
@@ -347,7 +349,7 @@ def run_ours(a):
     line = {
         "metric": "train_seqs_per_sec", "value": Bg / (ms_step / 1e3), "unit": "seq/s", "n_gpus": world,
         "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "tf32" if a.precision == "tf32" else "f32", "data": "synthetic",
+        "vs_baseline": None, "dtype": {"fp32": "f32", "tf32": "tf32", "bf16": "bf16"}[a.precision], "data": "synthetic",
         "config": {"workload": workload_name(a), "global_batch": Bg, "seq_len": L, "parallelism": f"dp{world}",
                    "l2": "no explicit flush: each step streams ~8 GB of activations, far larger than the 126 MB L2",
                    "table_update": ("dense" if a.dense_table else "row-sparse lazy Adam (exact dense semantics)") if world == 1

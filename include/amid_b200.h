@@ -129,6 +129,15 @@ int amid_encoder_bwd_tc(const amid_encoder_tensors* P, const float* x0, const ui
                         const float* enc_out, const float* d_enc, amid_encoder_tensors* G, float* dx0,
                         void* workspace, int64_t workspace_bytes, amid_stream_t stream);
 
+/* BF16-operand variants (fp32 accumulate, fp32 tensors in HBM; 2 CTAs per SM). */
+int amid_encoder_fwd_bf16(const amid_encoder_tensors* P, const float* x0, const uint32_t* tmask,
+                          int32_t B, int32_t L, const amid_dropout* drop, amid_encoder_saved* S,
+                          float* enc_out, void* workspace, int64_t workspace_bytes, amid_stream_t stream);
+int amid_encoder_bwd_bf16(const amid_encoder_tensors* P, const float* x0, const uint32_t* tmask,
+                          int32_t B, int32_t L, const amid_dropout* drop, const amid_encoder_saved* S,
+                          const float* enc_out, const float* d_enc, amid_encoder_tensors* G, float* dx0,
+                          void* workspace, int64_t workspace_bytes, amid_stream_t stream);
+
 /* ---- a6: InterComp / InnerComp in closed form (model_seq.py:474-497 / 450-472) ----- */
 /* m[j] = max_{s,t} <a[j,s,:], b[j,t,:]>,  a,b: [B,n,128]  (the [bs,B,n,n] matmul+max of
  * model_seq.py:489-490 without its redundant outer axis). */
@@ -236,6 +245,11 @@ int amid_dropout_mask_attn(const amid_dropout* drop, uint32_t site, int32_t B, i
 /* ---- tcgen05 bring-up / unit-test entry points (TF32 operands, fp32 accumulate in TMEM) ------ */
 /* y[M,128] = x[M,128] w[128,128]^T + b   (what nn.Linear / Conv1d(k=1) compute on the path) */
 int amid_tc_linear_test(const float* x, const float* w, const float* b, int32_t M, float* y, amid_stream_t stream);
+
+/* BF16-operand variants of the bring-up kernels; the second one accumulates dy^T x per CTA in TMEM
+ * using MN-major operand views of row-major token tiles (sum over cta of part = dy^T x). */
+int amid_tc_linear16_test(const float* x, const float* w, const float* b, int32_t M, float* y, amid_stream_t stream);
+int amid_tc_wgrad16_test(const float* dy, const float* x, int32_t M, float* part, int32_t n_ctas, amid_stream_t stream);
 
 #ifdef __cplusplus
 }
