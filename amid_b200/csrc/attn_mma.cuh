@@ -1,10 +1,12 @@
 // Causal multi-head attention for short sequences (L <= 512, head_dim 16) on the warp-level
 // tensor-core path (mma.sync m16n8k8, TF32 operands, fp32 accumulate).  One CTA per (sample, head);
-// q/k/v (and dO in the backward) of the head live in shared memory with a 20-float row stride, which
-// makes every fragment load bank-conflict free.  Softmax statistics, dropout and the causal mask are
-// applied on the accumulator fragments; P (or dS) goes straight back into the next MMA as the A
-// operand by relabelling the accumulator columns (2t -> k index t, 2t+1 -> k index t+4) and reading
-// the B operand rows in the same permuted order.
+// k/v (and q/dO in the backward) of the head live in shared memory with a 20-float row stride, which
+// makes every fragment load bank-conflict free; rows are padded with zeros to a multiple of 16 so no
+// index clamps are needed.  Softmax statistics, dropout and the causal mask are applied on the
+// accumulator fragments (only diagonal blocks evaluate the mask); P (or dS) goes straight back into
+// the next MMA as the A operand by relabelling the accumulator columns (2t -> k index t, 2t+1 -> k
+// index t+4) and reading the B operand rows in the same permuted order.  Row tiles are handed to warps
+// through a per-CTA queue, heaviest first.
 //
 // Arithmetic follows torch/nn/functional.py:6630-6647: S = (0.25 q) k^T with -inf above the
 // diagonal, P = softmax(S), dropout(P) (no renormalisation), O = P v.
@@ -18,6 +20,7 @@ constexpr int LDS = 20;          // smem row stride (floats)
 constexpr int NW = 4;            // warps per CTA (forward)
 constexpr int NWB = 8;           // warps per CTA (backward: 2 x ntile work items)
 constexpr float LOG2E = 1.4426950408889634f;
+constexpr float LN2 = 0.6931471805599453f;
 
 __device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
     asm volatile(
@@ -39,54 +42,51 @@ __device__ __forceinline__ int next_item(int* counter, int lane) {
     return __shfl_sync(0xffffffffu, it, 0);
 }
 
-// head slice [L,16] of a [M,128] tensor -> smem [L][LDS]
-__device__ __forceinline__ void stage(float* s, const float* __restrict__ g, int L) {
-    for (int idx = threadIdx.x; idx < L * 4; idx += blockDim.x) {
+// head slice [L,16] of a [M,128] tensor -> smem [Lpad][LDS], rows >= L zero, optionally scaled
+__device__ __forceinline__ void stage(float* s, const float* __restrict__ g, int L, int Lpad, float scale = 1.0f) {
+    for (int idx = threadIdx.x; idx < Lpad * 4; idx += blockDim.x) {
         const int r = idx >> 2, c4 = idx & 3;
-        *reinterpret_cast<float4*>(s + r * LDS + c4 * 4) = __ldg(reinterpret_cast<const float4*>(g + (size_t)r * D) + c4);
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (r < L) v = __ldg(reinterpret_cast<const float4*>(g + (size_t)r * D) + c4);
+        *reinterpret_cast<float4*>(s + r * LDS + c4 * 4) = make_float4(v.x * scale, v.y * scale, v.z * scale, v.w * scale);
     }
 }
-// A fragments (16 rows x 16 cols = 2 k-steps) of rows r0.. from a staged matrix; rows clamped to L-1
-__device__ __forceinline__ void load_a16(uint32_t (&a)[2][4], const float* s, int r0, int L, int g, int t) {
-    const int ra = min(r0 + g, L - 1), rb = min(r0 + g + 8, L - 1);
+// A fragments (16 rows x 16 cols = 2 k-steps) of rows r0.. from a staged (padded) matrix
+__device__ __forceinline__ void load_a16(uint32_t (&a)[2][4], const float* s, int r0, int g, int t) {
+    const float* pa = s + (r0 + g) * LDS;
+    const float* pb = pa + 8 * LDS;
 #pragma unroll
     for (int ks = 0; ks < 2; ++ks) {
-        a[ks][0] = fbits(s[ra * LDS + 8 * ks + t]);
-        a[ks][1] = fbits(s[rb * LDS + 8 * ks + t]);
-        a[ks][2] = fbits(s[ra * LDS + 8 * ks + t + 4]);
-        a[ks][3] = fbits(s[rb * LDS + 8 * ks + t + 4]);
+        a[ks][0] = fbits(pa[8 * ks + t]);
+        a[ks][1] = fbits(pb[8 * ks + t]);
+        a[ks][2] = fbits(pa[8 * ks + t + 4]);
+        a[ks][3] = fbits(pb[8 * ks + t + 4]);
     }
 }
-// the same from global memory (row stride D): used where the matrix is only ever an A operand
-__device__ __forceinline__ void load_a16_g(uint32_t (&a)[2][4], const float* __restrict__ p, int r0, int L, int g, int t) {
+// the same from global memory (row stride D, rows clamped to L-1), scaled
+__device__ __forceinline__ void load_a16_g(uint32_t (&a)[2][4], const float* __restrict__ p, int r0, int L, int g, int t, float scale) {
     const float* pa = p + (size_t)min(r0 + g, L - 1) * D;
     const float* pb = p + (size_t)min(r0 + g + 8, L - 1) * D;
 #pragma unroll
     for (int ks = 0; ks < 2; ++ks) {
-        a[ks][0] = fbits(__ldg(pa + 8 * ks + t));
-        a[ks][1] = fbits(__ldg(pb + 8 * ks + t));
-        a[ks][2] = fbits(__ldg(pa + 8 * ks + t + 4));
-        a[ks][3] = fbits(__ldg(pb + 8 * ks + t + 4));
+        a[ks][0] = fbits(__ldg(pa + 8 * ks + t) * scale);
+        a[ks][1] = fbits(__ldg(pb + 8 * ks + t) * scale);
+        a[ks][2] = fbits(__ldg(pa + 8 * ks + t + 4) * scale);
+        a[ks][3] = fbits(__ldg(pb + 8 * ks + t + 4) * scale);
     }
 }
 // D[16 x 8] = A[16 x 16] * X[n0..n0+8][16]^T   (X rows are the n index; k = feature)
-__device__ __forceinline__ void mma_xt(float (&d)[4], const uint32_t (&a)[2][4], const float* x, int n0, int L, int g, int t) {
-    const int n = min(n0 + g, L - 1);
-#pragma unroll
-    for (int ks = 0; ks < 2; ++ks) mma_tf32(d, a[ks], fbits(x[n * LDS + 8 * ks + t]), fbits(x[n * LDS + 8 * ks + t + 4]));
+__device__ __forceinline__ void mma_xt(float (&d)[4], const uint32_t (&a)[2][4], const float* x, int n0, int g, int t) {
+    const float* p = x + (n0 + g) * LDS + t;
+    mma_tf32(d, a[0], fbits(p[0]), fbits(p[4]));
+    mma_tf32(d, a[1], fbits(p[8]), fbits(p[12]));
 }
 // acc[dt][..] += P[16 x 8 (relabelled)] * X[n0..n0+8][16]   (X rows are the k index, permuted 2t / 2t+1)
-__device__ __forceinline__ void mma_px(float (&acc)[2][4], const float (&p)[4], const float* x, int n0, int L, int g, int t) {
+__device__ __forceinline__ void mma_px(float (&acc)[2][4], const float (&p)[4], const float* x, int n0, int g, int t) {
     const uint32_t a[4] = {fbits(p[0]), fbits(p[2]), fbits(p[1]), fbits(p[3])};
-    const int ka = min(n0 + 2 * t, L - 1), kb = min(n0 + 2 * t + 1, L - 1);
-#pragma unroll
-    for (int dt = 0; dt < 2; ++dt) mma_tf32(acc[dt], a, fbits(x[ka * LDS + 8 * dt + g]), fbits(x[kb * LDS + 8 * dt + g]));
-}
-// keep bits of the two elements (row, col), (row, col+1) with col even
-__device__ __forceinline__ void keep2(const DropCfg& dc, uint32_t site, uint64_t bhL, int row, int col, int Lp, bool& k0, bool& k1) {
-    const uint32_t r = rng4(dc.seed, site, ((bhL + row) * Lp + col) >> 2);
-    k0 = rng_keep(r, col & 3, dc.thr16);
-    k1 = rng_keep(r, (col & 3) + 1, dc.thr16);
+    const float* pa = x + (n0 + 2 * t) * LDS + g;
+    mma_tf32(acc[0], a, fbits(pa[0]), fbits(pa[LDS]));
+    mma_tf32(acc[1], a, fbits(pa[8]), fbits(pa[LDS + 8]));
 }
 __device__ __forceinline__ float quad_max(float v) {
     v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 1));
@@ -97,6 +97,22 @@ __device__ __forceinline__ float quad_sum(float v) {
     return v + __shfl_xor_sync(0xffffffffu, v, 2);
 }
 
+// Dropout keep bits of an accumulator fragment whose ROWS are query rows (a = row g, b = row g+8) and
+// whose columns are the keys n0+2t, n0+2t+1.  The two threads of a pair (t, t^1) share one 4-key hash
+// group, so each computes one of the two rows and they exchange.  rb4_* = (bh*L + row) * Lp / 4.
+struct RowKeep {
+    uint64_t rb4_a, rb4_b;
+};
+__device__ __forceinline__ void keep_rows(const DropCfg& dc, uint32_t site, const RowKeep& rk, int n0, int t, bool (&kp)[4]) {
+    const uint64_t idx4 = ((t & 1) ? rk.rb4_b : rk.rb4_a) + (uint32_t)((n0 >> 2) + (t >> 1));
+    const uint32_t mine = rng4(dc.seed, site, idx4);
+    const uint32_t other = __shfl_xor_sync(0xffffffffu, mine, 1);
+    const uint32_t ra = (t & 1) ? other : mine, rb = (t & 1) ? mine : other;
+    const int l0 = 2 * (t & 1);
+    kp[0] = rng_keep(ra, l0, dc.thr16); kp[1] = rng_keep(ra, l0 + 1, dc.thr16);
+    kp[2] = rng_keep(rb, l0, dc.thr16); kp[3] = rng_keep(rb, l0 + 1, dc.thr16);
+}
+
 // ----------------------------------------------------------------------------------------------
 // forward
 // ----------------------------------------------------------------------------------------------
@@ -105,92 +121,97 @@ k_attn_fwd_mma(const float* __restrict__ q, const float* __restrict__ k, const f
                float* __restrict__ o, float* __restrict__ lse, int L, DropCfg dc, uint32_t site) {
     extern __shared__ __align__(16) float smem[];
     __shared__ int queue;
+    const int ntile = (L + 15) / 16, Lpad = ntile * 16, Lp = (L + 3) & ~3;
     float* ks = smem;
-    float* vs = ks + L * LDS;
+    float* vs = ks + Lpad * LDS;
     const int bh = blockIdx.x, b = bh / H, hd = bh % H;
     const size_t base = (size_t)b * L * D + hd * DH;
     if (threadIdx.x == 0) queue = 0;
-    stage(ks, k + base, L);
-    stage(vs, v + base, L);
+    stage(ks, k + base, L, Lpad);
+    stage(vs, v + base, L, Lpad);
     __syncthreads();
     const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
-    const int ntile = (L + 15) / 16, Lp = (L + 3) & ~3;
     const uint64_t bhL = (uint64_t)bh * L;
-    // causal work per row tile grows with its index: hand tiles out from the last (heaviest) to the first
     for (;;) {
-        {
-            const int item = next_item(&queue, lane);
-            if (item >= ntile) break;
-            const int rt = ntile - 1 - item;
-            const int r0 = rt * 16;
-            uint32_t aq[2][4];
-            load_a16_g(aq, q + base, r0, L, g, t);
-            float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
-            float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
-            const int row_a = r0 + g, row_b = r0 + g + 8;
-            const int kend = min(r0 + 16, L);              // keys [0, kend) can be visible to this tile
-            for (int kb = 0; kb < kend; kb += 32) {
-                float s[4][4];
-                float mx0 = -INFINITY, mx1 = -INFINITY;
+        const int item = next_item(&queue, lane);
+        if (item >= ntile) break;
+        const int rt = ntile - 1 - item;          // heaviest (last) row tile first
+        const int r0 = rt * 16;
+        uint32_t aq[2][4];
+        load_a16_g(aq, q + base, r0, L, g, t, LOG2E);          // scores in the log2 domain
+        float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+        float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+        const int row_a = r0 + g, row_b = r0 + g + 8;
+        RowKeep rk;
+        rk.rb4_a = (bhL + min(row_a, L - 1)) * (uint64_t)(Lp >> 2);
+        rk.rb4_b = (bhL + min(row_b, L - 1)) * (uint64_t)(Lp >> 2);
+        const int kend = min(r0 + 16, L);         // keys [0, kend) can be visible to this tile
+        for (int kb = 0; kb < kend; kb += 32) {
+            float s[4][4];
+            float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
-                for (int nt = 0; nt < 4; ++nt) {
-                    const int n0 = kb + 8 * nt;
+            for (int nt = 0; nt < 4; ++nt) {
+                const int n0 = kb + 8 * nt;
+                if (n0 < kend) {                                  // warp-uniform
                     s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
-                    if (n0 < kend) mma_xt(s[nt], aq, ks, n0, L, g, t);     // warp-uniform
-                    const int c = n0 + 2 * t;
-                    s[nt][0] = (n0 < kend && c <= row_a && c < L) ? s[nt][0] : -INFINITY;
-                    s[nt][1] = (n0 < kend && c + 1 <= row_a && c + 1 < L) ? s[nt][1] : -INFINITY;
-                    s[nt][2] = (n0 < kend && c <= row_b && c < L) ? s[nt][2] : -INFINITY;
-                    s[nt][3] = (n0 < kend && c + 1 <= row_b && c + 1 < L) ? s[nt][3] : -INFINITY;
-                    mx0 = fmaxf(mx0, fmaxf(s[nt][0], s[nt][1]));
-                    mx1 = fmaxf(mx1, fmaxf(s[nt][2], s[nt][3]));
-                }
-                const float mn0 = fmaxf(m0, quad_max(mx0)), mn1 = fmaxf(m1, quad_max(mx1));
-                // rows beyond the sequence (clamped loads) can stay at -inf for a while: guard the subtraction
-                const float sub0 = mn0 == -INFINITY ? 0.f : mn0, sub1 = mn1 == -INFINITY ? 0.f : mn1;
-                const float c0 = ex2((m0 - sub0) * LOG2E), c1 = ex2((m1 - sub1) * LOG2E);
-                l0 *= c0; l1 *= c1;
-#pragma unroll
-                for (int dt = 0; dt < 2; ++dt) { acc[dt][0] *= c0; acc[dt][1] *= c0; acc[dt][2] *= c1; acc[dt][3] *= c1; }
-                m0 = mn0; m1 = mn1;
-#pragma unroll
-                for (int nt = 0; nt < 4; ++nt) {
-                    const int n0 = kb + 8 * nt;
-                    if (n0 >= kend) continue;                               // warp-uniform
-                    float p[4];
-                    p[0] = ex2((s[nt][0] - sub0) * LOG2E); p[1] = ex2((s[nt][1] - sub0) * LOG2E);
-                    p[2] = ex2((s[nt][2] - sub1) * LOG2E); p[3] = ex2((s[nt][3] - sub1) * LOG2E);
-                    l0 += p[0] + p[1]; l1 += p[2] + p[3];
-                    if (dc.train) {
-                        bool ka, kb_, kc, kd;
-                        keep2(dc, site, bhL, min(row_a, L - 1), n0 + 2 * t, Lp, ka, kb_);
-                        keep2(dc, site, bhL, min(row_b, L - 1), n0 + 2 * t, Lp, kc, kd);
-                        p[0] = ka ? p[0] * dc.scale : 0.f; p[1] = kb_ ? p[1] * dc.scale : 0.f;
-                        p[2] = kc ? p[2] * dc.scale : 0.f; p[3] = kd ? p[3] * dc.scale : 0.f;
+                    mma_xt(s[nt], aq, ks, n0, g, t);
+                    if (n0 + 8 > r0 + 1 || n0 + 8 > L) {          // diagonal / ragged block: apply the mask
+                        const int c = n0 + 2 * t;
+                        if (!(c <= row_a && c < L)) s[nt][0] = -INFINITY;
+                        if (!(c + 1 <= row_a && c + 1 < L)) s[nt][1] = -INFINITY;
+                        if (!(c <= row_b && c < L)) s[nt][2] = -INFINITY;
+                        if (!(c + 1 <= row_b && c + 1 < L)) s[nt][3] = -INFINITY;
                     }
-                    mma_px(acc, p, vs, n0, L, g, t);
+                } else {
+                    s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = -INFINITY;
                 }
+                mx0 = fmaxf(mx0, fmaxf(s[nt][0], s[nt][1]));
+                mx1 = fmaxf(mx1, fmaxf(s[nt][2], s[nt][3]));
             }
-            l0 = quad_sum(l0); l1 = quad_sum(l1);
-            const float i0 = 1.0f / l0, i1 = 1.0f / l1;
-            if (row_a < L) {
+            const float mn0 = fmaxf(m0, quad_max(mx0)), mn1 = fmaxf(m1, quad_max(mx1));
+            const float sub0 = mn0 == -INFINITY ? 0.f : mn0, sub1 = mn1 == -INFINITY ? 0.f : mn1;
+            const float c0 = ex2(m0 - sub0), c1 = ex2(m1 - sub1);
+            l0 *= c0; l1 *= c1;
 #pragma unroll
-                for (int dt = 0; dt < 2; ++dt)
-                    *reinterpret_cast<float2*>(o + base + (size_t)row_a * D + 8 * dt + 2 * t) = make_float2(acc[dt][0] * i0, acc[dt][1] * i0);
-                if (t == 0) lse[bhL + row_a] = m0 + logf(l0);
-            }
-            if (row_b < L) {
+            for (int dt = 0; dt < 2; ++dt) { acc[dt][0] *= c0; acc[dt][1] *= c0; acc[dt][2] *= c1; acc[dt][3] *= c1; }
+            m0 = mn0; m1 = mn1;
 #pragma unroll
-                for (int dt = 0; dt < 2; ++dt)
-                    *reinterpret_cast<float2*>(o + base + (size_t)row_b * D + 8 * dt + 2 * t) = make_float2(acc[dt][2] * i1, acc[dt][3] * i1);
-                if (t == 0) lse[bhL + row_b] = m1 + logf(l1);
+            for (int nt = 0; nt < 4; ++nt) {
+                const int n0 = kb + 8 * nt;
+                if (n0 >= kend) continue;                         // warp-uniform
+                float p[4];
+                p[0] = ex2(s[nt][0] - sub0); p[1] = ex2(s[nt][1] - sub0);
+                p[2] = ex2(s[nt][2] - sub1); p[3] = ex2(s[nt][3] - sub1);
+                l0 += p[0] + p[1]; l1 += p[2] + p[3];
+                if (dc.train) {
+                    bool kp[4];
+                    keep_rows(dc, site, rk, n0, t, kp);
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) p[e] = kp[e] ? p[e] * dc.scale : 0.f;
+                }
+                mma_px(acc, p, vs, n0, g, t);
             }
+        }
+        l0 = quad_sum(l0); l1 = quad_sum(l1);
+        const float i0 = 1.0f / l0, i1 = 1.0f / l1;
+        if (row_a < L) {
+#pragma unroll
+            for (int dt = 0; dt < 2; ++dt)
+                *reinterpret_cast<float2*>(o + base + (size_t)row_a * D + 8 * dt + 2 * t) = make_float2(acc[dt][0] * i0, acc[dt][1] * i0);
+            if (t == 0) lse[bhL + row_a] = m0 * LN2 + logf(l0);
+        }
+        if (row_b < L) {
+#pragma unroll
+            for (int dt = 0; dt < 2; ++dt)
+                *reinterpret_cast<float2*>(o + base + (size_t)row_b * D + 8 * dt + 2 * t) = make_float2(acc[dt][2] * i1, acc[dt][3] * i1);
+            if (t == 0) lse[bhL + row_b] = m1 * LN2 + logf(l1);
         }
     }
 }
 
 // ----------------------------------------------------------------------------------------------
-// backward: pass A (query tiles -> dq), pass B (key tiles -> dk, dv); P recomputed from lse
+// backward: pass A (query tiles -> dq), pass B (key tiles -> dk, dv); P recomputed from lse.
+// q is staged pre-multiplied by log2(e) (scores in the log2 domain); dk is rescaled at the store.
 // ----------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(NWB * 32)
 k_attn_bwd_mma(const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v,
@@ -199,64 +220,76 @@ k_attn_bwd_mma(const float* __restrict__ q, const float* __restrict__ k, const f
     extern __shared__ __align__(16) float smem[];
     __shared__ int queue;
     if (threadIdx.x == 0) queue = 0;
-    float* qs = smem;
-    float* ks = qs + L * LDS;
-    float* vs = ks + L * LDS;
-    float* gs = vs + L * LDS;     // dO
-    float* Dv = gs + L * LDS;     // D_i = <dO_i, O_i>
-    float* ls = Dv + L;           // lse * log2(e) is NOT folded: plain lse
+    const int ntile = (L + 15) / 16, Lpad = ntile * 16, Lp = (L + 3) & ~3;
+    float* qs = smem;                 // q * log2(e)
+    float* ks = qs + Lpad * LDS;
+    float* vs = ks + Lpad * LDS;
+    float* gs = vs + Lpad * LDS;      // dO
+    float* Dv = gs + Lpad * LDS;      // D_i = <dO_i, O_i>
+    float* ls = Dv + Lpad;            // lse * log2(e)
     const int bh = blockIdx.x, b = bh / H, hd = bh % H;
     const size_t base = (size_t)b * L * D + hd * DH;
-    stage(qs, q + base, L);
-    stage(ks, k + base, L);
-    stage(vs, v + base, L);
-    stage(gs, dO + base, L);
-    for (int i = threadIdx.x; i < L; i += blockDim.x) {
-        const float4* po = reinterpret_cast<const float4*>(o + base + (size_t)i * D);
-        const float4* pg = reinterpret_cast<const float4*>(dO + base + (size_t)i * D);
-        float s = 0.f;
+    stage(qs, q + base, L, Lpad, LOG2E);
+    stage(ks, k + base, L, Lpad);
+    stage(vs, v + base, L, Lpad);
+    stage(gs, dO + base, L, Lpad);
+    for (int i = threadIdx.x; i < Lpad; i += blockDim.x) {
+        float s = 0.f, le = 0.f;
+        if (i < L) {
+            const float4* po = reinterpret_cast<const float4*>(o + base + (size_t)i * D);
+            const float4* pg = reinterpret_cast<const float4*>(dO + base + (size_t)i * D);
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-            const float4 a = __ldg(po + c), bb = __ldg(pg + c);
-            s += a.x * bb.x + a.y * bb.y + a.z * bb.z + a.w * bb.w;
+            for (int c = 0; c < 4; ++c) {
+                const float4 a = __ldg(po + c), bb = __ldg(pg + c);
+                s += a.x * bb.x + a.y * bb.y + a.z * bb.z + a.w * bb.w;
+            }
+            le = lse[(size_t)bh * L + i] * LOG2E;
         }
         Dv[i] = s;
-        ls[i] = lse[(size_t)bh * L + i];
+        ls[i] = le;
     }
     __syncthreads();
     const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
-    const int ntile = (L + 15) / 16, Lp = (L + 3) & ~3;
     const uint64_t bhL = (uint64_t)bh * L;
+    const float sc = dc.train ? dc.scale : 1.0f;
     // Work items, heaviest first: item 2n = pass A on query tile ntile-1-n, item 2n+1 = pass B on key tile n.
     for (;;) {
         const int item = next_item(&queue, lane);
         if (item >= 2 * ntile) break;
         if ((item & 1) == 0) {
             // ---------------- pass A: dq[i] = 0.25 * sum_j dS_ij k_j
-            const int rt = ntile - 1 - (item >> 1);
-            const int r0 = rt * 16;
+            const int r0 = (ntile - 1 - (item >> 1)) * 16;
             uint32_t aq[2][4], ag[2][4];
-            load_a16(aq, qs, r0, L, g, t);
-            load_a16(ag, gs, r0, L, g, t);
+            load_a16(aq, qs, r0, g, t);
+            load_a16(ag, gs, r0, g, t);
             const int row_a = r0 + g, row_b = r0 + g + 8;
-            const int ra = min(row_a, L - 1), rb = min(row_b, L - 1);
-            const float la = ls[ra], lb = ls[rb], Da = Dv[ra], Db = Dv[rb];
+            const float la = ls[row_a], lb = ls[row_b], Da = Dv[row_a], Db = Dv[row_b];
+            RowKeep rk;
+            rk.rb4_a = (bhL + min(row_a, L - 1)) * (uint64_t)(Lp >> 2);
+            rk.rb4_b = (bhL + min(row_b, L - 1)) * (uint64_t)(Lp >> 2);
             float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
             const int kend = min(r0 + 16, L);
             for (int n0 = 0; n0 < kend; n0 += 8) {
                 float s[4] = {0.f, 0.f, 0.f, 0.f}, dp[4] = {0.f, 0.f, 0.f, 0.f};
-                mma_xt(s, aq, ks, n0, L, g, t);
-                mma_xt(dp, ag, vs, n0, L, g, t);
-                const int c = n0 + 2 * t;
-                bool k0 = true, k1 = true, k2 = true, k3 = true;
-                if (dc.train) { keep2(dc, site, bhL, ra, c, Lp, k0, k1); keep2(dc, site, bhL, rb, c, Lp, k2, k3); }
-                const float sc = dc.train ? dc.scale : 1.0f;
+                mma_xt(s, aq, ks, n0, g, t);
+                mma_xt(dp, ag, vs, n0, g, t);
+                if (dc.train) {
+                    bool kp[4];
+                    keep_rows(dc, site, rk, n0, t, kp);
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) dp[e] = kp[e] ? dp[e] * sc : 0.f;
+                }
                 float ds[4];
-                ds[0] = (c <= row_a && c < L) ? ex2((s[0] - la) * LOG2E) * ((k0 ? dp[0] * sc : 0.f) - Da) : 0.f;
-                ds[1] = (c + 1 <= row_a && c + 1 < L) ? ex2((s[1] - la) * LOG2E) * ((k1 ? dp[1] * sc : 0.f) - Da) : 0.f;
-                ds[2] = (c <= row_b && c < L) ? ex2((s[2] - lb) * LOG2E) * ((k2 ? dp[2] * sc : 0.f) - Db) : 0.f;
-                ds[3] = (c + 1 <= row_b && c + 1 < L) ? ex2((s[3] - lb) * LOG2E) * ((k3 ? dp[3] * sc : 0.f) - Db) : 0.f;
-                mma_px(acc, ds, ks, n0, L, g, t);
+                ds[0] = ex2(s[0] - la) * (dp[0] - Da); ds[1] = ex2(s[1] - la) * (dp[1] - Da);
+                ds[2] = ex2(s[2] - lb) * (dp[2] - Db); ds[3] = ex2(s[3] - lb) * (dp[3] - Db);
+                if (n0 + 8 > r0 + 1 || n0 + 8 > L) {              // diagonal / ragged block
+                    const int c = n0 + 2 * t;
+                    if (!(c <= row_a && c < L)) ds[0] = 0.f;
+                    if (!(c + 1 <= row_a && c + 1 < L)) ds[1] = 0.f;
+                    if (!(c <= row_b && c < L)) ds[2] = 0.f;
+                    if (!(c + 1 <= row_b && c + 1 < L)) ds[3] = 0.f;
+                }
+                mma_px(acc, ds, ks, n0, g, t);
             }
             if (row_a < L) {
 #pragma unroll
@@ -270,56 +303,65 @@ k_attn_bwd_mma(const float* __restrict__ q, const float* __restrict__ k, const f
             }
         } else {
             // ---------------- pass B: key tile; S^T = K Q^T so that P^T / dS^T land in accumulator layout
-            const int kt = item >> 1;
-            const int j0 = kt * 16;
+            const int j0 = (item >> 1) * 16;
             uint32_t ak[2][4], av[2][4];
-            load_a16(ak, ks, j0, L, g, t);
-            load_a16(av, vs, j0, L, g, t);
+            load_a16(ak, ks, j0, g, t);
+            load_a16(av, vs, j0, g, t);
             const int key_a = j0 + g, key_b = j0 + g + 8;
             float dka[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
             float dva[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
-            for (int i0 = j0 & ~7; i0 < L; i0 += 8) {      // queries i >= key; 8-query blocks from the tile's first key
+            // hash sharing: for a fixed query, the four keys of a hash group sit in the four lanes that differ in
+            // g & 3 (lane bits 2,3); lane (g & 3) == h computes hash #h of {(qa,key_a),(qb,key_a),(qa,key_b),(qb,key_b)}
+            const int hsel = g & 3;
+            const uint32_t grp_a = (uint32_t)(key_a >> 2), grp_b = (uint32_t)(key_b >> 2);
+            const int src_base = lane & ~12;
+            for (int i0 = j0; i0 < L; i0 += 8) {        // queries i >= key, 8 at a time
                 float st[4] = {0.f, 0.f, 0.f, 0.f}, dpt[4] = {0.f, 0.f, 0.f, 0.f};
-                mma_xt(st, ak, qs, i0, L, g, t);           // st[key][query] = k_key . q_query
-                mma_xt(dpt, av, gs, i0, L, g, t);          // dpt[key][query] = v_key . dO_query
-                const int qa = i0 + 2 * t, qb = qa + 1;    // the two query columns of this thread
-                const int qca = min(qa, L - 1), qcb = min(qb, L - 1);
-                const float lqa = ls[qca], lqb = ls[qcb], Dqa = Dv[qca], Dqb = Dv[qcb];
-                const float sc = dc.train ? dc.scale : 1.0f;
-                float pd[4], ds[4];
-                // element e: (key, query) = (key_a, qa), (key_a, qb), (key_b, qa), (key_b, qb)
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const int key = (e < 2) ? key_a : key_b;
-                    const int qi = (e & 1) ? qb : qa;
-                    const float lq = (e & 1) ? lqb : lqa, Dq = (e & 1) ? Dqb : Dqa;
-                    float pe = 0.f, de = 0.f;
-                    if (key <= qi && qi < L && key < L) {
-                        const float p = ex2((st[e] - lq) * LOG2E);
-                        bool kp = true;
-                        if (dc.train) {
-                            const uint32_t r = rng4(dc.seed, site, ((bhL + qi) * Lp + key) >> 2);
-                            kp = rng_keep(r, key & 3, dc.thr16);
-                        }
-                        pe = kp ? p * sc : 0.f;
-                        de = p * ((kp ? dpt[e] * sc : 0.f) - Dq);
-                    }
-                    pd[e] = pe; ds[e] = de;
+                mma_xt(st, ak, qs, i0, g, t);           // st[key][query] = k_key . q_query (log2 domain)
+                mma_xt(dpt, av, gs, i0, g, t);          // dpt[key][query] = v_key . dO_query
+                const int qa = i0 + 2 * t, qb = qa + 1;
+                const float lqa = ls[qa], lqb = ls[qb], Dqa = Dv[qa], Dqb = Dv[qb];
+                float p[4];
+                p[0] = ex2(st[0] - lqa); p[1] = ex2(st[1] - lqb); p[2] = ex2(st[2] - lqa); p[3] = ex2(st[3] - lqb);
+                if (i0 < j0 + 16 || i0 + 8 > L) {       // diagonal / ragged block: key <= query < L
+                    if (!(key_a <= qa && qa < L)) p[0] = 0.f;
+                    if (!(key_a <= qb && qb < L)) p[1] = 0.f;
+                    if (!(key_b <= qa && qa < L)) p[2] = 0.f;
+                    if (!(key_b <= qb && qb < L)) p[3] = 0.f;
                 }
-                mma_px(dva, pd, gs, i0, L, g, t);          // dv[key] += Pd^T[key][query] dO[query]
-                mma_px(dka, ds, qs, i0, L, g, t);          // dk[key] += dS^T[key][query] q[query]
+                float pd[4] = {p[0], p[1], p[2], p[3]};
+                if (dc.train) {
+                    const int qsel = min((hsel & 1) ? qb : qa, L - 1);
+                    const uint64_t idx4 = (bhL + qsel) * (uint64_t)(Lp >> 2) + ((hsel & 2) ? grp_b : grp_a);
+                    const uint32_t mine = rng4(dc.seed, site, idx4);
+                    uint32_t r[4];
+#pragma unroll
+                    for (int h4 = 0; h4 < 4; ++h4) r[h4] = __shfl_sync(0xffffffffu, mine, src_base | (h4 << 2));
+                    // r[0]=(qa,key_a) r[1]=(qb,key_a) r[2]=(qa,key_b) r[3]=(qb,key_b); lane inside the group = key & 3
+                    const bool k0 = rng_keep(r[0], key_a & 3, dc.thr16), k1 = rng_keep(r[1], key_a & 3, dc.thr16);
+                    const bool k2 = rng_keep(r[2], key_b & 3, dc.thr16), k3 = rng_keep(r[3], key_b & 3, dc.thr16);
+                    pd[0] = k0 ? p[0] * sc : 0.f; pd[1] = k1 ? p[1] * sc : 0.f;
+                    pd[2] = k2 ? p[2] * sc : 0.f; pd[3] = k3 ? p[3] * sc : 0.f;
+                    dpt[0] = k0 ? dpt[0] * sc : 0.f; dpt[1] = k1 ? dpt[1] * sc : 0.f;
+                    dpt[2] = k2 ? dpt[2] * sc : 0.f; dpt[3] = k3 ? dpt[3] * sc : 0.f;
+                }
+                float ds[4];
+                ds[0] = p[0] * (dpt[0] - Dqa); ds[1] = p[1] * (dpt[1] - Dqb);
+                ds[2] = p[2] * (dpt[2] - Dqa); ds[3] = p[3] * (dpt[3] - Dqb);
+                mma_px(dva, pd, gs, i0, g, t);          // dv[key] += Pd^T[key][query] dO[query]
+                mma_px(dka, ds, qs, i0, g, t);          // dk[key] += dS^T[key][query] q[query] (q carries log2e)
             }
             if (key_a < L) {
 #pragma unroll
                 for (int dt = 0; dt < 2; ++dt) {
-                    *reinterpret_cast<float2*>(dk + base + (size_t)key_a * D + 8 * dt + 2 * t) = make_float2(dka[dt][0], dka[dt][1]);
+                    *reinterpret_cast<float2*>(dk + base + (size_t)key_a * D + 8 * dt + 2 * t) = make_float2(dka[dt][0] * LN2, dka[dt][1] * LN2);
                     *reinterpret_cast<float2*>(dv + base + (size_t)key_a * D + 8 * dt + 2 * t) = make_float2(dva[dt][0], dva[dt][1]);
                 }
             }
             if (key_b < L) {
 #pragma unroll
                 for (int dt = 0; dt < 2; ++dt) {
-                    *reinterpret_cast<float2*>(dk + base + (size_t)key_b * D + 8 * dt + 2 * t) = make_float2(dka[dt][2], dka[dt][3]);
+                    *reinterpret_cast<float2*>(dk + base + (size_t)key_b * D + 8 * dt + 2 * t) = make_float2(dka[dt][2] * LN2, dka[dt][3] * LN2);
                     *reinterpret_cast<float2*>(dv + base + (size_t)key_b * D + 8 * dt + 2 * t) = make_float2(dva[dt][2], dva[dt][3]);
                 }
             }

@@ -768,7 +768,7 @@ static int encoder_fwd_impl(const amid_encoder_tensors* P, const float* x0, cons
     if (mode == 2) {   // BF16 operands: convert the 12 weight matrices once, then 2 CTAs/SM chain kernels
         if (int rc = ensure_smem((const void*)tc16::k_ln_qkv_16, tc16::CHAIN16_SMEM)) return rc;
         if (int rc = ensure_smem((const void*)tc16::k_proj_ffn_16, tc16::CHAIN16_SMEM)) return rc;
-        const size_t mma_smem = (size_t)2 * L * attn::LDS * sizeof(float);
+        const size_t mma_smem = (size_t)2 * ((L + 15) / 16 * 16) * attn::LDS * sizeof(float);
         if (int rc = ensure_smem((const void*)attn::k_attn_fwd_mma, mma_smem)) return rc;
         uint16_t* w16 = (uint16_t*)workspace;
         tc16::PrepJobs pj;
@@ -810,7 +810,7 @@ static int encoder_fwd_impl(const amid_encoder_tensors* P, const float* x0, cons
     if (use_tc) {   // tcgen05 path: the weights are consumed K-major in their natural [out][in] layout
         if (int rc = ensure_smem((const void*)tcenc::k_ln_qkv_tc, tcenc::CHAIN_SMEM)) return rc;
         if (int rc = ensure_smem((const void*)tcenc::k_proj_ffn_tc, tcenc::CHAIN_SMEM)) return rc;
-        const size_t mma_smem = (size_t)2 * L * attn::LDS * sizeof(float);
+        const size_t mma_smem = (size_t)2 * ((L + 15) / 16 * 16) * attn::LDS * sizeof(float);
         if (int rc = ensure_smem((const void*)attn::k_attn_fwd_mma, mma_smem)) return rc;
         const float* xin = x0;
         for (int i = 0; i < 2; ++i) {
@@ -1018,7 +1018,7 @@ static int encoder_bwd_impl(const amid_encoder_tensors* P, const float* x0, cons
         k_reduce_ln<<<16, 256, 0, stream>>>(lnp0, tiles, G->ln2_w[i], G->ln2_b[i]);
         AMID_LAUNCH_CHECK("k_reduce_ln");
         if (use_tc) {
-            const size_t mma_smem = (size_t)(4 * L * attn::LDS + 2 * L) * sizeof(float);
+            const size_t mma_smem = (size_t)((L + 15) / 16 * 16) * (4 * attn::LDS + 2) * sizeof(float);
             if (int rc = ensure_smem((const void*)attn::k_attn_bwd_mma, mma_smem)) return rc;
             AMID_K("k_attn_bwd_mma", stream);
             attn::k_attn_bwd_mma<<<B * H, attn::NWB * 32, mma_smem, stream>>>(S->q[i], S->k[i], S->v[i], S->o[i], S->lse[i], dO,
