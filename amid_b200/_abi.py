@@ -52,6 +52,8 @@ _SIGS = {
     "amid_emb_gather_fwd": (c_int32, [P, c_int64, P, c_int64, P, P]),
     "amid_gather_error_host_sync": (c_int32, []),
     "amid_seq_embed_fwd": (c_int32, [P, c_int64, P, P, P, c_int32, c_int32, P, P, POINTER(Dropout), P]),
+    "amid_embed_all_fwd": (c_int32, [P, c_int64, P, c_int64, P, P, P, P, c_int32, c_int32, P, P, P, P, P,
+                                     POINTER(Dropout), P]),
     "amid_seq_embed_bwd": (c_int32, [P, P, c_int32, c_int32, P, POINTER(Dropout), P]),
     "amid_encoder_fwd_workspace_bytes": (c_int64, [c_int32, c_int32]),
     "amid_encoder_fwd": (c_int32, [POINTER(EncoderTensors), P, P, c_int32, c_int32, POINTER(Dropout),

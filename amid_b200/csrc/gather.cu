@@ -86,6 +86,62 @@ k_seq_embed(const float* __restrict__ table, const int64_t* __restrict__ ids, co
     }
 }
 
+// One launch for every table row a training / eval step reads (model_seq.py:418-421 + the two Log2feats
+// prologues :360-366): rows [0, n_items) = candidates (plain copy), then seq_d1, then seq_d2 (fused
+// pos add, timeline-mask bits, dropout).  8 rows in flight per warp.
+struct EmbedAll {
+    const int64_t* ids[3];
+    const float* pos[2];
+    float* out[3];
+    uint32_t* tmask[2];
+    int64_t n[3];          // rows per segment
+};
+constexpr int RPW2 = 8;
+__global__ void __launch_bounds__(256)
+k_embed_all(const float* __restrict__ table, int64_t V, EmbedAll ea, int L, DropCfg dc, int* __restrict__ err) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t total = ea.n[0] + ea.n[1] + ea.n[2];
+    const int64_t r0 = warp * RPW2;
+    if (r0 >= total) return;
+    // lane u < 8 resolves row r0+u: segment, local row, id
+    int seg = 0;
+    int64_t lr = 0, id = 0;
+    if (lane < RPW2 && r0 + lane < total) {
+        lr = r0 + lane;
+        if (lr >= ea.n[0]) { lr -= ea.n[0]; seg = 1; if (lr >= ea.n[1]) { lr -= ea.n[1]; seg = 2; } }
+        id = __ldg(ea.ids[seg] + lr);
+    }
+    float4 v[RPW2];
+    bool ok[RPW2];
+#pragma unroll
+    for (int u = 0; u < RPW2; ++u) {
+        const int64_t idu = __shfl_sync(0xffffffffu, id, u);
+        ok[u] = (r0 + u < total);
+        if (ok[u] && (idu < 0 || idu >= V)) { ok[u] = false; if (lane == 0) atomicExch(err, 1); }
+        if (ok[u]) v[u] = ldg_stream(reinterpret_cast<const float4*>(table + idu * D) + lane);
+    }
+#pragma unroll
+    for (int u = 0; u < RPW2; ++u) {
+        const int su = __shfl_sync(0xffffffffu, seg, u);
+        const int64_t lru = __shfl_sync(0xffffffffu, lr, u);
+        if (!ok[u]) continue;   // warp-uniform
+        float4 x = v[u];
+        if (su > 0) {
+            const int l = (int)(lru % L);
+            const float4 p = __ldg(reinterpret_cast<const float4*>(ea.pos[su - 1] + (size_t)l * D) + lane);
+            x = make_float4(x.x + p.x, x.y + p.y, x.z + p.z, x.w + p.w);
+            const uint32_t w0 = __ballot_sync(0xffffffffu, x.x == 0.f);
+            const uint32_t w1 = __ballot_sync(0xffffffffu, x.y == 0.f);
+            const uint32_t w2 = __ballot_sync(0xffffffffu, x.z == 0.f);
+            const uint32_t w3 = __ballot_sync(0xffffffffu, x.w == 0.f);
+            if (lane == 0) *reinterpret_cast<uint4*>(ea.tmask[su - 1] + lru * 4) = make_uint4(w0, w1, w2, w3);
+            if (dc.train) x = drop4(x, dc, 8u * (su - 1) + SITE_EMB, (uint64_t)lru * D + lane * 4);
+        }
+        stg_stream(reinterpret_cast<float4*>(ea.out[su] + lru * D) + lane, x);
+    }
+}
+
 // backward: dx0 <- dx0 * ~tmask * keep*scale (in place); dpos[l] = sum_b dx0[b,l].
 // One CTA per position l; its 8 warps stride over the batch, then a fixed-order
 // cross-warp sum (deterministic, no atomics).
@@ -200,6 +256,33 @@ extern "C" int amid_seq_embed_fwd(const float* table, int64_t V, const int64_t* 
         k_seq_embed<false><<<blocks, 256, 0, stream>>>(nullptr, nullptr, rows, pos, n_rows, L, V, x0, tmask, dc, err);
     }
     AMID_LAUNCH_CHECK("k_seq_embed");
+    return 0;
+}
+
+extern "C" int amid_embed_all_fwd(const float* table, int64_t V, const int64_t* ids_items, int64_t n_items,
+                                  const int64_t* ids_d1, const int64_t* ids_d2, const float* pos_d1, const float* pos_d2,
+                                  int32_t B, int32_t L, float* items, float* x0_d1, float* x0_d2, uint32_t* tmask_d1,
+                                  uint32_t* tmask_d2, const amid_dropout* drop, amid_stream_t stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    AMID_REQUIRE(table && ids_items && ids_d1 && ids_d2 && pos_d1 && pos_d2 && items && x0_d1 && x0_d2 && tmask_d1 && tmask_d2,
+                 "embed_all_fwd: null argument");
+    AMID_REQUIRE(V > 0 && n_items >= 0 && B > 0 && L > 0, "embed_all_fwd: bad sizes");
+    AMID_REQUIRE(aligned16(table) && aligned16(items) && aligned16(x0_d1) && aligned16(x0_d2) && aligned16(tmask_d1) &&
+                 aligned16(tmask_d2) && aligned16(pos_d1) && aligned16(pos_d2), "embed_all_fwd: misaligned buffer");
+    int* err = err_flag();
+    AMID_REQUIRE(err, "embed_all_fwd: cannot allocate error flag");
+    EmbedAll ea;
+    ea.ids[0] = ids_items; ea.ids[1] = ids_d1; ea.ids[2] = ids_d2;
+    ea.pos[0] = pos_d1; ea.pos[1] = pos_d2;
+    ea.out[0] = items; ea.out[1] = x0_d1; ea.out[2] = x0_d2;
+    ea.tmask[0] = tmask_d1; ea.tmask[1] = tmask_d2;
+    ea.n[0] = n_items; ea.n[1] = (int64_t)B * L; ea.n[2] = (int64_t)B * L;
+    const int64_t total = ea.n[0] + ea.n[1] + ea.n[2];
+    const int64_t warps = (total + RPW2 - 1) / RPW2;
+    const DropCfg dc = make_drop(drop);
+    AMID_K("k_embed_all", stream);
+    k_embed_all<<<(unsigned)((warps + 7) / 8), 256, 0, stream>>>(table, V, ea, L, dc, err);
+    AMID_LAUNCH_CHECK("k_embed_all");
     return 0;
 }
 

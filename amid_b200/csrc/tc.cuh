@@ -181,14 +181,22 @@ __device__ __forceinline__ void issue_gemm16_kk(uint32_t tmem_d, uint32_t a_addr
         for (int ks = 0; ks < 4; ++ks)
             mma_bf16(tmem_d, desc16_k(a_addr, c, ks), desc16_k(b_addr, c, ks), id, (accumulate || c || ks) ? 1u : 0u);
 }
-// global fp32 [M,128] rows row0.. -> bf16 tile (warp per row; rows >= M zero)
+// global fp32 [M,128] rows row0.. -> bf16 tile (warp per row; rows >= M zero).  All 16 loads of a thread are
+// issued before the first conversion so that a CTA keeps 64 KB in flight.
 __device__ __forceinline__ void fill_tile16(uint8_t* tile, const float* __restrict__ g, int row0, int M) {
-#pragma unroll 4
-    for (int idx = threadIdx.x; idx < 128 * 32; idx += 256) {
-        const int r = idx >> 5, c4 = idx & 31;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (row0 + r < M) v = __ldg(reinterpret_cast<const float4*>(g + (size_t)(row0 + r) * D) + c4);
-        *reinterpret_cast<uint2*>(tile + tile16_off8(r, c4 >> 1) + (c4 & 1) * 8) = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
+    const int c4 = threadIdx.x & 31, rb = threadIdx.x >> 5;
+    float4 v[16];
+#pragma unroll
+    for (int it = 0; it < 16; ++it) {
+        const int r = it * 8 + rb;
+        v[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (row0 + r < M) v[it] = __ldg(reinterpret_cast<const float4*>(g + (size_t)(row0 + r) * D) + c4);
+    }
+#pragma unroll
+    for (int it = 0; it < 16; ++it) {
+        const int r = it * 8 + rb;
+        *reinterpret_cast<uint2*>(tile + tile16_off8(r, c4 >> 1) + (c4 & 1) * 8) =
+            make_uint2(pack_bf16(v[it].x, v[it].y), pack_bf16(v[it].z, v[it].w));
     }
 }
 // registers (one row, 32 consecutive fp32 columns starting at c0, c0 % 32 == 0) -> bf16 tile

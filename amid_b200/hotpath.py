@@ -239,17 +239,25 @@ def forward(P: Dict[str, torch.Tensor], cfg: Config, i_node, neg_samples, seq_d1
     ctx.B, ctx.L, ctx.Le, ctx.C, ctx.V, ctx.train, ctx.seed, ctx.j0 = B, L, Le, Cn, V, train, seed, j0
     ctx.ids_items, ctx.seqs = ids_items, seqs
 
-    # a1: candidate rows
+    # a1 (+a2): every table read of the step
     items = f(B, Cn, D)
-    call("amid_emb_gather_fwd", _ptr(table), V, _ptr(ids_items), B * Cn, _ptr(items), s)
     ctx.items = items
-
     encs, x0s, tms, saveds, incs, raws = [], [], [], [], [], []
+    pre_x0 = pre_tm = None
+    if not cfg.isInC:
+        pre_x0 = [f(B * Le, D), f(B * Le, D)]
+        pre_tm = [torch.empty(B * Le * 4, device=dev, dtype=torch.int32) for _ in range(2)]
+        drop0 = _dropout(cfg, train, seed, 0)
+        call("amid_embed_all_fwd", _ptr(table), V, _ptr(ids_items), B * Cn, _ptr(seqs[0]), _ptr(seqs[1]),
+             _ptr(P["sac1.pos_emb.weight"]), _ptr(P["sac2.pos_emb.weight"]), B, L, _ptr(items), _ptr(pre_x0[0]),
+             _ptr(pre_x0[1]), _ptr(pre_tm[0]), _ptr(pre_tm[1]), C.byref(drop0), s)
+    else:
+        call("amid_emb_gather_fwd", _ptr(table), V, _ptr(ids_items), B * Cn, _ptr(items), s)
     for k, sac in enumerate(("sac1.", "sac2.")):
         drop = _dropout(cfg, train, seed, 8 * k)
-        x0 = f(B * Le, D)
-        tm = torch.empty(B * Le * 4, device=dev, dtype=torch.int32)
         if cfg.isInC:
+            x0 = f(B * Le, D)
+            tm = torch.empty(B * Le * 4, device=dev, dtype=torch.int32)
             # model_seq.py:422-424  InnerComp before the encoder
             raw = f(B, L, D)
             call("amid_emb_gather_fwd", _ptr(table), V, _ptr(seqs[k]), B * L, _ptr(raw), s)
@@ -262,8 +270,7 @@ def forward(P: Dict[str, torch.Tensor], cfg: Config, i_node, neg_samples, seq_d1
             incs.append(st)
             raws.append(raw)
         else:
-            call("amid_seq_embed_fwd", _ptr(table), V, _ptr(seqs[k]), None, _ptr(P[sac + "pos_emb.weight"]), B, Le,
-                 _ptr(x0), _ptr(tm), C.byref(drop), s)
+            x0, tm = pre_x0[k], pre_tm[k]
         sv = _Saved(B, Le, dev)
         enc = f(B * Le, D)
         ws_bytes = _abi.lib().amid_encoder_fwd_workspace_bytes(B, Le)

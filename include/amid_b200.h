@@ -100,6 +100,13 @@ int amid_gather_error_host_sync(void);
 int amid_seq_embed_fwd(const float* table, int64_t V, const int64_t* ids, const float* rows,
                        const float* pos, int32_t B, int32_t L, float* x0, uint32_t* tmask,
                        const amid_dropout* drop, amid_stream_t stream);
+/* All table reads of one step in ONE launch: the candidate rows (plain copy, a1) and both domains'
+ * sequences with the fused prologue (a1+a2).  Dropout sites: domain 1 uses site 0, domain 2 site 8
+ * (the site_base of `drop` is ignored).  This launch is the "emb-gather HBM GB/s" metric. */
+int amid_embed_all_fwd(const float* table, int64_t V, const int64_t* ids_items, int64_t n_items,
+                       const int64_t* ids_d1, const int64_t* ids_d2, const float* pos_d1, const float* pos_d2,
+                       int32_t B, int32_t L, float* items, float* x0_d1, float* x0_d2, uint32_t* tmask_d1,
+                       uint32_t* tmask_d2, const amid_dropout* drop, amid_stream_t stream);
 /* backward of the above: dx0 <- dx0 * ~tmask * keep/(1-p) in place (this is then the
  * per-row table gradient), dpos[l,:] = sum_b dx0[b,l,:]. */
 int amid_seq_embed_bwd(float* dx0, const uint32_t* tmask, int32_t B, int32_t L, float* dpos,

@@ -83,6 +83,41 @@ def test_seq_embed_bit_exact_and_mask_bits(B, L):
         assert mask[0].all() and mask[B * L - 1, 3]
 
 
+@pytest.mark.parametrize("B,L,C", [(1, 1, 2), (3, 7, 5), (37, 20, 2), (9, 200, 3)])
+def test_embed_all_single_launch_bit_exact(B, L, C):
+    """The fused one-launch gather (candidates + both sequences with pos add and mask bits)."""
+    import ctypes as Ct
+    hp = _hp()
+    from amid_b200._abi import Dropout, call
+    g = torch.Generator().manual_seed(B * 131 + L)
+    V = 1000
+    table = torch.randn(V, D, generator=g)
+    pos = [torch.randn(L, D, generator=g), torch.randn(L, D, generator=g)]
+    ids_items = torch.randint(0, V, (B, C), generator=g)
+    seqs = [torch.randint(0, V, (B, L), generator=g), torch.randint(0, V, (B, L), generator=g)]
+    table[3] = 0.0
+    pos[1][0] = 0.0
+    seqs[1][0, 0] = 3
+    tc = table.cuda()
+    outs = [torch.empty(B * C, D, device="cuda"), torch.empty(B * L, D, device="cuda"), torch.empty(B * L, D, device="cuda")]
+    tms = [torch.zeros(B * L * 4, dtype=torch.int32, device="cuda") for _ in range(2)]
+    drop = Dropout(0, 0.5, 0, 0)
+    ii, s1, s2, p1, p2 = ids_items.cuda(), seqs[0].cuda(), seqs[1].cuda(), pos[0].cuda(), pos[1].cuda()
+    call("amid_embed_all_fwd", hp._ptr(tc), V, hp._ptr(ii), B * C, hp._ptr(s1), hp._ptr(s2), hp._ptr(p1), hp._ptr(p2), B, L,
+         hp._ptr(outs[0]), hp._ptr(outs[1]), hp._ptr(outs[2]), hp._ptr(tms[0]), hp._ptr(tms[1]), Ct.byref(drop), hp._stream())
+    assert torch.equal(outs[0].cpu(), table[ids_items.reshape(-1)])
+    for k in range(2):
+        want = (table[seqs[k]] + pos[k][:L]).view(B * L, D)
+        assert torch.equal(outs[k + 1].cpu(), want)
+        bits = tms[k].view(B * L, 4).cpu().numpy().astype(np.uint32)
+        mask = np.zeros((B * L, D), dtype=bool)
+        for e in range(4):
+            for j in range(32):
+                mask[:, 4 * j + e] = (bits[:, e] >> j) & 1
+        assert np.array_equal(mask, (want == 0).numpy())
+    assert (tms[1].view(B * L, 4)[0] != 0).all()
+
+
 # ------------------------------------------------------------------ whole forward vs reference goldens
 def test_forward_c1_golden():
     z = load("c1_fwd_eval.npz")
