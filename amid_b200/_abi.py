@@ -70,6 +70,7 @@ _SIGS = {
     "amid_encoder_bwd_bf16": (c_int32, [POINTER(EncoderTensors), P, P, c_int32, c_int32, POINTER(Dropout),
                                         POINTER(EncoderSaved), P, P, POINTER(EncoderTensors), P, P, c_int64, P]),
     "amid_mim_scores": (c_int32, [P, P, c_int32, c_int32, P, P]),
+    "amid_mim_scores_tc": (c_int32, [P, P, c_int32, c_int32, P, P]),
     "amid_mim_gate": (c_int32, [P, P, c_int32, c_float, P, P, P, P, P, P, P]),
     "amid_mim_aggregate": (c_int32, [P, P, P, P, c_int32, c_int32, c_int32, P, P]),
     "amid_mim_project": (c_int32, [P, P, P, P, P, c_int32, P, P, P]),

@@ -161,10 +161,42 @@ k_adam_dense(float* __restrict__ p, const float* __restrict__ g, float* __restri
     }
 }
 
+// Host-computed constants of the most recent steps, so that the replay of a short gap needs no FP64 on the device.
+constexpr int ADAM_HIST = 48;
+struct AdamHist {
+    int first_step;                 // hist[i] belongs to step first_step + i
+    float step_size[ADAM_HIST];
+    float bc2_sqrt[ADAM_HIST];
+};
+static AdamHist adam_hist(int step, float lr, float b1, float b2) {
+    AdamHist h;
+    h.first_step = step - ADAM_HIST + 1;
+    for (int i = 0; i < ADAM_HIST; ++i) {
+        const int s = h.first_step + i;
+        if (s < 1) { h.step_size[i] = 0.f; h.bc2_sqrt[i] = 1.f; continue; }
+        h.step_size[i] = (float)((double)lr / (1.0 - pow((double)b1, (double)s)));
+        h.bc2_sqrt[i] = (float)sqrt(1.0 - pow((double)b2, (double)s));
+    }
+    return h;
+}
 // replay of zero-gradient steps s0..s1 (inclusive) for one float4 of a row
 __device__ __forceinline__ void adam_replay(float4& P, float4& M, float4& Vv, int s0, int s1, float lr, double b1,
-                                            double b2, float eps) {
+                                            double b2, float eps, const AdamHist& hist) {
     if (s0 > s1) return;
+    if (s0 >= hist.first_step && s0 >= 1) {            // common case: the gap is covered by the host table
+        AdamStep a;
+        a.w1 = (float)(1.0 - b1);
+        a.beta2 = (float)b2;
+        a.omb2 = (float)(1.0 - b2);
+        a.eps = eps;
+        for (int s = s0; s <= s1; ++s) {
+            a.step_size = hist.step_size[s - hist.first_step];
+            a.bc2_sqrt = hist.bc2_sqrt[s - hist.first_step];
+            adam1(P.x, 0.f, M.x, Vv.x, a); adam1(P.y, 0.f, M.y, Vv.y, a);
+            adam1(P.z, 0.f, M.z, Vv.z, a); adam1(P.w, 0.f, M.w, Vv.w, a);
+        }
+        return;
+    }
     double p1 = pow(b1, (double)(s0 - 1)), p2 = pow(b2, (double)(s0 - 1));
     AdamStep a;
     a.w1 = (float)(1.0 - b1);
@@ -183,7 +215,8 @@ __device__ __forceinline__ void adam_replay(float4& P, float4& M, float4& Vv, in
 __global__ void __launch_bounds__(256)
 k_adam_rows_lazy(float* __restrict__ table, float* __restrict__ m, float* __restrict__ v, int* __restrict__ last_step,
                  const int64_t* __restrict__ uniq_ids, const float* __restrict__ uniq_grads,
-                 const int* __restrict__ n_uniq, int step, float lr, float b1, float b2, float eps, AdamStep a) {
+                 const int* __restrict__ n_uniq, int step, float lr, float b1, float b2, float eps, AdamStep a,
+                 const __grid_constant__ AdamHist hist) {
     const int lane = threadIdx.x & 31;
     const int u = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
     if (u >= n_uniq[0]) return;
@@ -193,7 +226,7 @@ k_adam_rows_lazy(float* __restrict__ table, float* __restrict__ m, float* __rest
     float4* Vp = reinterpret_cast<float4*>(v + id * D) + lane;
     float4 P = *Pp, M = *Mp, Vv = *Vp;
     const int last = last_step[id];
-    if (last > 0) adam_replay(P, M, Vv, last + 1, step - 1, lr, (double)b1, (double)b2, eps);
+    if (last > 0) adam_replay(P, M, Vv, last + 1, step - 1, lr, (double)b1, (double)b2, eps, hist);
     const float4 G = reinterpret_cast<const float4*>(uniq_grads + (size_t)u * D)[lane];
     adam1(P.x, G.x, M.x, Vv.x, a); adam1(P.y, G.y, M.y, Vv.y, a);
     adam1(P.z, G.z, M.z, Vv.z, a); adam1(P.w, G.w, M.w, Vv.w, a);
@@ -203,7 +236,7 @@ k_adam_rows_lazy(float* __restrict__ table, float* __restrict__ m, float* __rest
 }
 __global__ void __launch_bounds__(256)
 k_adam_rows_flush(float* __restrict__ table, float* __restrict__ m, float* __restrict__ v, int* __restrict__ last_step,
-                  int64_t V, int step, float lr, float b1, float b2, float eps) {
+                  int64_t V, int step, float lr, float b1, float b2, float eps, const __grid_constant__ AdamHist hist) {
     const int lane = threadIdx.x & 31;
     const int64_t id = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (id >= V) return;
@@ -213,7 +246,7 @@ k_adam_rows_flush(float* __restrict__ table, float* __restrict__ m, float* __res
     float4* Mp = reinterpret_cast<float4*>(m + id * D) + lane;
     float4* Vp = reinterpret_cast<float4*>(v + id * D) + lane;
     float4 P = *Pp, M = *Mp, Vv = *Vp;
-    adam_replay(P, M, Vv, last + 1, step, lr, (double)b1, (double)b2, eps);
+    adam_replay(P, M, Vv, last + 1, step, lr, (double)b1, (double)b2, eps, hist);
     *Pp = P; *Mp = M; *Vp = Vv;
     __syncwarp();
     if (lane == 0) last_step[id] = step;
@@ -347,7 +380,7 @@ extern "C" int amid_adam_rows_lazy(float* table, float* m, float* v, int32_t* la
     const AdamStep a = adam_consts(step, lr, beta1, beta2, eps);
     AMID_K("k_adam_rows_lazy", (cudaStream_t)s_);
     k_adam_rows_lazy<<<(unsigned)((max_rows * 32 + 255) / 256), 256, 0, (cudaStream_t)s_>>>(
-        table, m, v, last_step, uniq_ids, uniq_grads, n_uniq, step, lr, beta1, beta2, eps, a);
+        table, m, v, last_step, uniq_ids, uniq_grads, n_uniq, step, lr, beta1, beta2, eps, a, adam_hist(step, lr, beta1, beta2));
     AMID_LAUNCH_CHECK("k_adam_rows_lazy");
     return 0;
 }
@@ -358,7 +391,8 @@ extern "C" int amid_adam_rows_flush(float* table, float* m, float* v, int32_t* l
     if (step == 0) return 0;
     AMID_K("k_adam_rows_flush", (cudaStream_t)s_);
     k_adam_rows_flush<<<(unsigned)((V * 32 + 255) / 256), 256, 0, (cudaStream_t)s_>>>(table, m, v, last_step, V, step,
-                                                                                       lr, beta1, beta2, eps);
+                                                                                       lr, beta1, beta2, eps,
+                                                                                       adam_hist(step, lr, beta1, beta2));
     AMID_LAUNCH_CHECK("k_adam_rows_flush");
     return 0;
 }

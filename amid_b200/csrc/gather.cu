@@ -90,27 +90,29 @@ k_seq_embed(const float* __restrict__ table, const int64_t* __restrict__ ids, co
 // prologues :360-366): rows [0, n_items) = candidates (plain copy), then seq_d1, then seq_d2 (fused
 // pos add, timeline-mask bits, dropout).  8 rows in flight per warp.
 struct EmbedAll {
-    const int64_t* ids[3];
-    const float* pos[2];
-    float* out[3];
-    uint32_t* tmask[2];
-    int64_t n[3];          // rows per segment
+    const int64_t *ids0, *ids1, *ids2;
+    const float *pos1, *pos2;
+    float *out0, *out1, *out2;
+    uint32_t *tm1, *tm2;
+    uint32_t n0, n1, n2;          // rows per segment (each < 2^31)
 };
 constexpr int RPW2 = 8;
 __global__ void __launch_bounds__(256)
-k_embed_all(const float* __restrict__ table, int64_t V, EmbedAll ea, int L, DropCfg dc, int* __restrict__ err) {
+k_embed_all(const float* __restrict__ table, int64_t V, EmbedAll ea, uint32_t L, DropCfg dc, int* __restrict__ err) {
     const int lane = threadIdx.x & 31;
-    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int64_t total = ea.n[0] + ea.n[1] + ea.n[2];
-    const int64_t r0 = warp * RPW2;
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t total = ea.n0 + ea.n1 + ea.n2;
+    const uint32_t r0 = warp * RPW2;
     if (r0 >= total) return;
-    // lane u < 8 resolves row r0+u: segment, local row, id
+    // lane u < 8 resolves row r0+u: segment, local row, id   (no dynamic indexing of the parameter struct)
     int seg = 0;
-    int64_t lr = 0, id = 0;
+    uint32_t lr = 0;
+    int64_t id = 0;
     if (lane < RPW2 && r0 + lane < total) {
         lr = r0 + lane;
-        if (lr >= ea.n[0]) { lr -= ea.n[0]; seg = 1; if (lr >= ea.n[1]) { lr -= ea.n[1]; seg = 2; } }
-        id = __ldg(ea.ids[seg] + lr);
+        if (lr >= ea.n0) { lr -= ea.n0; seg = 1; if (lr >= ea.n1) { lr -= ea.n1; seg = 2; } }
+        const int64_t* src = seg == 0 ? ea.ids0 : (seg == 1 ? ea.ids1 : ea.ids2);
+        id = __ldg(src + lr);
     }
     float4 v[RPW2];
     bool ok[RPW2];
@@ -124,21 +126,24 @@ k_embed_all(const float* __restrict__ table, int64_t V, EmbedAll ea, int L, Drop
 #pragma unroll
     for (int u = 0; u < RPW2; ++u) {
         const int su = __shfl_sync(0xffffffffu, seg, u);
-        const int64_t lru = __shfl_sync(0xffffffffu, lr, u);
+        const uint32_t lru = __shfl_sync(0xffffffffu, lr, u);
         if (!ok[u]) continue;   // warp-uniform
         float4 x = v[u];
+        float* dst = su == 0 ? ea.out0 : (su == 1 ? ea.out1 : ea.out2);
         if (su > 0) {
-            const int l = (int)(lru % L);
-            const float4 p = __ldg(reinterpret_cast<const float4*>(ea.pos[su - 1] + (size_t)l * D) + lane);
+            const uint32_t l = lru % L;
+            const float* pp = su == 1 ? ea.pos1 : ea.pos2;
+            uint32_t* tmk = su == 1 ? ea.tm1 : ea.tm2;
+            const float4 p = __ldg(reinterpret_cast<const float4*>(pp + (size_t)l * D) + lane);
             x = make_float4(x.x + p.x, x.y + p.y, x.z + p.z, x.w + p.w);
             const uint32_t w0 = __ballot_sync(0xffffffffu, x.x == 0.f);
             const uint32_t w1 = __ballot_sync(0xffffffffu, x.y == 0.f);
             const uint32_t w2 = __ballot_sync(0xffffffffu, x.z == 0.f);
             const uint32_t w3 = __ballot_sync(0xffffffffu, x.w == 0.f);
-            if (lane == 0) *reinterpret_cast<uint4*>(ea.tmask[su - 1] + lru * 4) = make_uint4(w0, w1, w2, w3);
+            if (lane == 0) *reinterpret_cast<uint4*>(tmk + (size_t)lru * 4) = make_uint4(w0, w1, w2, w3);
             if (dc.train) x = drop4(x, dc, 8u * (su - 1) + SITE_EMB, (uint64_t)lru * D + lane * 4);
         }
-        stg_stream(reinterpret_cast<float4*>(ea.out[su] + lru * D) + lane, x);
+        stg_stream(reinterpret_cast<float4*>(dst + (size_t)lru * D) + lane, x);
     }
 }
 
@@ -271,17 +276,18 @@ extern "C" int amid_embed_all_fwd(const float* table, int64_t V, const int64_t* 
                  aligned16(tmask_d2) && aligned16(pos_d1) && aligned16(pos_d2), "embed_all_fwd: misaligned buffer");
     int* err = err_flag();
     AMID_REQUIRE(err, "embed_all_fwd: cannot allocate error flag");
+    AMID_REQUIRE(n_items < (1ll << 30) && (int64_t)B * L < (1ll << 30), "embed_all_fwd: too many rows for one launch");
     EmbedAll ea;
-    ea.ids[0] = ids_items; ea.ids[1] = ids_d1; ea.ids[2] = ids_d2;
-    ea.pos[0] = pos_d1; ea.pos[1] = pos_d2;
-    ea.out[0] = items; ea.out[1] = x0_d1; ea.out[2] = x0_d2;
-    ea.tmask[0] = tmask_d1; ea.tmask[1] = tmask_d2;
-    ea.n[0] = n_items; ea.n[1] = (int64_t)B * L; ea.n[2] = (int64_t)B * L;
-    const int64_t total = ea.n[0] + ea.n[1] + ea.n[2];
+    ea.ids0 = ids_items; ea.ids1 = ids_d1; ea.ids2 = ids_d2;
+    ea.pos1 = pos_d1; ea.pos2 = pos_d2;
+    ea.out0 = items; ea.out1 = x0_d1; ea.out2 = x0_d2;
+    ea.tm1 = tmask_d1; ea.tm2 = tmask_d2;
+    ea.n0 = (uint32_t)n_items; ea.n1 = (uint32_t)((int64_t)B * L); ea.n2 = ea.n1;
+    const int64_t total = (int64_t)ea.n0 + ea.n1 + ea.n2;
     const int64_t warps = (total + RPW2 - 1) / RPW2;
     const DropCfg dc = make_drop(drop);
     AMID_K("k_embed_all", stream);
-    k_embed_all<<<(unsigned)((warps + 7) / 8), 256, 0, stream>>>(table, V, ea, L, dc, err);
+    k_embed_all<<<(unsigned)((warps + 7) / 8), 256, 0, stream>>>(table, V, ea, (uint32_t)L, dc, err);
     AMID_LAUNCH_CHECK("k_embed_all");
     return 0;
 }

@@ -79,6 +79,93 @@ k_mim_scores(const float* __restrict__ a, const float* __restrict__ b, int n, fl
     }
 }
 
+// Tensor-core version: the 64x64 similarity block as mma.sync m16n8k8 with the 3xTF32 split
+// (a = a_hi + a_lo, products a_hi b_hi + a_hi b_lo + a_lo b_hi), which keeps the scores at fp32
+// accuracy -- the hard gate p > ts downstream must not depend on the precision mode.
+constexpr int MLD2 = D + 4;    // 132: fragment loads are bank-conflict free (4g + t distinct)
+__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(x));
+    const float r = x - __uint_as_float(hi);
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(r));
+}
+__device__ __forceinline__ void mma8(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__global__ void __launch_bounds__(256)
+k_mim_scores_mma(const float* __restrict__ a, const float* __restrict__ b, int n, float* __restrict__ m) {
+    extern __shared__ __align__(16) float smem[];
+    __shared__ float wmax[8];
+    float* As = smem;
+    float* Bs = smem + MT * MLD2;
+    const int j = blockIdx.x;
+    const float* aj = a + (size_t)j * n * D;
+    const float* bj = b + (size_t)j * n * D;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+    const int rw = (warp & 3) * 16;      // this warp's 16 rows of the 64-row block
+    const int cw = (warp >> 2) * 32;     // and its 32 columns (4 n-tiles)
+    float best = -INFINITY;
+    for (int s0 = 0; s0 < n; s0 += MT) {
+        __syncthreads();
+        for (int idx = threadIdx.x; idx < MT * (D / 4); idx += 256) {
+            int r = idx >> 5, c4 = idx & 31;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (s0 + r < n) v = __ldg(reinterpret_cast<const float4*>(aj + (size_t)(s0 + r) * D) + c4);
+            *reinterpret_cast<float4*>(As + r * MLD2 + c4 * 4) = v;
+        }
+        for (int t0 = 0; t0 < n; t0 += MT) {
+            __syncthreads();
+            for (int idx = threadIdx.x; idx < MT * (D / 4); idx += 256) {
+                int r = idx >> 5, c4 = idx & 31;
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (t0 + r < n) v = __ldg(reinterpret_cast<const float4*>(bj + (size_t)(t0 + r) * D) + c4);
+                *reinterpret_cast<float4*>(Bs + r * MLD2 + c4 * 4) = v;
+            }
+            __syncthreads();
+            float acc[4][4];
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f;
+            const float* pa = As + (rw + g) * MLD2 + t;
+#pragma unroll 4
+            for (int k0 = 0; k0 < D; k0 += 8) {
+                uint32_t ah[4], al[4];
+                split_tf32(pa[k0], ah[0], al[0]);
+                split_tf32(pa[8 * MLD2 + k0], ah[1], al[1]);
+                split_tf32(pa[k0 + 4], ah[2], al[2]);
+                split_tf32(pa[8 * MLD2 + k0 + 4], ah[3], al[3]);
+#pragma unroll
+                for (int nt = 0; nt < 4; ++nt) {
+                    const float* pb = Bs + (cw + 8 * nt + g) * MLD2 + k0 + t;
+                    uint32_t bh0, bl0, bh1, bl1;
+                    split_tf32(pb[0], bh0, bl0);
+                    split_tf32(pb[4], bh1, bl1);
+                    mma8(acc[nt], al, bh0, bh1);
+                    mma8(acc[nt], ah, bl0, bl1);
+                    mma8(acc[nt], ah, bh0, bh1);
+                }
+            }
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) {
+                const int ra = s0 + rw + g, rb = ra + 8, c = t0 + cw + 8 * nt + 2 * t;
+                if (ra < n && c < n) best = fmaxf(best, acc[nt][0]);
+                if (ra < n && c + 1 < n) best = fmaxf(best, acc[nt][1]);
+                if (rb < n && c < n) best = fmaxf(best, acc[nt][2]);
+                if (rb < n && c + 1 < n) best = fmaxf(best, acc[nt][3]);
+            }
+        }
+    }
+    best = warp_max(best);
+    if (lane == 0) wmax[warp] = best;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float r = wmax[0];
+        for (int w = 1; w < 8; ++w) r = fmaxf(r, wmax[w]);
+        m[j] = r;
+    }
+}
+
 // softmax over the batch + hard gate + ordered compaction.  Single CTA, 1024 threads.
 __global__ void __launch_bounds__(1024)
 k_mim_gate(const float* __restrict__ m, const float* __restrict__ w_bs, int B, float ts, float* __restrict__ p,
@@ -334,6 +421,18 @@ extern "C" int amid_mim_scores(const float* a, const float* b, int32_t B, int32_
     AMID_K("k_mim_scores", (cudaStream_t)s_);
     k_mim_scores<<<B, 256, MIM_SMEM, (cudaStream_t)s_>>>(a, b, n, m);
     AMID_LAUNCH_CHECK("k_mim_scores");
+    return 0;
+}
+
+extern "C" int amid_mim_scores_tc(const float* a, const float* b, int32_t B, int32_t n, float* m, amid_stream_t s_) {
+    AMID_REQUIRE(a && b && m && B > 0 && n > 0, "mim_scores_tc: bad argument");
+    AMID_REQUIRE(aligned16(a) && aligned16(b), "mim_scores_tc: misaligned buffer");
+    const size_t smem = (size_t)2 * MT * MLD2 * sizeof(float);
+    cudaError_t e = cudaFuncSetAttribute((const void*)k_mim_scores_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return set_error(-3, "mim_scores_tc: smem attribute: %s", cudaGetErrorString(e));
+    AMID_K("k_mim_scores_mma", s_);
+    k_mim_scores_mma<<<B, 256, smem, (cudaStream_t)s_>>>(a, b, n, m);
+    AMID_LAUNCH_CHECK("k_mim_scores_mma");
     return 0;
 }
 

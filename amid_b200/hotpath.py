@@ -176,10 +176,10 @@ def _mim_forward(P, name: str, m_global: torch.Tensor, other: torch.Tensor, n: i
     return st
 
 
-def _mim_scores(a: torch.Tensor, b: torch.Tensor, n: int, dist: Optional[DistCtx]) -> torch.Tensor:
+def _mim_scores(a: torch.Tensor, b: torch.Tensor, n: int, dist: Optional[DistCtx], tc: bool = False) -> torch.Tensor:
     Bl = a.numel() // (n * D)
     m = torch.empty(Bl, device=a.device, dtype=torch.float32)
-    call("amid_mim_scores", _ptr(a), _ptr(b), Bl, n, _ptr(m), _stream())
+    call("amid_mim_scores_tc" if tc else "amid_mim_scores", _ptr(a), _ptr(b), Bl, n, _ptr(m), _stream())
     if dist is not None and dist.world > 1:
         mg = torch.empty(Bl * dist.world, device=a.device, dtype=torch.float32)
         dist.all_gather_into(mg, m)
@@ -261,7 +261,7 @@ def forward(P: Dict[str, torch.Tensor], cfg: Config, i_node, neg_samples, seq_d1
             # model_seq.py:422-424  InnerComp before the encoder
             raw = f(B, L, D)
             call("amid_emb_gather_fwd", _ptr(table), V, _ptr(seqs[k]), B * L, _ptr(raw), s)
-            mg = _mim_scores(raw, raw, L, dist)
+            mg = _mim_scores(raw, raw, L, dist, cfg.precision != "fp32")
             st = _mim_forward(P, f"inc_d{k + 1}", mg, raw, L, cfg.ts1, j0, dist, want_esum=False)
             cat = f(B, 2 * L, D)
             call("amid_mim_concat", _ptr(raw), _ptr(st.E), B, L, _ptr(cat), s)
@@ -285,7 +285,7 @@ def forward(P: Dict[str, torch.Tensor], cfg: Config, i_node, neg_samples, seq_d1
     us = [f(B, D), f(B, D)]
     ctx.itcs = []
     if cfg.isItC:
-        mg = _mim_scores(encs[0], encs[1], Le, dist)          # max of a matrix == max of its transpose
+        mg = _mim_scores(encs[0], encs[1], Le, dist, cfg.precision != "fp32")   # max of a matrix == max of its transpose
         for k in range(2):
             st = _mim_forward(P, f"itc_d{k + 1}", mg, encs[1 - k].view(B, Le, D), Le, cfg.ts2, j0, dist, True)
             ctx.itcs.append(st)

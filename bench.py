@@ -190,7 +190,7 @@ def kernel_work(name, B, L, C):
         "k_attn_fwd_mma": ("flop", attn_full), "k_attn_bwd_mma": ("flop", 2.5 * attn_full),
         "k_seq_embed": ("byte", rows_seq * (2 * D * 4 + 8)), "k_gather": ("byte", rows_items * (2 * D * 4 + 8)),
         "k_embed_all": ("byte", (2 * rows_seq + rows_items) * (2 * D * 4 + 8)),
-        "k_mim_scores": ("flop", 2.0 * B * L * L * D),
+        "k_mim_scores": ("flop", 2.0 * B * L * L * D), "k_mim_scores_mma": ("flop", 2.0 * B * L * L * D),
     }
     return table.get(name)
 

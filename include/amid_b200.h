@@ -149,6 +149,8 @@ int amid_encoder_bwd_bf16(const amid_encoder_tensors* P, const float* x0, const 
 /* m[j] = max_{s,t} <a[j,s,:], b[j,t,:]>,  a,b: [B,n,128]  (the [bs,B,n,n] matmul+max of
  * model_seq.py:489-490 without its redundant outer axis). */
 int amid_mim_scores(const float* a, const float* b, int32_t B, int32_t n, float* m, amid_stream_t stream);
+/* the same on the tensor cores (mma.sync TF32 with the 3xTF32 split: fp32-accurate scores) */
+int amid_mim_scores_tc(const float* a, const float* b, int32_t B, int32_t n, float* m, amid_stream_t stream);
 /* p = softmax_j(m) over the (global) batch, g = 1[p > ts], coef[j] = w_bs[j]*g[j];
  * scal[0] = sum_j w_bs[j]; active list = indices with g=1 (ascending), n_active[0]. */
 int amid_mim_gate(const float* m, const float* w_bs, int32_t Bglobal, float ts, float* p, float* gate, float* coef,

@@ -269,6 +269,47 @@ def test_dropin_unchanged_driver_loop_with_torch_adam():
     assert sd["item_emb_layer.emb_item.weight"].shape == (V, D)
 
 
+def test_trainer_dr_two_phase_two_adams_vs_oracle():
+    """train_sr_dr.py: phase 1 (loss_cls + dr_e_w * loss_dr_e, `optimizer`) and phase 2 (loss_dr_r,
+    `optimizer2` with lr * lr2) interleave on the same parameters, each Adam with its own state and
+    dense semantics on the table."""
+    from amid_b200.engine import Trainer
+    B, L, C, V = 8, 12, 2, 53
+    rng = np.random.default_rng(21)
+    P = make_params(33, V, D, L, HID, B, isDR=True)
+    m = build_model(P, V, L, B, ts2=0.3, isDR=True, drop_p=0.0).train()
+    tr = Trainer(m, lr=5e-4, lr2=0.5, dr_e_w=0.01)
+    Po = {k: v.clone().requires_grad_(True) for k, v in P.items()}
+    st = [{k: (torch.zeros_like(v), torch.zeros_like(v)) for k, v in Po.items()} for _ in range(2)]
+    steps = [0, 0]
+    for phase in (1, 2, 2, 1, 2, 1):
+        b = random_batch(rng, B, L, C, V)
+        losses = tr.step(to_cuda(b), phase=phase)
+        outs = oracle_forward(Po, b, isInC=False, isItC=True, ts1=0.5, ts2=0.3, isDR=True)
+        lab, dom, ob = b["label"], b["domain_id"], b["ob_label"]
+        if phase == 1:
+            lc, le = O.loss_cls(outs[0], outs[1], lab, dom), O.loss_dr_e(*outs, lab, dom)
+            lo = lc + 0.01 * le
+            assert_close(losses[0], lc, 3e-5, 0)
+            assert_close(losses[1], le, 3e-5, 1e-7)
+        else:
+            lo = O.loss_dr_r(*outs, lab, dom, ob)
+            assert_close(losses[2], lo, 3e-5, 1e-7)
+        for v in Po.values():
+            v.grad = None
+        lo.backward()
+        oi = phase - 1
+        steps[oi] += 1
+        with torch.no_grad():
+            for k, v in Po.items():
+                g = v.grad if v.grad is not None else torch.zeros_like(v)
+                O.adam_step(v, g, st[oi][k][0], st[oi][k][1], steps[oi], 5e-4 if oi == 0 else 2.5e-4)
+    tr.flush()
+    named = dict(m.named_parameters())
+    for k, v in Po.items():
+        assert_close(named[k], v, 0, 3e-5, k)
+
+
 # ------------------------------------------------------------------ train mode WITH dropout: oracle + our masks
 @pytest.mark.parametrize("B,L,C,isDR", [(6, 9, 2, False), (5, 20, 3, True)])
 def test_train_dropout_vs_oracle_with_exported_masks(B, L, C, isDR):

@@ -56,6 +56,19 @@ def test_tc_wgrad_bf16_mn_major(M, ctas):
     assert (got - ref).abs().max().item() < 1e-4 * ref.abs().max().item() + 1e-3
 
 
+@pytest.mark.parametrize("B,n", [(1, 1), (5, 7), (3, 64), (4, 200), (2, 130)])
+def test_mim_scores_3xtf32_matches_fp32(B, n):
+    from amid_b200 import hotpath as hp
+    g = torch.Generator().manual_seed(B * 100 + n)
+    a = torch.randn(B, n, D, generator=g).cuda()
+    b = torch.randn(B, n, D, generator=g).cuda()
+    m_tc = hp._mim_scores(a, b, n, None, True)
+    m_ref = hp._mim_scores(a, b, n, None, False)
+    want = torch.einsum("jsd,jtd->jst", a.double(), b.double()).flatten(1).max(1)[0].float()
+    assert (m_ref - want).abs().max().item() < 1e-4
+    assert (m_tc - want).abs().max().item() < 1e-4
+
+
 # ------------------------------------------------------------------ the encoder on the tensor-core path
 # TF32 operands: 10-bit mantissa, truncated by the MMA unit.  Stated tolerance for this path:
 # probabilities 5e-3 abs, losses 3e-3 rel, gradient tensors 4e-2 in relative Frobenius norm (a ReLU
