@@ -32,6 +32,7 @@ class Config:
     ts2: float
     isDR: bool
     drop_p: float = 0.5          # model_seq.py:335,350,355 (hard-coded in the reference)
+    overlap_encoders: bool = True   # run the two domain encoders on two streams
     precision: str = "fp32"      # GEMM stages: "fp32" exact CUDA-core tiles | "tf32" / "bf16" tcgen05 tiles, fp32 accumulate
 
     @property
@@ -63,6 +64,48 @@ class DistCtx:
 
     def all_reduce(self, t):
         self.dist.all_reduce(t, group=self.group)
+
+
+_SIDE_STREAMS = {}
+
+
+def _side_stream(dev) -> "torch.cuda.Stream":
+    """Second stream per device: the two domain encoders are independent (sac1 / sac2, model_seq.py:425-426),
+    so their kernel chains run concurrently and fill each other's wave tails."""
+    key = torch.device(dev).index if torch.device(dev).index is not None else torch.cuda.current_device()
+    if key not in _SIDE_STREAMS:
+        _SIDE_STREAMS[key] = torch.cuda.Stream(device=key)
+    return _SIDE_STREAMS[key]
+
+
+class _Fork:
+    """Run branch 1 on the side stream while branch 0 stays on the current stream; join at exit.
+    Every buffer is allocated on the current stream BEFORE the fork (caching-allocator safety)."""
+
+    def __init__(self, dev, enabled: bool):
+        self.enabled = enabled
+        self.main = torch.cuda.current_stream()
+        self.side = _side_stream(dev) if enabled else None
+
+    def __enter__(self):
+        if self.enabled:
+            ev = torch.cuda.Event()
+            ev.record(self.main)
+            self.side.wait_event(ev)
+        return self
+
+    def branch(self, k: int):
+        import contextlib
+        if self.enabled and k == 1:
+            return torch.cuda.stream(self.side)
+        return contextlib.nullcontext()
+
+    def __exit__(self, *exc):
+        if self.enabled:
+            ev = torch.cuda.Event()
+            ev.record(self.side)
+            self.main.wait_event(ev)
+        return False
 
 
 def _ptr(t: Optional[torch.Tensor]):
@@ -271,14 +314,19 @@ def forward(P: Dict[str, torch.Tensor], cfg: Config, i_node, neg_samples, seq_d1
             raws.append(raw)
         else:
             x0, tm = pre_x0[k], pre_tm[k]
-        sv = _Saved(B, Le, dev)
-        enc = f(B * Le, D)
-        ws_bytes = _abi.lib().amid_encoder_fwd_workspace_bytes(B, Le)
-        ws = torch.empty(ws_bytes, device=dev, dtype=torch.uint8)
-        es = encoder_struct(P, sac)
-        call(_ENC_FWD[cfg.precision], C.byref(es), _ptr(x0), _ptr(tm), B, Le, C.byref(drop), C.byref(sv.struct), _ptr(enc),
-             _ptr(ws), ws_bytes, s)
-        encs.append(enc); x0s.append(x0); tms.append(tm); saveds.append(sv)
+        x0s.append(x0); tms.append(tm)
+    ws_bytes = _abi.lib().amid_encoder_fwd_workspace_bytes(B, Le)
+    wss = [torch.empty(ws_bytes, device=dev, dtype=torch.uint8) for _ in range(2)]
+    for k in range(2):
+        saveds.append(_Saved(B, Le, dev))
+        encs.append(f(B * Le, D))
+    with _Fork(dev, cfg.overlap_encoders) as fork:
+        for k, sac in enumerate(("sac1.", "sac2.")):
+            with fork.branch(k):
+                drop = _dropout(cfg, train, seed, 8 * k)
+                es = encoder_struct(P, sac)
+                call(_ENC_FWD[cfg.precision], C.byref(es), _ptr(x0s[k]), _ptr(tms[k]), B, Le, C.byref(drop),
+                     C.byref(saveds[k].struct), _ptr(encs[k]), _ptr(wss[k]), ws_bytes, _stream())
     ctx.encs, ctx.x0s, ctx.tms, ctx.saveds, ctx.incs, ctx.raws = encs, x0s, tms, saveds, incs, raws
 
     # a6 + a7: ItC and mean pool
@@ -367,26 +415,29 @@ def backward(P: Dict[str, torch.Tensor], cfg: Config, ctx: Ctx, dprobs: torch.Te
 
     # a3-a5 backward, then a2 / a1
     wsb = _abi.lib().amid_encoder_bwd_workspace_bytes(B, Le)
-    ws = torch.empty(wsb, device=dev, dtype=torch.uint8)
-    for k, sac in enumerate(("sac1.", "sac2.")):
-        drop = _dropout(cfg, ctx.train, ctx.seed, 8 * k)
-        es = encoder_struct(P, sac)
-        gstruct = encoder_struct(G, sac)
-        dx0 = f(B * Le, D) if cfg.isInC else dseq[k]
-        call(_ENC_BWD[cfg.precision], C.byref(es), _ptr(ctx.x0s[k]), _ptr(ctx.tms[k]), B, Le, C.byref(drop),
-             C.byref(ctx.saveds[k].struct), _ptr(ctx.encs[k]), _ptr(d_encs[k]), C.byref(gstruct), _ptr(dx0), _ptr(ws),
-             wsb, s)
-        gpos = G[sac + "pos_emb.weight"]
-        call("amid_seq_embed_bwd", _ptr(dx0), _ptr(ctx.tms[k]), B, Le, _ptr(gpos), C.byref(drop), s)
-        if cfg.isInC:
-            # dx0 is the gradient of cat(seq, E): the E half summed over the batch is exactly
-            # what amid_seq_embed_bwd just accumulated into rows [L, 2L) of the positional grad.
-            st = ctx.incs[k]
-            dE = gpos[L:2 * L].clone()
-            if dist is not None and dist.world > 1:
-                dist.all_reduce(dE)
-            dseq[k].view(B, L, D).copy_(dx0.view(B, 2 * L, D)[:, :L])
-            _mim_backward(P, G, st, dE, dseq[k], ctx.j0, dist)
+    wss = [torch.empty(wsb, device=dev, dtype=torch.uint8) for _ in range(2)]
+    dx0s = [f(B * Le, D) if cfg.isInC else dseq[k] for k in range(2)]
+    with _Fork(dev, cfg.overlap_encoders and not cfg.isInC) as fork:
+        for k, sac in enumerate(("sac1.", "sac2.")):
+            with fork.branch(k):
+                drop = _dropout(cfg, ctx.train, ctx.seed, 8 * k)
+                es = encoder_struct(P, sac)
+                gstruct = encoder_struct(G, sac)
+                dx0 = dx0s[k]
+                call(_ENC_BWD[cfg.precision], C.byref(es), _ptr(ctx.x0s[k]), _ptr(ctx.tms[k]), B, Le, C.byref(drop),
+                     C.byref(ctx.saveds[k].struct), _ptr(ctx.encs[k]), _ptr(d_encs[k]), C.byref(gstruct), _ptr(dx0),
+                     _ptr(wss[k]), wsb, _stream())
+                gpos = G[sac + "pos_emb.weight"]
+                call("amid_seq_embed_bwd", _ptr(dx0), _ptr(ctx.tms[k]), B, Le, _ptr(gpos), C.byref(drop), _stream())
+                if cfg.isInC:
+                    # dx0 is the gradient of cat(seq, E): the E half summed over the batch is exactly
+                    # what amid_seq_embed_bwd just accumulated into rows [L, 2L) of the positional grad.
+                    st = ctx.incs[k]
+                    dE = gpos[L:2 * L].clone()
+                    if dist is not None and dist.world > 1:
+                        dist.all_reduce(dE)
+                    dseq[k].view(B, L, D).copy_(dx0.view(B, 2 * L, D)[:, :L])
+                    _mim_backward(P, G, st, dE, dseq[k], ctx.j0, dist)
     return G, ids_all, rows_all
 
 
