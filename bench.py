@@ -310,13 +310,17 @@ def run_ours(a):
     ms_e2e = timed(host_step, a.steps)
     h2d = sum(v.numel() * (4 if k == "label" else 8) for k, v in host[0].items())
 
-    # per-kernel CUDA-event profile of 3 more steps of the same workload (rank 0 reports)
+    # per-kernel CUDA-event profile of 3 more steps of the same workload (rank 0 reports).  The two encoder
+    # chains are serialised for these steps: with both streams active a kernel's event interval would also
+    # contain its neighbour's work.
+    model.cfg.overlap_encoders = False
     _abi.profile(True)
     prof_steps = 3
     for i in range(prof_steps):
         dev_step(i)
     rep = _abi.profile_report()
     _abi.profile(False)
+    model.cfg.overlap_encoders = True
     final_loss = float(tr.last_losses[0].item())
 
     if rank != 0:
