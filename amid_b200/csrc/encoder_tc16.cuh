@@ -342,17 +342,30 @@ k_ffn_bwd_16(const float* __restrict__ dxo, const float* __restrict__ h, const f
     const int row0 = blockIdx.x * 128;
     setup(sh, 128);
     load_w16_async(sm.W, W2t);
-#pragma unroll 2
-    for (int idx = threadIdx.x; idx < 128 * 32; idx += 256) {      // A = do2 = dropout2-mask * (dxo * ~tmask)
-        const int r = idx >> 5, c4 = idx & 31, grr = row0 + r;
-        float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (grr < M) {
-            g = __ldg(reinterpret_cast<const float4*>(dxo + (size_t)grr * D) + c4);
-            g = apply_tmask(g, __ldg(reinterpret_cast<const uint4*>(tmask) + grr), c4);
-            if (dc.train) g = drop4(g, dc, site2, (uint64_t)grr * D + c4 * 4);
-            *(reinterpret_cast<float4*>(do2 + (size_t)grr * D) + c4) = g;
+    {   // A = do2 = dropout2-mask * (dxo * ~tmask): warp per row, all 16 row loads of a thread in flight at once
+        const int c4 = threadIdx.x & 31, rb = threadIdx.x >> 5;
+        float4 g[16];
+        uint4 twl = make_uint4(0u, 0u, 0u, 0u);
+        if (c4 < 16 && row0 + c4 * 8 + rb < M) twl = __ldg(reinterpret_cast<const uint4*>(tmask) + row0 + c4 * 8 + rb);   // lane i: row of iteration i
+#pragma unroll
+        for (int it = 0; it < 16; ++it) {
+            const int grr = row0 + it * 8 + rb;
+            g[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (grr < M) g[it] = __ldg(reinterpret_cast<const float4*>(dxo + (size_t)grr * D) + c4);
         }
-        *reinterpret_cast<uint2*>(sm.A + tile16_off8(r, c4 >> 1) + (c4 & 1) * 8) = make_uint2(pack_bf16(g.x, g.y), pack_bf16(g.z, g.w));
+#pragma unroll
+        for (int it = 0; it < 16; ++it) {
+            const int r = it * 8 + rb, grr = row0 + r;
+            uint4 tw;
+            tw.x = __shfl_sync(0xffffffffu, twl.x, it); tw.y = __shfl_sync(0xffffffffu, twl.y, it);
+            tw.z = __shfl_sync(0xffffffffu, twl.z, it); tw.w = __shfl_sync(0xffffffffu, twl.w, it);
+            float4 gg = apply_tmask(g[it], tw, c4);
+            if (grr < M) {
+                if (dc.train) gg = drop4(gg, dc, site2, (uint64_t)grr * D + c4 * 4);
+                *(reinterpret_cast<float4*>(do2 + (size_t)grr * D) + c4) = gg;
+            }
+            *reinterpret_cast<uint2*>(sm.A + tile16_off8(r, c4 >> 1) + (c4 & 1) * 8) = make_uint2(pack_bf16(gg.x, gg.y), pack_bf16(gg.z, gg.w));
+        }
     }
     Epi e;
     const int gr = row0 + e.row;
