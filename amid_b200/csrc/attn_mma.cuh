@@ -81,12 +81,20 @@ __device__ __forceinline__ void mma_xt(float (&d)[4], const uint32_t (&a)[2][4],
     mma_tf32(d, a[0], fbits(p[0]), fbits(p[4]));
     mma_tf32(d, a[1], fbits(p[8]), fbits(p[12]));
 }
-// acc[dt][..] += P[16 x 8 (relabelled)] * X[n0..n0+8][16]   (X rows are the k index, permuted 2t / 2t+1)
+// acc[dt][..] += P[16 x 8 (relabelled)] * X[n0..n0+8][16]   (X rows are the k index, permuted 2t / 2t+1).
+// The output features are permuted too -- n index g of n-tile dt is feature 2g+dt -- so the B operands of both
+// n-tiles come from one 64-bit load per key row and a thread ends up owning the four consecutive features
+// 4t..4t+3 of its rows: {acc[0][0], acc[1][0], acc[0][1], acc[1][1]} (row g) and the [..][2], [..][3] set (row g+8).
 __device__ __forceinline__ void mma_px(float (&acc)[2][4], const float (&p)[4], const float* x, int n0, int g, int t) {
     const uint32_t a[4] = {fbits(p[0]), fbits(p[2]), fbits(p[1]), fbits(p[3])};
-    const float* pa = x + (n0 + 2 * t) * LDS + g;
-    mma_tf32(acc[0], a, fbits(pa[0]), fbits(pa[LDS]));
-    mma_tf32(acc[1], a, fbits(pa[8]), fbits(pa[LDS + 8]));
+    const float* pa = x + (n0 + 2 * t) * LDS + 2 * g;
+    const float2 u = *reinterpret_cast<const float2*>(pa), w = *reinterpret_cast<const float2*>(pa + LDS);
+    mma_tf32(acc[0], a, fbits(u.x), fbits(w.x));
+    mma_tf32(acc[1], a, fbits(u.y), fbits(w.y));
+}
+// features 4t..4t+3 of row g (hi = 0) or g+8 (hi = 1) out of a mma_px accumulator, scaled
+__device__ __forceinline__ float4 px_row(const float (&acc)[2][4], int hi, float sc) {
+    return make_float4(acc[0][2 * hi] * sc, acc[1][2 * hi] * sc, acc[0][2 * hi + 1] * sc, acc[1][2 * hi + 1] * sc);
 }
 __device__ __forceinline__ float quad_max(float v) {
     v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 1));
@@ -187,23 +195,20 @@ k_attn_fwd_mma(const float* __restrict__ q, const float* __restrict__ k, const f
                     bool kp[4];
                     keep_rows(dc, site, rk, n0, t, kp);
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) p[e] = kp[e] ? p[e] * dc.scale : 0.f;
+                    for (int e = 0; e < 4; ++e) p[e] = kp[e] ? p[e] : 0.f;      // 1/(1-p) folded into the final scale
                 }
                 mma_px(acc, p, vs, n0, g, t);
             }
         }
         l0 = quad_sum(l0); l1 = quad_sum(l1);
-        const float i0 = 1.0f / l0, i1 = 1.0f / l1;
+        const float osc = dc.train ? dc.scale : 1.0f;
+        const float i0 = osc / l0, i1 = osc / l1;
         if (row_a < L) {
-#pragma unroll
-            for (int dt = 0; dt < 2; ++dt)
-                *reinterpret_cast<float2*>(o + base + (size_t)row_a * D + 8 * dt + 2 * t) = make_float2(acc[dt][0] * i0, acc[dt][1] * i0);
+            *reinterpret_cast<float4*>(o + base + (size_t)row_a * D + 4 * t) = px_row(acc, 0, i0);
             if (t == 0) lse[bhL + row_a] = m0 * LN2 + logf(l0);
         }
         if (row_b < L) {
-#pragma unroll
-            for (int dt = 0; dt < 2; ++dt)
-                *reinterpret_cast<float2*>(o + base + (size_t)row_b * D + 8 * dt + 2 * t) = make_float2(acc[dt][2] * i1, acc[dt][3] * i1);
+            *reinterpret_cast<float4*>(o + base + (size_t)row_b * D + 4 * t) = px_row(acc, 1, i1);
             if (t == 0) lse[bhL + row_b] = m1 * LN2 + logf(l1);
         }
     }
@@ -231,7 +236,8 @@ k_attn_bwd_mma(const float* __restrict__ q, const float* __restrict__ k, const f
     const size_t base = (size_t)b * L * D + hd * DH;
     stage(qs, q + base, L, Lpad, LOG2E);
     stage(ks, k + base, L, Lpad);
-    stage(vs, v + base, L, Lpad);
+    const float sc = dc.train ? dc.scale : 1.0f;      // dropout scale rides on the staged v (dP) and the dv store
+    stage(vs, v + base, L, Lpad, sc);
     stage(gs, dO + base, L, Lpad);
     for (int i = threadIdx.x; i < Lpad; i += blockDim.x) {
         float s = 0.f, le = 0.f;
@@ -251,7 +257,6 @@ k_attn_bwd_mma(const float* __restrict__ q, const float* __restrict__ k, const f
     __syncthreads();
     const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
     const uint64_t bhL = (uint64_t)bh * L;
-    const float sc = dc.train ? dc.scale : 1.0f;
     // Work items, heaviest first: item 2n = pass A on query tile ntile-1-n, item 2n+1 = pass B on key tile n.
     for (;;) {
         const int item = next_item(&queue, lane);
@@ -277,7 +282,7 @@ k_attn_bwd_mma(const float* __restrict__ q, const float* __restrict__ k, const f
                     bool kp[4];
                     keep_rows(dc, site, rk, n0, t, kp);
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) dp[e] = kp[e] ? dp[e] * sc : 0.f;
+                    for (int e = 0; e < 4; ++e) dp[e] = kp[e] ? dp[e] : 0.f;
                 }
                 float ds[4];
                 ds[0] = ex2(s[0] - la) * (dp[0] - Da); ds[1] = ex2(s[1] - la) * (dp[1] - Da);
@@ -291,16 +296,8 @@ k_attn_bwd_mma(const float* __restrict__ q, const float* __restrict__ k, const f
                 }
                 mma_px(acc, ds, ks, n0, g, t);
             }
-            if (row_a < L) {
-#pragma unroll
-                for (int dt = 0; dt < 2; ++dt)
-                    *reinterpret_cast<float2*>(dq + base + (size_t)row_a * D + 8 * dt + 2 * t) = make_float2(acc[dt][0] * 0.25f, acc[dt][1] * 0.25f);
-            }
-            if (row_b < L) {
-#pragma unroll
-                for (int dt = 0; dt < 2; ++dt)
-                    *reinterpret_cast<float2*>(dq + base + (size_t)row_b * D + 8 * dt + 2 * t) = make_float2(acc[dt][2] * 0.25f, acc[dt][3] * 0.25f);
-            }
+            if (row_a < L) *reinterpret_cast<float4*>(dq + base + (size_t)row_a * D + 4 * t) = px_row(acc, 0, 0.25f);
+            if (row_b < L) *reinterpret_cast<float4*>(dq + base + (size_t)row_b * D + 4 * t) = px_row(acc, 1, 0.25f);
         } else {
             // ---------------- pass B: key tile; S^T = K Q^T so that P^T / dS^T land in accumulator layout
             const int j0 = (item >> 1) * 16;
@@ -340,10 +337,10 @@ k_attn_bwd_mma(const float* __restrict__ q, const float* __restrict__ k, const f
                     // r[0]=(qa,key_a) r[1]=(qb,key_a) r[2]=(qa,key_b) r[3]=(qb,key_b); lane inside the group = key & 3
                     const bool k0 = rng_keep(r[0], key_a & 3, dc.thr16), k1 = rng_keep(r[1], key_a & 3, dc.thr16);
                     const bool k2 = rng_keep(r[2], key_b & 3, dc.thr16), k3 = rng_keep(r[3], key_b & 3, dc.thr16);
-                    pd[0] = k0 ? p[0] * sc : 0.f; pd[1] = k1 ? p[1] * sc : 0.f;
-                    pd[2] = k2 ? p[2] * sc : 0.f; pd[3] = k3 ? p[3] * sc : 0.f;
-                    dpt[0] = k0 ? dpt[0] * sc : 0.f; dpt[1] = k1 ? dpt[1] * sc : 0.f;
-                    dpt[2] = k2 ? dpt[2] * sc : 0.f; dpt[3] = k3 ? dpt[3] * sc : 0.f;
+                    pd[0] = k0 ? p[0] : 0.f; pd[1] = k1 ? p[1] : 0.f;
+                    pd[2] = k2 ? p[2] : 0.f; pd[3] = k3 ? p[3] : 0.f;
+                    dpt[0] = k0 ? dpt[0] : 0.f; dpt[1] = k1 ? dpt[1] : 0.f;
+                    dpt[2] = k2 ? dpt[2] : 0.f; dpt[3] = k3 ? dpt[3] : 0.f;
                 }
                 float ds[4];
                 ds[0] = p[0] * (dpt[0] - Dqa); ds[1] = p[1] * (dpt[1] - Dqb);
@@ -352,18 +349,12 @@ k_attn_bwd_mma(const float* __restrict__ q, const float* __restrict__ k, const f
                 mma_px(dka, ds, qs, i0, g, t);          // dk[key] += dS^T[key][query] q[query] (q carries log2e)
             }
             if (key_a < L) {
-#pragma unroll
-                for (int dt = 0; dt < 2; ++dt) {
-                    *reinterpret_cast<float2*>(dk + base + (size_t)key_a * D + 8 * dt + 2 * t) = make_float2(dka[dt][0] * LN2, dka[dt][1] * LN2);
-                    *reinterpret_cast<float2*>(dv + base + (size_t)key_a * D + 8 * dt + 2 * t) = make_float2(dva[dt][0], dva[dt][1]);
-                }
+                *reinterpret_cast<float4*>(dk + base + (size_t)key_a * D + 4 * t) = px_row(dka, 0, LN2);
+                *reinterpret_cast<float4*>(dv + base + (size_t)key_a * D + 4 * t) = px_row(dva, 0, sc);
             }
             if (key_b < L) {
-#pragma unroll
-                for (int dt = 0; dt < 2; ++dt) {
-                    *reinterpret_cast<float2*>(dk + base + (size_t)key_b * D + 8 * dt + 2 * t) = make_float2(dka[dt][2] * LN2, dka[dt][3] * LN2);
-                    *reinterpret_cast<float2*>(dv + base + (size_t)key_b * D + 8 * dt + 2 * t) = make_float2(dva[dt][2], dva[dt][3]);
-                }
+                *reinterpret_cast<float4*>(dk + base + (size_t)key_b * D + 4 * t) = px_row(dka, 1, LN2);
+                *reinterpret_cast<float4*>(dv + base + (size_t)key_b * D + 4 * t) = px_row(dva, 1, sc);
             }
         }
     }

@@ -30,10 +30,9 @@ __device__ __forceinline__ float4 ld_row4(const float* g, uint32_t row, int lane
 }
 __device__ __forceinline__ void acc4(float4& a, const float4 b) { a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w; }
 
-// sum rows vals[lo..hi) in order (4 independent loads in flight, added in index order)
-__device__ __forceinline__ float4 sum_range(const float* __restrict__ grads, const uint32_t* __restrict__ vals, int lo,
-                                            int hi, int lane) {
-    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+// s += rows vals[lo..hi) in index order (4 independent loads in flight)
+__device__ __forceinline__ void sum_range_into(float4& s, const float* __restrict__ grads, const uint32_t* __restrict__ vals,
+                                               int lo, int hi, int lane) {
     int p = lo;
     for (; p + 4 <= hi; p += 4) {
         const float4 a = ld_row4(grads, vals[p], lane), b = ld_row4(grads, vals[p + 1], lane);
@@ -41,6 +40,11 @@ __device__ __forceinline__ float4 sum_range(const float* __restrict__ grads, con
         acc4(s, a); acc4(s, b); acc4(s, c); acc4(s, d);
     }
     for (; p < hi; ++p) acc4(s, ld_row4(grads, vals[p], lane));
+}
+__device__ __forceinline__ float4 sum_range(const float* __restrict__ grads, const uint32_t* __restrict__ vals, int lo,
+                                            int hi, int lane) {
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    sum_range_into(s, grads, vals, lo, hi, lane);
     return s;
 }
 __device__ __forceinline__ void chunk_bounds(int off, int cnt, int ch, int* lo, int* hi) {
@@ -49,36 +53,57 @@ __device__ __forceinline__ void chunk_bounds(int off, int cnt, int ch, int* lo, 
     *hi = off + min(cnt, (ch + 1) * per);
 }
 
-// warp per unique id
+// One warp per SEG_PER_WARP consecutive unique ids: the segment descriptors and the first source row of every
+// segment are fetched together (most segments have one or two rows), the remaining rows are added in order.
+constexpr int SEG_PER_WARP = 4;
 __global__ void __launch_bounds__(256)
 k_segreduce(const float* __restrict__ grads, const uint32_t* __restrict__ vals, const uint32_t* __restrict__ ukeys,
             const int* __restrict__ counts, const int* __restrict__ offsets, const int* __restrict__ n_uniq,
             int64_t* __restrict__ uniq_ids, float* __restrict__ uniq_grads, int* __restrict__ long_list,
             int* __restrict__ n_long) {
     const int lane = threadIdx.x & 31;
-    const int u = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
-    if (u >= n_uniq[0]) return;
-    const int off = offsets[u], cnt = counts[u];
-    if (lane == 0) uniq_ids[u] = (int64_t)ukeys[u];
-    float4 s;
-    if (cnt <= LONG_SEG) {
-        s = sum_range(grads, vals, off, off + cnt, lane);
-    } else {
-        int slot = 0;
-        if (lane == 0) slot = atomicAdd(n_long, 1);
-        slot = __shfl_sync(0xffffffffu, slot, 0);
-        if (slot < MAX_LONG) {           // handed to the parallel path (identical summation order)
-            if (lane == 0) long_list[slot] = u;
-            return;
-        }
-        s = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int ch = 0; ch < LONG_CHUNKS; ++ch) {
-            int lo, hi;
-            chunk_bounds(off, cnt, ch, &lo, &hi);
-            acc4(s, sum_range(grads, vals, lo, hi, lane));
-        }
+    const int u0 = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * SEG_PER_WARP;
+    const int nu = n_uniq[0];
+    if (u0 >= nu) return;
+    int off = 0, cnt = 0;
+    uint32_t first = 0;
+    if (lane < SEG_PER_WARP && u0 + lane < nu) {
+        off = offsets[u0 + lane];
+        cnt = counts[u0 + lane];
+        uniq_ids[u0 + lane] = (int64_t)ukeys[u0 + lane];
+        first = vals[off];
     }
-    reinterpret_cast<float4*>(uniq_grads + (size_t)u * D)[lane] = s;
+    float4 s[SEG_PER_WARP];
+    int offs[SEG_PER_WARP], cnts[SEG_PER_WARP];
+#pragma unroll
+    for (int j = 0; j < SEG_PER_WARP; ++j) {
+        offs[j] = __shfl_sync(0xffffffffu, off, j);
+        cnts[j] = __shfl_sync(0xffffffffu, cnt, j);
+        s[j] = ld_row4(grads, __shfl_sync(0xffffffffu, first, j), lane);      // past-the-end slots read row 0, unused
+    }
+#pragma unroll
+    for (int j = 0; j < SEG_PER_WARP; ++j) {
+        const int u = u0 + j;
+        if (u >= nu) break;
+        if (cnts[j] <= LONG_SEG) {
+            sum_range_into(s[j], grads, vals, offs[j] + 1, offs[j] + cnts[j], lane);
+        } else {
+            int slot = 0;
+            if (lane == 0) slot = atomicAdd(n_long, 1);
+            slot = __shfl_sync(0xffffffffu, slot, 0);
+            if (slot < MAX_LONG) {           // handed to the parallel path (identical summation order)
+                if (lane == 0) long_list[slot] = u;
+                continue;
+            }
+            s[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int ch = 0; ch < LONG_CHUNKS; ++ch) {
+                int lo, hi;
+                chunk_bounds(offs[j], cnts[j], ch, &lo, &hi);
+                acc4(s[j], sum_range(grads, vals, lo, hi, lane));
+            }
+        }
+        reinterpret_cast<float4*>(uniq_grads + (size_t)u * D)[lane] = s[j];
+    }
 }
 // grid (LONG_CHUNKS, MAX_LONG), one warp per chunk of a long segment
 __global__ void __launch_bounds__(32)
@@ -335,7 +360,7 @@ extern "C" int amid_embgrad_segreduce(const int64_t* ids, const float* grad_rows
     if (e != cudaSuccess) return set_error(-2, "embgrad: scan: %s", cudaGetErrorString(e));
     e = cudaMemsetAsync(w.n_long, 0, 4, s);
     if (e != cudaSuccess) return set_error(-2, "embgrad: memset: %s", cudaGetErrorString(e));
-    const unsigned blocks = (unsigned)((n * 32 + 255) / 256);
+    const unsigned blocks = (unsigned)(((n + SEG_PER_WARP - 1) / SEG_PER_WARP * 32 + 255) / 256);
     AMID_K("k_segreduce", s);
     k_segreduce<<<blocks, 256, 0, s>>>(grad_rows, w.vals_out, w.ukeys, w.counts, w.offsets, n_uniq, uniq_ids, uniq_grads,
                                        w.long_list, w.n_long);

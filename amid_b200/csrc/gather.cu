@@ -97,68 +97,76 @@ struct EmbedAll {
     uint32_t n0, n1, n2;          // rows per segment (each < 2^31)
 };
 constexpr int RPW2 = 8;
+// CTAs never straddle a segment (each segment is rounded up to whole CTAs of 8 warps x 8 rows), so the segment,
+// its pointers and the dropout site are block-uniform and the row loop is straight-line code.
+__host__ __device__ inline uint32_t embed_all_ctas(uint32_t n) { return (n + 8 * RPW2 - 1) / (8 * RPW2); }
 __global__ void __launch_bounds__(256)
 k_embed_all(const float* __restrict__ table, int64_t V, EmbedAll ea, uint32_t L, DropCfg dc, int* __restrict__ err) {
     const int lane = threadIdx.x & 31;
-    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const uint32_t total = ea.n0 + ea.n1 + ea.n2;
-    const uint32_t r0 = warp * RPW2;
-    if (r0 >= total) return;
-    // lane u < 8 resolves row r0+u: segment, local row, id   (no dynamic indexing of the parameter struct)
-    int seg = 0;
-    uint32_t lr = 0;
+    uint32_t cta = blockIdx.x;
+    const uint32_t c0 = embed_all_ctas(ea.n0), c1 = embed_all_ctas(ea.n1);
+    uint32_t n;
+    const int64_t* ids;
+    float* out;
+    const float* pos = nullptr;
+    uint32_t* tmk = nullptr;
+    uint32_t site = 0;
+    if (cta < c0) { n = ea.n0; ids = ea.ids0; out = ea.out0; }
+    else if (cta < c0 + c1) { cta -= c0; n = ea.n1; ids = ea.ids1; out = ea.out1; pos = ea.pos1; tmk = ea.tm1; site = SITE_EMB; }
+    else { cta -= c0 + c1; n = ea.n2; ids = ea.ids2; out = ea.out2; pos = ea.pos2; tmk = ea.tm2; site = 8u + SITE_EMB; }
+    const uint32_t r0 = (cta * 8 + (threadIdx.x >> 5)) * RPW2;
+    if (r0 >= n) return;
     int64_t id = 0;
-    if (lane < RPW2 && r0 + lane < total) {
-        lr = r0 + lane;
-        if (lr >= ea.n0) { lr -= ea.n0; seg = 1; if (lr >= ea.n1) { lr -= ea.n1; seg = 2; } }
-        const int64_t* src = seg == 0 ? ea.ids0 : (seg == 1 ? ea.ids1 : ea.ids2);
-        id = __ldg(src + lr);
+    if (lane < RPW2) id = __ldg(ids + min(r0 + lane, n - 1));          // tail rows re-read the last id, never stored
+    const bool bad = id < 0 || id >= V;
+    if (__any_sync(0xffffffffu, bad)) {                                  // host raises on the flag; keep the loads in range
+        if (lane == 0) atomicExch(err, 1);
+        if (bad) id = 0;
     }
     float4 v[RPW2];
-    bool ok[RPW2];
 #pragma unroll
     for (int u = 0; u < RPW2; ++u) {
         const int64_t idu = __shfl_sync(0xffffffffu, id, u);
-        ok[u] = (r0 + u < total);
-        if (ok[u] && (idu < 0 || idu >= V)) { ok[u] = false; if (lane == 0) atomicExch(err, 1); }
-        if (ok[u]) v[u] = ldg_stream(reinterpret_cast<const float4*>(table + idu * D) + lane);
+        v[u] = ldg_stream(reinterpret_cast<const float4*>(table + idu * D) + lane);
     }
+    uint32_t l = pos ? r0 % L : 0u;
 #pragma unroll
     for (int u = 0; u < RPW2; ++u) {
-        const int su = __shfl_sync(0xffffffffu, seg, u);
-        const uint32_t lru = __shfl_sync(0xffffffffu, lr, u);
-        if (!ok[u]) continue;   // warp-uniform
+        const uint32_t r = r0 + u;
+        if (r >= n) break;                                               // warp-uniform, last warp of a segment only
         float4 x = v[u];
-        float* dst = su == 0 ? ea.out0 : (su == 1 ? ea.out1 : ea.out2);
-        if (su > 0) {
-            const uint32_t l = lru % L;
-            const float* pp = su == 1 ? ea.pos1 : ea.pos2;
-            uint32_t* tmk = su == 1 ? ea.tm1 : ea.tm2;
-            const float4 p = __ldg(reinterpret_cast<const float4*>(pp + (size_t)l * D) + lane);
-            x = make_float4(x.x + p.x, x.y + p.y, x.z + p.z, x.w + p.w);
-            const uint32_t w0 = __ballot_sync(0xffffffffu, x.x == 0.f);
-            const uint32_t w1 = __ballot_sync(0xffffffffu, x.y == 0.f);
-            const uint32_t w2 = __ballot_sync(0xffffffffu, x.z == 0.f);
-            const uint32_t w3 = __ballot_sync(0xffffffffu, x.w == 0.f);
-            if (lane == 0) *reinterpret_cast<uint4*>(tmk + (size_t)lru * 4) = make_uint4(w0, w1, w2, w3);
-            if (dc.train) x = drop4(x, dc, 8u * (su - 1) + SITE_EMB, (uint64_t)lru * D + lane * 4);
+        if (pos) {                                                       // warp-uniform
+            const float4 p = __ldg(reinterpret_cast<const float4*>(pos + (size_t)l * D) + lane);
+            x = make_float4(x.x + p.x, x.y + p.y, x.z + p.z, x.w + p.w);                       // model_seq.py:362
+            // timeline-mask bits of the pre-dropout features (:365); exact zeros are rare, so vote once first
+            uint4 bits = make_uint4(0u, 0u, 0u, 0u);
+            if (__any_sync(0xffffffffu, x.x == 0.f || x.y == 0.f || x.z == 0.f || x.w == 0.f)) {
+                bits.x = __ballot_sync(0xffffffffu, x.x == 0.f);
+                bits.y = __ballot_sync(0xffffffffu, x.y == 0.f);
+                bits.z = __ballot_sync(0xffffffffu, x.z == 0.f);
+                bits.w = __ballot_sync(0xffffffffu, x.w == 0.f);
+            }
+            if (lane == 0) *reinterpret_cast<uint4*>(tmk + (size_t)r * 4) = bits;
+            if (dc.train) x = drop4(x, dc, site, (uint64_t)r * D + lane * 4);                  // :363
+            if (++l == L) l = 0;
         }
-        stg_stream(reinterpret_cast<float4*>(dst + (size_t)lru * D) + lane, x);
+        stg_stream(reinterpret_cast<float4*>(out + (size_t)r * D) + lane, x);
     }
 }
 
 // backward: dx0 <- dx0 * ~tmask * keep*scale (in place); dpos[l] = sum_b dx0[b,l].
-// One CTA per position l; its 8 warps stride over the batch, then a fixed-order
-// cross-warp sum (deterministic, no atomics).
-__global__ void __launch_bounds__(256)
+// One CTA of 32 warps per position l; the warps stride over the batch (4 rows in flight each), then a
+// fixed-order cross-warp sum (deterministic, no atomics).
+constexpr int SEB_WARPS = 32;
+__global__ void __launch_bounds__(SEB_WARPS * 32)
 k_seq_embed_bwd(float* __restrict__ dx0, const uint32_t* __restrict__ tmask, int B, int L, float* __restrict__ dpos,
                 DropCfg dc) {
-    __shared__ float4 red[8][32];
+    __shared__ float4 red[SEB_WARPS][32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int l = blockIdx.x;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 4
-    for (int b = warp; b < B; b += 8) {
+    for (int b = warp; b < B; b += SEB_WARPS) {
         const int64_t r = (int64_t)b * L + l;
         float4 g = *(reinterpret_cast<const float4*>(dx0 + r * D) + lane);
         const uint4 tw = __ldg(reinterpret_cast<const uint4*>(tmask) + r);
@@ -175,7 +183,7 @@ k_seq_embed_bwd(float* __restrict__ dx0, const uint32_t* __restrict__ tmask, int
     if (warp == 0) {
         float4 s = red[0][lane];
 #pragma unroll
-        for (int w = 1; w < 8; ++w) { s.x += red[w][lane].x; s.y += red[w][lane].y; s.z += red[w][lane].z; s.w += red[w][lane].w; }
+        for (int w = 1; w < SEB_WARPS; ++w) { s.x += red[w][lane].x; s.y += red[w][lane].y; s.z += red[w][lane].z; s.w += red[w][lane].w; }
         *(reinterpret_cast<float4*>(dpos + (size_t)l * D) + lane) = s;
     }
 }
@@ -283,11 +291,10 @@ extern "C" int amid_embed_all_fwd(const float* table, int64_t V, const int64_t* 
     ea.out0 = items; ea.out1 = x0_d1; ea.out2 = x0_d2;
     ea.tm1 = tmask_d1; ea.tm2 = tmask_d2;
     ea.n0 = (uint32_t)n_items; ea.n1 = (uint32_t)((int64_t)B * L); ea.n2 = ea.n1;
-    const int64_t total = (int64_t)ea.n0 + ea.n1 + ea.n2;
-    const int64_t warps = (total + RPW2 - 1) / RPW2;
+    const int64_t ctas = (int64_t)embed_all_ctas(ea.n0) + embed_all_ctas(ea.n1) + embed_all_ctas(ea.n2);
     const DropCfg dc = make_drop(drop);
     AMID_K("k_embed_all", stream);
-    k_embed_all<<<(unsigned)((warps + 7) / 8), 256, 0, stream>>>(table, V, ea, (uint32_t)L, dc, err);
+    k_embed_all<<<(unsigned)ctas, 256, 0, stream>>>(table, V, ea, (uint32_t)L, dc, err);
     AMID_LAUNCH_CHECK("k_embed_all");
     return 0;
 }
@@ -299,7 +306,7 @@ extern "C" int amid_seq_embed_bwd(float* dx0, const uint32_t* tmask, int32_t B, 
     AMID_REQUIRE(B > 0 && L > 0, "seq_embed_bwd: B=%d L=%d", B, L);
     const DropCfg dc = make_drop(drop);
     AMID_K("k_seq_embed_bwd", stream);
-    k_seq_embed_bwd<<<L, 256, 0, stream>>>(dx0, tmask, B, L, dpos, dc);
+    k_seq_embed_bwd<<<L, SEB_WARPS * 32, 0, stream>>>(dx0, tmask, B, L, dpos, dc);
     AMID_LAUNCH_CHECK("k_seq_embed_bwd");
     return 0;
 }

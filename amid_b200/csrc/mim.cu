@@ -3,6 +3,7 @@
 // [bs,B,n,n] tensors whose outer axis is redundant; here the only O(n^2 d) work is one
 // similarity-max per sample (k_mim_scores), everything else is O(B n d) or smaller.
 #include "common.cuh"
+#include "tc.cuh"
 
 namespace amid {
 
@@ -164,6 +165,120 @@ k_mim_scores_mma(const float* __restrict__ a, const float* __restrict__ b, int n
         for (int w = 1; w < 8; ++w) r = fmaxf(r, wmax[w]);
         m[j] = r;
     }
+}
+
+// tcgen05 version (n <= 256): one CTA per sample, 2 CTAs per SM.  The 128-feature contraction is streamed in four
+// 32-feature chunks; per chunk the CTA stages hi / lo TF32 halves of 128 rows of a and of all (padded) rows of b as
+// K-major SWIZZLE_128B operands and one thread issues 4 k-steps x {lo*hi, hi*lo, hi*hi} into a [128 x NB] fp32
+// accumulator in TMEM.  The epilogue takes the masked maximum straight out of TMEM.
+namespace mimtc {
+using namespace tc;
+constexpr int A_BYTES = 128 * 128;            // one operand half: [128 rows][32 fp32]
+__host__ __device__ inline int nb_rows(int n) { return (n + 31) & ~31; }
+__host__ __device__ inline size_t smem_bytes(int n) { return (size_t)2 * A_BYTES + (size_t)2 * nb_rows(n) * 128 + 1024; }
+__device__ __forceinline__ uint32_t chunk_off4(int r, int c4) {      // 16-byte unit c4 (0..7) of row r
+    return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((c4 ^ (r & 7)) << 4));
+}
+__device__ __forceinline__ void store_split(uint8_t* hi, uint8_t* lo, uint32_t off, const float4 v) {
+    uint4 h, l;
+    split_tf32(v.x, h.x, l.x); split_tf32(v.y, h.y, l.y); split_tf32(v.z, h.z, l.z); split_tf32(v.w, h.w, l.w);
+    *reinterpret_cast<uint4*>(hi + off) = h;
+    *reinterpret_cast<uint4*>(lo + off) = l;
+}
+// rows [row0, row0 + rows) x features [32 kc, 32 kc + 32) of g[n,128] -> hi / lo chunk (rows >= n zero)
+__device__ __forceinline__ void fill_split(uint8_t* hi, uint8_t* lo, const float* __restrict__ g, int row0, int rows,
+                                           int n, int kc) {
+    const int c4 = threadIdx.x & 7, rb = threadIdx.x >> 3;             // 32 rows x 8 units per pass
+    for (int r = rb; r < rows; r += 128) {
+        float4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int rr = r + 32 * u;
+            v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (rr < rows && row0 + rr < n) v[u] = __ldg(reinterpret_cast<const float4*>(g + (size_t)(row0 + rr) * D + kc * 32) + c4);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int rr = r + 32 * u;
+            if (rr < rows) store_split(hi, lo, chunk_off4(rr, c4), v[u]);
+        }
+    }
+}
+}  // namespace mimtc
+
+__global__ void __launch_bounds__(256, 2)
+k_mim_scores_tc5(const float* __restrict__ a, const float* __restrict__ b, int n, float* __restrict__ m) {
+    using namespace mimtc;
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ uint64_t bar;
+    __shared__ uint32_t tmem_base_s;
+    __shared__ float wmax[8];
+    uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const int NB = nb_rows(n);
+    uint8_t* Ahi = base;
+    uint8_t* Alo = Ahi + A_BYTES;
+    uint8_t* Bhi = Alo + A_BYTES;
+    uint8_t* Blo = Bhi + NB * 128;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int j = blockIdx.x;
+    const float* aj = a + (size_t)j * n * D;
+    const float* bj = b + (size_t)j * n * D;
+    if (warp == 0) tmem_alloc(&tmem_base_s, 256);
+    if (threadIdx.x == 0) { mbar_init(&bar, 1); fence_barrier_init(); }
+    fence_before();
+    __syncthreads();
+    fence_after();
+    const uint32_t tmem = tmem_base_s;
+    const uint32_t id = idesc_tf32(NB, false, false);
+    uint32_t phase = 0;
+    float best = -INFINITY;
+    for (int m0 = 0; m0 < n; m0 += 128) {
+        for (int kc = 0; kc < 4; ++kc) {
+            if (kc) { mbar_wait(&bar, phase); phase ^= 1; }          // the previous chunk's MMAs have read the stage
+            fill_split(Ahi, Alo, aj, m0, 128, n, kc);
+            fill_split(Bhi, Blo, bj, 0, NB, n, kc);
+            fence_async_smem();
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                fence_after();
+                const uint32_t ah = smem_u32(Ahi), al = smem_u32(Alo), bh = smem_u32(Bhi), bl = smem_u32(Blo);
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) {
+                    const uint64_t dah = make_desc(ah + ks * 32, 16, 1024), dal = make_desc(al + ks * 32, 16, 1024);
+                    const uint64_t dbh = make_desc(bh + ks * 32, 16, 1024), dbl = make_desc(bl + ks * 32, 16, 1024);
+                    mma_tf32(tmem, dal, dbh, id, (kc || ks) ? 1u : 0u);
+                    mma_tf32(tmem, dah, dbl, id, 1u);
+                    mma_tf32(tmem, dah, dbh, id, 1u);
+                }
+                mma_commit(&bar);
+            }
+        }
+        mbar_wait(&bar, phase);
+        phase ^= 1;
+        fence_after();
+        const int row = m0 + 32 * (warp & 3) + lane;
+        for (int cg = (warp >> 2); cg * 32 < NB; cg += 2) {
+            float v[32];
+            tmem_ld32(tmem + ((uint32_t)(32 * (warp & 3)) << 16) + cg * 32, v);
+            if (row < n) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i)
+                    if (cg * 32 + i < n) best = fmaxf(best, v[i]);
+            }
+        }
+        fence_before();
+        __syncthreads();                                              // TMEM drained before the next row tile overwrites it
+        fence_after();
+    }
+    best = warp_max(best);
+    if (lane == 0) wmax[warp] = best;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float r = wmax[0];
+        for (int w = 1; w < 8; ++w) r = fmaxf(r, wmax[w]);
+        m[j] = r;
+    }
+    if (warp == 0) tmem_dealloc(tmem, 256);
 }
 
 // softmax over the batch + hard gate + ordered compaction.  Single CTA, 1024 threads.
@@ -427,6 +542,15 @@ extern "C" int amid_mim_scores(const float* a, const float* b, int32_t B, int32_
 extern "C" int amid_mim_scores_tc(const float* a, const float* b, int32_t B, int32_t n, float* m, amid_stream_t s_) {
     AMID_REQUIRE(a && b && m && B > 0 && n > 0, "mim_scores_tc: bad argument");
     AMID_REQUIRE(aligned16(a) && aligned16(b), "mim_scores_tc: misaligned buffer");
+    if (n <= 256) {                           // tcgen05: the whole key axis is one MMA N extent
+        const size_t smem = mimtc::smem_bytes(n);
+        cudaError_t e = cudaFuncSetAttribute((const void*)k_mim_scores_tc5, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return set_error(-3, "mim_scores_tc: smem attribute: %s", cudaGetErrorString(e));
+        AMID_K("k_mim_scores_tc5", s_);
+        k_mim_scores_tc5<<<B, 256, smem, (cudaStream_t)s_>>>(a, b, n, m);
+        AMID_LAUNCH_CHECK("k_mim_scores_tc5");
+        return 0;
+    }
     const size_t smem = (size_t)2 * MT * MLD2 * sizeof(float);
     cudaError_t e = cudaFuncSetAttribute((const void*)k_mim_scores_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return set_error(-3, "mim_scores_tc: smem attribute: %s", cudaGetErrorString(e));

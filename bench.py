@@ -173,26 +173,45 @@ def peaks():
 
 
 def kernel_work(name, B, L, C):
-    """ALGORITHMIC work of ONE launch of a kernel at this workload: (kind, amount) in FLOP or bytes
-    (DESIGN.md section 'Kernels').  M = B*L tokens."""
+    """ALGORITHMIC work of ONE launch of a kernel at this workload: a dict with
+    'flop' and/or 'byte'.  M = B*L tokens; act = one fp32 [M,128] activation tensor.  The byte figure counts
+    every distinct activation tensor the kernel must read or write once (weights and statistics are noise)."""
     M = B * L
+    act = M * D * 4.0
     gemm = 2.0 * M * D * D                      # one [M,128]x[128,128] contraction
     attn_full = 4.0 * B * L * L * D             # q k^T and P v over the full square, all 8 heads (SURVEY 8d)
     rows_seq, rows_items = M, B * C
-    table = {
-        "k_ln_qkv": ("flop", 3 * gemm), "k_proj_ffn": ("flop", 3 * gemm), "k_ffn_bwd": ("flop", 3 * gemm),
-        "k_qkv_bwd": ("flop", 3 * gemm), "k_wgrad": ("flop", 6 * gemm),
-        "k_ln_qkv_tc": ("flop", 3 * gemm), "k_proj_ffn_tc": ("flop", 3 * gemm), "k_ffn_bwd_tc": ("flop", 3 * gemm),
-        "k_qkv_bwd_tc": ("flop", 3 * gemm), "k_wgrad_tc": ("flop", 6 * gemm),
-        "k_ln_qkv_16": ("flop", 3 * gemm), "k_proj_ffn_16": ("flop", 3 * gemm), "k_ffn_bwd_16": ("flop", 3 * gemm),
-        "k_qkv_bwd_16": ("flop", 3 * gemm), "k_wgrad_16": ("flop", 6 * gemm),
-        "k_attn_fwd": ("flop", attn_full), "k_attn_bwd": ("flop", 2.5 * attn_full),
-        "k_attn_fwd_mma": ("flop", attn_full), "k_attn_bwd_mma": ("flop", 2.5 * attn_full),
-        "k_seq_embed": ("byte", rows_seq * (2 * D * 4 + 8)), "k_gather": ("byte", rows_items * (2 * D * 4 + 8)),
-        "k_embed_all": ("byte", (2 * rows_seq + rows_items) * (2 * D * 4 + 8)),
-        "k_mim_scores": ("flop", 2.0 * B * L * L * D), "k_mim_scores_mma": ("flop", 2.0 * B * L * L * D),
+    chain = {
+        "k_ln_qkv": (3 * gemm, 5 * act),        # r: x            w: qn q k v
+        "k_proj_ffn": (3 * gemm, 6 * act),      # r: o qn         w: x1 y h xout
+        "k_ffn_bwd": (3 * gemm, 7 * act),       # r: dxo h x1     w: do2 dhpre dx1 dO
+        "k_qkv_bwd": (3 * gemm, 6 * act),       # r: dq dk dv dx1 xin   w: dxin
+        "k_wgrad": (6 * gemm, 11 * act),        # r: 6 dY + 5 distinct X
     }
+    table = {
+        "k_attn_fwd": {"flop": attn_full, "byte": 4 * act}, "k_attn_bwd": {"flop": 2.5 * attn_full, "byte": 8 * act},
+        "k_attn_fwd_mma": {"flop": attn_full, "byte": 4 * act}, "k_attn_bwd_mma": {"flop": 2.5 * attn_full, "byte": 8 * act},
+        "k_seq_embed": {"byte": rows_seq * (2 * D * 4 + 8)}, "k_gather": {"byte": rows_items * (2 * D * 4 + 8)},
+        "k_embed_all": {"byte": (2 * rows_seq + rows_items) * (2 * D * 4 + 8)},
+        "k_mim_scores": {"flop": 2.0 * B * L * L * D, "byte": 2 * act},
+        "k_mim_scores_mma": {"flop": 2.0 * B * L * L * D, "byte": 2 * act},
+        "k_mim_scores_tc5": {"flop": 3 * 2.0 * B * L * L * D, "byte": 2 * act},   # 3xTF32: three MMAs per product
+    }
+    for k, (f, b) in chain.items():
+        for suffix in ("", "_tc", "_16"):
+            table[k + suffix] = {"flop": f, "byte": b}
     return table.get(name)
+
+
+def measured_traffic(name, a):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch from the committed `ncu --set full` capture
+    (profiles/r01_traffic_c3.json); only meaningful for the default C3 shape it was captured on."""
+    if (a.batch, a.seq_len, a.neg) != (1024, 200, 1):
+        return None
+    path = os.path.join(ROOT, "profiles", "r01_traffic_c3.json")
+    if not os.path.exists(path):
+        return None
+    return json.load(open(path)).get("bytes_per_launch", {}).get(name)
 
 
 def eval_users_per_sec(a, n_batches=20):
@@ -336,21 +355,36 @@ def run_ours(a):
                "share": ms / tot}
         w = kernel_work(name, B, L, C)
         if w:
+            # the binding roofline is the one with the larger lower bound on the launch time
             per_launch_s = (ms / cnt) / 1e3
-            if w[0] == "flop":
-                ent.update(bound="tensor", achieved=w[1] / per_launch_s / 1e12, unit="TFLOP/s")
+            t_hbm = w.get("byte", 0.0) / (pk["hbm"] * 1e9)
+            t_tc = w.get("flop", 0.0) / (pk["tensor"] * 1e12)
+            if t_tc > t_hbm:
+                ent.update(bound="tensor", achieved=w["flop"] / per_launch_s / 1e12, unit="TFLOP/s")
                 ent["frac"] = ent["achieved"] / pk["tensor"]
             else:
-                ent.update(bound="hbm", achieved=w[1] / per_launch_s / 1e9, unit="GB/s")
+                ent.update(bound="hbm", achieved=w["byte"] / per_launch_s / 1e9, unit="GB/s")
                 ent["frac"] = ent["achieved"] / pk["hbm"]
+            if "flop" in w:
+                ent["tflops"] = w["flop"] / per_launch_s / 1e12
         breakdown.append(ent)
     dom = next((e for e in breakdown if "bound" in e), None)
     roofline = None
     if dom:
         roofline = {"kernel": dom["kernel"], "bound": dom["bound"], "achieved": dom["achieved"],
                     "peak": pk["tensor"] if dom["bound"] == "tensor" else pk["hbm"], "unit": dom["unit"],
-                    "frac": dom["frac"], "traffic": None, "peak_source": pk["src"], "share_of_step": dom["share"]}
+                    "frac": dom["frac"], "traffic": measured_traffic(dom["kernel"], a), "peak_source": pk["src"],
+                    "share_of_step": dom["share"]}
     gat = next((e for e in breakdown if e["kernel"] == "k_embed_all"), None)
+    # tensor-pipe utilisation is quoted on the 12*L*d^2 projection/FFN part only (fwd + 2x bwd),
+    # over the time of the kernels that hold those contractions
+    gemm_ms = sum(e["ms_per_step"] for e in breakdown
+                  if e["kernel"].split("_tc")[0].split("_16")[0] in ("k_ln_qkv", "k_proj_ffn", "k_ffn_bwd", "k_qkv_bwd", "k_wgrad"))
+    gemm_flop = 3.0 * 4 * 12 * L * D * D * B          # 2 blocks x 2 encoders, fwd + dX + dW
+    tensor_pipe = None if gemm_ms <= 0 else {
+        "flop_per_step": gemm_flop, "ms_in_gemm_kernels": gemm_ms, "achieved_tflops": gemm_flop / (gemm_ms / 1e3) / 1e12,
+        "peak_tflops": pk["tensor"], "frac": gemm_flop / (gemm_ms / 1e3) / 1e12 / pk["tensor"],
+        "note": "d=128 chains move 5-11 fp32 activation tensors per 3-6 GEMMs (32-64 flop/B): HBM-bound, see per-kernel frac"}
     line = {
         "metric": "train_seqs_per_sec", "value": Bg / (ms_step / 1e3), "unit": "seq/s", "n_gpus": world,
         "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
@@ -367,7 +401,9 @@ def run_ours(a):
         "roofline_gather": None if gat is None else {"kernel": "k_embed_all", "bound": "hbm", "achieved": gat["achieved"],
                                                      "peak": pk["hbm"], "unit": "GB/s", "frac": gat["frac"],
                                                      "traffic": None, "peak_source": pk["src"]},
+        "tensor_pipe": tensor_pipe,
         "kernel_breakdown": breakdown[:12],
+        "kernel_tail_ms": {e["kernel"]: round(e["ms_per_step"], 4) for e in breakdown[12:]},
         "final_loss": final_loss,
     }
     try:
