@@ -242,6 +242,8 @@ k_adam_rows_lazy(float* __restrict__ table, float* __restrict__ m, float* __rest
                  const int64_t* __restrict__ uniq_ids, const float* __restrict__ uniq_grads,
                  const int* __restrict__ n_uniq, int step, float lr, float b1, float b2, float eps, AdamStep a,
                  const __grid_constant__ AdamHist hist) {
+    // one warp per unique row (the kernel is bound by the IEEE divide / sqrt of the replayed steps, not by its
+    // four 512 B row reads, so more rows per warp only costs occupancy)
     const int lane = threadIdx.x & 31;
     const int u = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
     if (u >= n_uniq[0]) return;
@@ -250,9 +252,9 @@ k_adam_rows_lazy(float* __restrict__ table, float* __restrict__ m, float* __rest
     float4* Mp = reinterpret_cast<float4*>(m + id * D) + lane;
     float4* Vp = reinterpret_cast<float4*>(v + id * D) + lane;
     float4 P = *Pp, M = *Mp, Vv = *Vp;
+    const float4 G = reinterpret_cast<const float4*>(uniq_grads + (size_t)u * D)[lane];
     const int last = last_step[id];
     if (last > 0) adam_replay(P, M, Vv, last + 1, step - 1, lr, (double)b1, (double)b2, eps, hist);
-    const float4 G = reinterpret_cast<const float4*>(uniq_grads + (size_t)u * D)[lane];
     adam1(P.x, G.x, M.x, Vv.x, a); adam1(P.y, G.y, M.y, Vv.y, a);
     adam1(P.z, G.z, M.z, Vv.z, a); adam1(P.w, G.w, M.w, Vv.w, a);
     *Pp = P; *Mp = M; *Vp = Vv;

@@ -696,25 +696,27 @@ __global__ void k_reduce_partials(const float* __restrict__ part, int S, int n, 
     if (e >= n) return;
     const float* p = part + (size_t)blockIdx.y * S * n + e;
     float s = 0.f;
+#pragma unroll 8
     for (int i = 0; i < S; ++i) s += p[(size_t)i * n];
     outs.out[blockIdx.y][e] = s;
 }
-// LN partials are [S][256] = (dw[128], db[128]) per tile.  16 CTAs x 256 threads: a CTA owns 16
-// columns, its 16 row groups sum their rows in order, then the group sums are added in fixed order.
-__global__ void __launch_bounds__(256)
+// LN partials are [S][256] = (dw[128], db[128]) per tile.  16 CTAs x 1024 threads: a CTA owns 16
+// columns, its 64 row groups sum their rows in order, then the group sums are added in fixed order.
+__global__ void __launch_bounds__(1024)
 k_reduce_ln(const float* __restrict__ part, int S, float* __restrict__ dw, float* __restrict__ db) {
-    __shared__ float red[16][16];
+    // 16 columns x 64 row groups per CTA (1024 threads): short dependent chains, fixed summation order
+    __shared__ float red[64][16];
     const int c = threadIdx.x & 15, g = threadIdx.x >> 4;
     const int e = blockIdx.x * 16 + c;
     float s = 0.f;
 #pragma unroll 8
-    for (int i = g; i < S; i += 16) s += part[(size_t)i * 2 * D + e];
+    for (int i = g; i < S; i += 64) s += part[(size_t)i * 2 * D + e];
     red[g][c] = s;
     __syncthreads();
     if (g == 0) {
         float t = red[0][c];
 #pragma unroll
-        for (int k = 1; k < 16; ++k) t += red[k][c];
+        for (int k = 1; k < 64; ++k) t += red[k][c];
         if (e < D) dw[e] = t; else db[e - D] = t;
     }
 }
@@ -986,7 +988,7 @@ static int encoder_bwd_impl(const amid_encoder_tensors* P, const float* x0, cons
     k_ln_bwd<<<tiles, NT, 0, stream>>>(d_enc, S->xout[1], S->st3, P->ln3_w, M, dxa, lnp0);
     AMID_LAUNCH_CHECK("k_ln_bwd");
     AMID_K("k_reduce_ln", stream);
-    k_reduce_ln<<<16, 256, 0, stream>>>(lnp0, tiles, G->ln3_w, G->ln3_b);
+    k_reduce_ln<<<16, 1024, 0, stream>>>(lnp0, tiles, G->ln3_w, G->ln3_b);
     AMID_LAUNCH_CHECK("k_reduce_ln");
 
     for (int i = 1; i >= 0; --i) {
@@ -1015,7 +1017,7 @@ static int encoder_bwd_impl(const amid_encoder_tensors* P, const float* x0, cons
         AMID_LAUNCH_CHECK("k_ffn_bwd");
         }
         AMID_K("k_reduce_ln", stream);
-        k_reduce_ln<<<16, 256, 0, stream>>>(lnp0, tiles, G->ln2_w[i], G->ln2_b[i]);
+        k_reduce_ln<<<16, 1024, 0, stream>>>(lnp0, tiles, G->ln2_w[i], G->ln2_b[i]);
         AMID_LAUNCH_CHECK("k_reduce_ln");
         if (use_tc) {
             const size_t mma_smem = (size_t)((L + 15) / 16 * 16) * (4 * attn::LDS + 2) * sizeof(float);
@@ -1051,7 +1053,7 @@ static int encoder_bwd_impl(const amid_encoder_tensors* P, const float* x0, cons
         AMID_LAUNCH_CHECK("k_qkv_bwd");
         }
         AMID_K("k_reduce_ln", stream);
-        k_reduce_ln<<<16, 256, 0, stream>>>(lnp1, tiles, G->ln1_w[i], G->ln1_b[i]);
+        k_reduce_ln<<<16, 1024, 0, stream>>>(lnp1, tiles, G->ln1_w[i], G->ln1_b[i]);
         AMID_LAUNCH_CHECK("k_reduce_ln");
         // weight gradients of the block, one launch: W2, W1, Wo, Wq, Wk, Wv
         WgradJobs wj;

@@ -80,7 +80,7 @@ k_score_fwd(const float* __restrict__ u1, const float* __restrict__ u2, const fl
 
 // ---- backward.  One CTA per group of SB samples; weight-gradient partial per CTA.
 // partial layout per (group, head): dW0[hid][256] | db0[hid] | dw2[hid] | db2[1]
-constexpr int SB = 8;
+constexpr int SB = 4;
 __host__ __device__ inline int head_grad_floats(int hid) { return hid * 2 * D + 2 * hid + 1; }
 
 __global__ void __launch_bounds__(256)
