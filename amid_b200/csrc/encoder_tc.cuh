@@ -35,8 +35,11 @@ struct Epi {
     }
 };
 
+// (pointer arithmetic on the shared array, not an integer round trip: the compiler keeps the shared address
+// space and emits LDS / STS instead of generic LD / ST for everything derived from the result)
 __device__ __forceinline__ uint8_t* align1k(uint8_t* p) {
-    return reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(p) + 1023) & ~(uintptr_t)1023);
+    const uint32_t a = (uint32_t)__cvta_generic_to_shared(p);
+    return p + ((1024u - (a & 1023u)) & 1023u);
 }
 __device__ __forceinline__ void setup(Shared& sh, int tmem_cols) {
     if ((threadIdx.x >> 5) == 0) tmem_alloc(&sh.tmem, tmem_cols);

@@ -213,7 +213,7 @@ k_mim_scores_tc5(const float* __restrict__ a, const float* __restrict__ b, int n
     __shared__ uint64_t bar;
     __shared__ uint32_t tmem_base_s;
     __shared__ float wmax[8];
-    uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* base = smem_raw + ((1024u - ((uint32_t)__cvta_generic_to_shared(smem_raw) & 1023u)) & 1023u);
     const int NB = nb_rows(n);
     uint8_t* Ahi = base;
     uint8_t* Alo = Ahi + A_BYTES;

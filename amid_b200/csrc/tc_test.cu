@@ -14,7 +14,7 @@ k_tc_linear(const float* __restrict__ x, const float* __restrict__ w, const floa
     extern __shared__ uint8_t smem_raw[];
     __shared__ uint64_t bar;
     __shared__ uint32_t tmem_base_s;
-    uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* base = smem_raw + ((1024u - ((uint32_t)__cvta_generic_to_shared(smem_raw) & 1023u)) & 1023u);
     uint8_t* At = base;
     uint8_t* Bt = base + TILE_BYTES;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -63,7 +63,7 @@ k_tc_linear16(const float* __restrict__ x, const float* __restrict__ w, const fl
     extern __shared__ uint8_t smem_raw[];
     __shared__ uint64_t bar;
     __shared__ uint32_t tmem_base_s;
-    uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* base = smem_raw + ((1024u - ((uint32_t)__cvta_generic_to_shared(smem_raw) & 1023u)) & 1023u);
     uint8_t* At = base;
     uint8_t* Bt = base + TILE16_BYTES;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -108,7 +108,7 @@ k_tc_wgrad16(const float* __restrict__ dy, const float* __restrict__ x, int M, f
     extern __shared__ uint8_t smem_raw[];
     __shared__ uint64_t bar;
     __shared__ uint32_t tmem_base_s;
-    uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* base = smem_raw + ((1024u - ((uint32_t)__cvta_generic_to_shared(smem_raw) & 1023u)) & 1023u);
     uint8_t* At = base;
     uint8_t* Bt = base + TILE16_BYTES;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
