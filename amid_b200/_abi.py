@@ -90,6 +90,10 @@ _SIGS = {
     "amid_adam_rows_lazy": (c_int32, [P, P, P, P, P, P, P, c_int64, c_int32, c_float, c_float, c_float, c_float, P]),
     "amid_adam_rows_flush": (c_int32, [P, P, P, P, c_int64, c_int32, c_float, c_float, c_float, c_float, P]),
     "amid_rank_counts": (c_int32, [P, c_int64, c_int32, c_float, P, P, P]),
+    "amid_catalogue_item_proj": (c_int32, [P, c_int64, P, c_int64, P, P, c_int32, P, P]),
+    "amid_catalogue_user_proj": (c_int32, [P, P, c_int32, P, c_int32, P, P]),
+    "amid_catalogue_rank": (c_int32, [P, P, c_int32, c_int32, P, c_int32, c_int32, P, P, P, c_float, P, P, P]),
+    "amid_catalogue_scores": (c_int32, [P, P, c_int32, c_int32, P, c_int32, c_int32, P, P, P, P, P, P]),
     "amid_tc_linear_test": (c_int32, [P, P, P, c_int32, P, P]),
     "amid_tc_linear16_test": (c_int32, [P, P, P, c_int32, P, P]),
     "amid_tc_wgrad16_test": (c_int32, [P, P, c_int32, P, c_int32, P]),

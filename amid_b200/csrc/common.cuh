@@ -48,6 +48,10 @@ __device__ __forceinline__ float warp_max(float v) {
     return v;
 }
 
+// device-side "id out of range" flag shared by every kernel that indexes the table (gather.cu);
+// read and cleared by amid_gather_error_host_sync()
+int* err_flag();
+
 // ------------------------------------------------------------------ counter-based dropout RNG
 // One 32-bit integer hash yields four 8-bit lanes = the keep decisions of 4 consecutive elements
 // (idx4 = element_index >> 2).  keep <=> lane >= thr8, thr8 = round(p * 256)  (p = 0.5 is exact).

@@ -207,7 +207,7 @@ __global__ void k_mask_attn(DropCfg dc, uint32_t site, int64_t BH, int L, uint8_
 
 // device-side error flag shared by the gather kernels (ids out of range)
 static int* g_err_flag = nullptr;
-static int* err_flag() {
+int* err_flag() {
     if (!g_err_flag) {
         if (cudaMalloc(&g_err_flag, sizeof(int)) != cudaSuccess) return nullptr;
         cudaMemset(g_err_flag, 0, sizeof(int));

@@ -211,3 +211,16 @@ class Trainer:
         probs, _ = hotpath.forward(self.P, self.cfg, batch["i_node"], batch["neg_samples"], batch["seq_d1"],
                                    batch["seq_d2"], train=False, seed=0, dist=self.dist, need_ctx=False)
         return probs
+
+    # ------------------------------------------------------------------ full-catalogue evaluation (config 5)
+    def catalogue(self, pool_d1: torch.Tensor, pool_d2: torch.Tensor):
+        """Item halves of the scorer for both domain pools; pending lazy-Adam rows are flushed first."""
+        from . import evaluate
+        self.flush()
+        return evaluate.Catalogue(self.P, self.cfg, pool_d1, pool_d2)
+
+    def evaluate_full_catalogue(self, cat, batches):
+        """HR/NDCG/MRR of every user against the whole pool of its target domain.  Under data parallelism each
+        rank passes its own contiguous block of whole eval batches; the rank lists are gathered in rank order."""
+        from . import evaluate
+        return evaluate.evaluate_full_catalogue(self.P, self.cfg, cat, batches, self.dist)

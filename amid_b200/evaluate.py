@@ -74,3 +74,131 @@ def evaluate_lists(pred_d1: torch.Tensor, pred_d2: torch.Tensor, domain_id: torc
         if rows.shape[0]:
             res[name] = metrics_from_ranks(rank_of_positive(rows, FIX_VALUE))
     return res
+
+
+# --------------------------------------------------------------------------------------------------
+# Full-catalogue evaluation (BASELINE config 5): every user against the whole target-domain pool.
+# The reference only ever scores 1 + neg_nums sampled candidates (dataset_seq.py:201); here the candidate
+# list of a user is [positive, every other pool item in pool order], scored by the same predictModule and
+# ranked by the same rule.  The U x I score matrix is never materialised: csrc/catalogue.cu counts, per
+# user, the pool items that beat / tie the positive.
+# --------------------------------------------------------------------------------------------------
+class Catalogue:
+    """Item halves ``Bc = W0[:, 128:] item + b0`` of predictModule for the item pools of both domains.
+    They do not depend on the users, so they are built once per evaluation (call ``refresh`` after the
+    weights change).  ``pool_d1`` / ``pool_d2`` are int64 item ids (dataset_seq.py:141-142, 151-158)."""
+
+    def __init__(self, P: Dict[str, torch.Tensor], cfg, pool_d1: torch.Tensor, pool_d2: torch.Tensor):
+        dev = P["item_emb_layer.emb_item.weight"].device
+        if cfg.hid_dim != 32:
+            raise ValueError("the full-catalogue path is written for hid_dim == 32")
+        self.P, self.cfg = P, cfg
+        self.pools = [pool_d1.to(dev, torch.int64).contiguous(), pool_d2.to(dev, torch.int64).contiguous()]
+        n1, n2 = self.pools[0].numel(), self.pools[1].numel()
+        if n1 == 0 or n2 == 0:
+            raise ValueError("empty item pool")
+        self.ranges = [(0, n1), (n1, n1 + n2)]
+        V = P["item_emb_layer.emb_item.weight"].shape[0]
+        self.index_of = []                         # per domain: item id -> row of Bc (-1 = not in the pool)
+        for d, (lo, hi) in enumerate(self.ranges):
+            m = torch.full((V,), -1, device=dev, dtype=torch.int32)
+            m[self.pools[d]] = torch.arange(lo, hi, device=dev, dtype=torch.int32)
+            self.index_of.append(m)
+        self.Bc = torch.empty(n1 + n2, 32, device=dev, dtype=torch.float32)
+        self.refresh()
+
+    def refresh(self):
+        P = self.P
+        table = P["item_emb_layer.emb_item.weight"]
+        ids = torch.cat(self.pools)
+        call("amid_catalogue_item_proj", _ptr(table), table.shape[0], _ptr(ids), ids.numel(),
+             _ptr(P["predictModule.fc.0.weight"]), _ptr(P["predictModule.fc.0.bias"]), 32, _ptr(self.Bc), _stream())
+        if _abi_gather_error():
+            raise IndexError("catalogue: item id out of range")
+
+
+def _abi_gather_error() -> bool:
+    from ._abi import lib
+    return bool(lib().amid_gather_error_host_sync())
+
+
+@torch.no_grad()
+def full_catalogue_ranks(P: Dict[str, torch.Tensor], cfg, cat: Catalogue, batch: Dict[str, torch.Tensor], dist=None):
+    """Ranks of the positives of one eval batch against the whole pool of their target domain.
+    Returns {dom: (user_rows, ranks_fix, ranks_nofix)} with numpy int64 arrays; ranks_fix applies the 1e-7 fix
+    (aggregate lists, train_sr.py:114-115), ranks_nofix does not (overlap / non-overlap lists, :120-123)."""
+    from . import hotpath
+    i_node = batch["i_node"]
+    dev = i_node.device
+    B = i_node.shape[0]
+    neg = batch["neg_samples"][:, :1].contiguous() if "neg_samples" in batch else i_node.view(B, 1).clone()
+    _, ctx = hotpath.forward(P, cfg, i_node, neg, batch["seq_d1"], batch["seq_d2"], train=False, seed=0, dist=dist,
+                             need_ctx=True)
+    A = torch.empty(B, 2, 32, device=dev, dtype=torch.float32)
+    s = _stream()
+    call("amid_catalogue_user_proj", _ptr(ctx.us[0]), _ptr(ctx.us[1]), B, _ptr(P["predictModule.fc.0.weight"]), 32, _ptr(A), s)
+    w2, b2 = P["predictModule.fc.2.weight"], P["predictModule.fc.2.bias"]
+    out = {}
+    fix32 = float(np.float32(FIX_VALUE))
+    for dom in (0, 1):
+        rows = torch.nonzero(batch["domain_id"] == dom).flatten().to(torch.int32)
+        n = rows.numel()
+        if n == 0:
+            continue
+        pos_idx = cat.index_of[dom][i_node.reshape(-1)].contiguous()
+        if bool((pos_idx[rows.long()] < 0).any()):
+            raise IndexError(f"full_catalogue_ranks: a positive item of domain {dom + 1} is not in its pool")
+        lo, hi = cat.ranges[dom]
+        counts = torch.empty(n, 4, device=dev, dtype=torch.int32)
+        s_pos = torch.empty(n, device=dev, dtype=torch.float32)
+        call("amid_catalogue_rank", _ptr(A), _ptr(rows), n, dom, _ptr(cat.Bc), lo, hi, _ptr(pos_idx), _ptr(w2), _ptr(b2),
+             fix32, _ptr(counts), _ptr(s_pos), s)
+        c = counts.cpu().numpy().astype(np.int64)
+        ranks_nofix, ranks_fix = c[:, 0].copy(), c[:, 2].copy()
+        tied = np.nonzero((c[:, 1] > 0) | (c[:, 3] > 0))[0]
+        if len(tied):                              # resolve with the reference's own numpy expression (utils.py:297)
+            sel = rows[torch.from_numpy(tied).to(dev)].contiguous()
+            sc = torch.empty(len(tied), hi - lo, device=dev, dtype=torch.float32)
+            sp = torch.empty(len(tied), device=dev, dtype=torch.float32)
+            call("amid_catalogue_scores", _ptr(A), _ptr(sel), len(tied), dom, _ptr(cat.Bc), lo, hi, _ptr(pos_idx), _ptr(w2),
+                 _ptr(b2), _ptr(sp), _ptr(sc), s)
+            sc, sp = sc.cpu().numpy(), sp.cpu().numpy()
+            pcol = (pos_idx[sel.long()] - lo).cpu().numpy()
+            for k, t in enumerate(tied):
+                others = np.delete(sc[k], pcol[k]) if 0 <= pcol[k] < hi - lo else sc[k]
+                for fixv, dst in ((0.0, ranks_nofix), (FIX_VALUE, ranks_fix)):
+                    row = np.concatenate((np.array([sp[k]], dtype=np.float32), others))
+                    row[0] = row[0] - fixv
+                    dst[t] = (-row).argsort().argsort()[0]
+        out[dom] = (rows.cpu().numpy().astype(np.int64), ranks_fix, ranks_nofix)
+    return out
+
+
+def evaluate_full_catalogue(P, cfg, cat: Catalogue, batches, dist=None) -> Dict[str, tuple]:
+    """test() of train_sr.py:31-128 with the whole pool as the candidate list: the same six lists
+    (d1, d2, and their overlap / non-overlap splits) and the same seven metrics per list.  With ``dist`` the
+    caller shards whole batches across ranks; rank lists are gathered in rank order before the metrics."""
+    acc = {k: [] for k in ("d1", "d2", "d1_ov", "d1_no", "d2_ov", "d2_no")}
+    for b in batches:
+        r = full_catalogue_ranks(P, cfg, cat, b, dist=None)
+        ov = b["overlap_label"].cpu().numpy() if "overlap_label" in b else None
+        for dom, name in ((0, "d1"), (1, "d2")):
+            if dom not in r:
+                continue
+            rows, rf, rn = r[dom]
+            acc[name].append(rf)
+            if ov is not None:
+                o = ov[rows] != 0
+                acc[name + "_ov"].append(rn[o])
+                acc[name + "_no"].append(rn[~o])
+    res = {}
+    for k, parts in acc.items():
+        ranks = np.concatenate(parts) if parts else np.zeros(0, dtype=np.int64)
+        if dist is not None and dist.world > 1:
+            import torch.distributed as td
+            gathered = [None] * dist.world
+            td.all_gather_object(gathered, ranks, group=dist.group)
+            ranks = np.concatenate(gathered)
+        if len(ranks):
+            res[k] = metrics_from_ranks(ranks)
+    return res

@@ -256,6 +256,67 @@ def gather_gbs(model, a, iters=40):
     return nbytes / (us * 1e-6) / 1e9, us
 
 
+def eval_full_catalogue_users_per_sec(a, n_batches=12):
+    """BASELINE config 5 on one GPU: 256-user eval batches (L=20, the C1 eval shape), every user ranked against the
+    whole item pool of its target domain (16,084 / 12,153 items: the cloth_sport_train75 pools) by
+    csrc/catalogue.cu; includes the encoder forward, the D2H of the counts and the metric reduce."""
+    from amid_b200 import evaluate
+    from amid_b200.engine import Trainer
+    from amid_b200.model_seq import SASRec
+    B, L = 256, 20
+    n1, n2 = 16084, 12153
+    torch.manual_seed(2)
+    m = SASRec(0, D, V_ITEMS, D, L, HID, B, False, True, 0.5, 0.4, isDR=False).cuda().eval()
+    m.cfg.precision = a.precision
+    tr = Trainer(m)
+    rng = np.random.default_rng(9)
+    perm = torch.from_numpy(rng.permutation(V_ITEMS)[:n1 + n2])
+    pool1, pool2 = perm[:n1], perm[n1:]
+    cat = tr.catalogue(pool1, pool2)
+    bs = []
+    for _ in range(4):
+        b = synth_batch(rng, B, L, 2, V_ITEMS)
+        dom = b["domain_id"]
+        b["i_node"] = torch.where(dom == 0, pool1[torch.from_numpy(rng.integers(0, n1, B))], pool2[torch.from_numpy(rng.integers(0, n2, B))])
+        b["overlap_label"] = torch.from_numpy(rng.integers(0, 2, B))
+        bs.append(tr.to_device(b))
+    evaluate.evaluate_full_catalogue(tr.P, tr.cfg, cat, bs[:2])
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    evaluate.evaluate_full_catalogue(tr.P, tr.cfg, cat, [bs[i % 4] for i in range(n_batches)])
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    pairs = n_batches * B * (n1 + n2) / 2.0
+    # the U x I stage alone at catalogue scale: 16,384 users of one domain against its pool (kernel time, CUDA events)
+    from amid_b200 import hotpath as hp
+    from amid_b200._abi import call
+    nu = 16384
+    A = torch.randn(nu, 2, 32, device="cuda")
+    rows = torch.arange(nu, device="cuda", dtype=torch.int32)
+    pos_idx = torch.randint(0, n1, (nu,), device="cuda", dtype=torch.int32)
+    counts = torch.empty(nu, 4, device="cuda", dtype=torch.int32)
+    s_pos = torch.empty(nu, device="cuda")
+    w2, b2 = tr.P["predictModule.fc.2.weight"], tr.P["predictModule.fc.2.bias"]
+
+    def rank_once():
+        call("amid_catalogue_rank", hp._ptr(A), hp._ptr(rows), nu, 0, hp._ptr(cat.Bc), 0, n1, hp._ptr(pos_idx), hp._ptr(w2),
+             hp._ptr(b2), 1e-7, hp._ptr(counts), hp._ptr(s_pos), hp._stream())
+
+    rank_once()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(5):
+        rank_once()
+    e1.record()
+    torch.cuda.synchronize()
+    kernel_pairs = 5.0 * nu * n1 / (e0.elapsed_time(e1) / 1e3)
+    return {"metric": "eval_users_per_sec_full_catalogue", "value": n_batches * B / dt, "unit": "users/s",
+            "ms_per_batch": 1e3 * dt / n_batches, "pairs_per_sec": pairs / dt,
+            "kernel_pairs_per_sec": kernel_pairs, "kernel_users_per_sec": kernel_pairs / n1,
+            "config": f"256 users per batch, L={L}, pools {n1} / {n2} items (every pool item scored, fp32 post-sigmoid), 1 GPU"}
+
+
 def eval_users_per_sec(a, n_batches=20):
     """BASELINE metric 3 ("eval users/sec"): the C1 evaluation shape of run.sh -- 256 users per batch,
     1 + 999 candidates, L = 20 -- scored in eval mode and ranked on the device (test() of train_sr.py:31-128).
@@ -462,6 +523,10 @@ def run_ours(a):
         line["eval"] = eval_users_per_sec(a)
     except Exception as e:
         line["eval"] = {"value": None, "error": repr(e)}
+    try:
+        line["eval_full_catalogue"] = eval_full_catalogue_users_per_sec(a)
+    except Exception as e:
+        line["eval_full_catalogue"] = {"value": None, "error": repr(e)}
     if world == 1 and not a.no_cpu_baseline:
         try:
             v, ms, cores = cpu_reference_steps(a, 2, 1, a.cpu_sample)

@@ -246,6 +246,27 @@ int amid_adam_rows_flush(float* table, float* m, float* v, int32_t* last_step, i
 int amid_rank_counts(const float* scores, int64_t N, int32_t C, float fix, int32_t* n_greater,
                      int32_t* n_equal, amid_stream_t stream);
 
+/* ---- a10 at catalogue scale (BASELINE config 5: every user against every pool item) ----
+ * The reference scores 1 + neg_nums sampled candidates per user (dataset_seq.py:201, train_sr.py:56-128); the
+ * full-catalogue variant scores the whole target-domain pool with the same predictModule (model_seq.py:40-54)
+ * and the same ranking rule (utils.py:296-301).  hid must be 32.
+ * item_proj:  Bc[i,:] = W0[:,128:] table[ids[i]] + b0      ([n_items,32]; ids NULL = rows 0..n_items-1)
+ * user_proj:  A[b,dom,:] = W0[:,:128] u_dom[b]             ([B,2,32])
+ * rank:       for slot s < n_users, user row r = user_rows[s], positive = Bc row pos_idx[r]:
+ *             counts[s] = {#gt, #eq against s_pos ; #gt, #eq against s_pos - fix (fp32)} over Bc rows
+ *             [i_lo, i_hi) except the positive itself; s_pos[s] = the positive's score.
+ * scores:     the same scores written out, [n_users, i_hi - i_lo] (tie fallback and tests). */
+int amid_catalogue_item_proj(const float* table, int64_t V, const int64_t* ids, int64_t n_items, const float* w0,
+                             const float* b0, int32_t hid, float* Bc, amid_stream_t stream);
+int amid_catalogue_user_proj(const float* u1, const float* u2, int32_t B, const float* w0, int32_t hid, float* A,
+                             amid_stream_t stream);
+int amid_catalogue_rank(const float* A, const int32_t* user_rows, int32_t n_users, int32_t dom, const float* Bc,
+                        int32_t i_lo, int32_t i_hi, const int32_t* pos_idx, const float* w2, const float* b2, float fix,
+                        int32_t* counts, float* s_pos, amid_stream_t stream);
+int amid_catalogue_scores(const float* A, const int32_t* user_rows, int32_t n_users, int32_t dom, const float* Bc,
+                          int32_t i_lo, int32_t i_hi, const int32_t* pos_idx, const float* w2, const float* b2,
+                          float* s_pos, float* scores, amid_stream_t stream);
+
 /* ---- test support: the keep-mask a dropout site uses (for oracle mask injection) ---- */
 /* feature site: out[r*128+c] for r<rows; attention site: out[((b*8+h)*L+i)*L+j]. */
 int amid_dropout_mask_feature(const amid_dropout* drop, uint32_t site, int64_t rows, uint8_t* out, amid_stream_t stream);
