@@ -80,7 +80,11 @@ class Trainer:
         if table_sync == "auto":
             rows = rows_per_step_hint if rows_per_step_hint is not None else 0
             table_sync = "dense" if (self.world > 1 and rows * self.world * 2 >= self.V) else "sparse"
-        self.table_sync = table_sync if self.world > 1 else "local"
+        if table_sync == "sharded" and dist is None:
+            raise _abi.AmidError("table_sync='sharded' needs a DistCtx (a process group, possibly of size 1)")
+        self.table_sync = table_sync if (self.world > 1 or table_sync == "sharded") else "local"
+        self.V_local = self.V
+        self.sharded = None
         n_opt = 2 if self.cfg.isDR else 1                        # optimizer2 (train_sr_dr.py:669)
         if self.table_sync == "dense":
             self.Vs = (self.V + self.world - 1) // self.world     # rows per shard
@@ -97,6 +101,15 @@ class Trainer:
                 st.tm = torch.zeros(self.Vs, D, device=dev, dtype=torch.float32)
                 st.tv = torch.zeros(self.Vs, D, device=dev, dtype=torch.float32)
             self.sparse_table = False
+        elif self.table_sync == "sharded":
+            # large-vocabulary mode (BASELINE config 4): this rank keeps rows {rank, rank+G, ...} and their Adam
+            # state only; every step fetches the rows it reads with one all-to-all lookup (amid_b200/sharded.py)
+            from .sharded import ShardedTable
+            self.sharded = ShardedTable.from_full(self.table.data, dist.rank, dist.world, dist.group)
+            dist.sharded = self.sharded
+            self.table.data = self.sharded.shard                   # the full table is released here
+            self.V_local = self.sharded.Vs
+            self.opt = [_AdamState(total, self.V_local, dev) for _ in range(n_opt)]
         else:
             self.opt = [_AdamState(total, self.V, dev) for _ in range(n_opt)]
         self.P = {n: p.data for n, p in model.named_parameters()}   # (re)bind after any re-pointing above
@@ -115,7 +128,7 @@ class Trainer:
         for i, st in enumerate(self.opt):
             if st.step > 0 and self.sparse_table:
                 lr = self.lr if i == 0 else self.lr2
-                call("amid_adam_rows_flush", _ptr(self.table.data), _ptr(st.tm), _ptr(st.tv), _ptr(st.last), self.V,
+                call("amid_adam_rows_flush", _ptr(self.table.data), _ptr(st.tm), _ptr(st.tv), _ptr(st.last), self.V_local,
                      st.step, lr, self.betas[0], self.betas[1], self.eps, _stream())
 
     def to_device(self, host_batch: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
@@ -153,6 +166,23 @@ class Trainer:
         losses, dprobs = hotpath.loss_fwd_bwd(probs, batch["label"], batch["domain_id"], batch.get("ob_label"), mode,
                                               self.dr_e_w, B * self.world)
         _, ids_all, rows_all = hotpath.backward(self.P, cfg, ctx, dprobs, G=self.G, dist=self.dist)
+        if self.table_sync == "sharded":
+            # ids_all are rows of the step table: the local reduction yields one gradient row per step-table row, in
+            # bucket order; the owners reduce what all ranks send them and update their shard
+            U = ctx.route.rows.shape[0]
+            _, ug, _ = hotpath.segreduce(ids_all, rows_all, U)
+            recv = self.sharded.push_grads(ctx.route, ug[:U])
+            if self.world > 1:
+                self.dist.all_reduce(self.flat_g)
+                self.dist.all_reduce(losses)
+            st.step += 1
+            call("amid_adam_dense", _ptr(self.flat_p), _ptr(self.flat_g), _ptr(st.m), _ptr(st.v), self.flat_p.numel(),
+                 st.step, lr, self.betas[0], self.betas[1], self.eps, _stream())
+            if recv.shape[0]:
+                uid, ug, nu = hotpath.segreduce(ctx.route.recv_local, recv, self.V_local)
+                self._table_adam(st, uid, ug, nu, lr)
+            self.last_losses = losses
+            return losses
         uid, ug, nu = hotpath.segreduce(ids_all, rows_all, self.V)
         if self.world > 1:
             self.dist.all_reduce(self.flat_g)                      # dense grads: one NCCL call
@@ -224,3 +254,8 @@ class Trainer:
         rank passes its own contiguous block of whole eval batches; the rank lists are gathered in rank order."""
         from . import evaluate
         return evaluate.evaluate_full_catalogue(self.P, self.cfg, cat, batches, self.dist)
+
+    def full_table(self) -> torch.Tensor:
+        """The whole [V,128] item table on every rank (checkpoint / state_dict); pending lazy-Adam rows are flushed."""
+        self.flush()
+        return self.sharded.full_table() if self.sharded is not None else self.table.data[:self.V]

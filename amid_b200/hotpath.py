@@ -58,6 +58,7 @@ class DistCtx:
         self.group = group
         self.world = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
+        self.sharded = None          # amid_b200.sharded.ShardedTable when the item table is row-sharded (config 4)
 
     def all_gather_into(self, out, inp):
         self.dist.all_gather_into_tensor(out, inp, group=self.group)
@@ -279,6 +280,17 @@ def forward(P: Dict[str, torch.Tensor], cfg: Config, i_node, neg_samples, seq_d1
     f = lambda *sh: torch.empty(*sh, device=dev, dtype=torch.float32)
 
     ctx = Ctx()
+    ctx.route = None
+    sharded = dist.sharded if dist is not None else None
+    if sharded is not None:
+        # row-sharded table: one all-to-all lookup fetches the unique rows of the step into a compact step table;
+        # from here on the kernels see (step table, position -> step-table row) instead of (table, item id)
+        route = sharded.lookup(torch.cat((ids_items.reshape(-1), seqs[0].reshape(-1), seqs[1].reshape(-1))))
+        table, V = route.rows, route.rows.shape[0]
+        n_it, n_sq = B * Cn, B * L
+        ids_items = route.virtual_ids[:n_it].view(B, Cn)
+        seqs = [route.virtual_ids[n_it:n_it + n_sq].view(B, L), route.virtual_ids[n_it + n_sq:].view(B, L)]
+        ctx.route = route
     ctx.B, ctx.L, ctx.Le, ctx.C, ctx.V, ctx.train, ctx.seed, ctx.j0 = B, L, Le, Cn, V, train, seed, j0
     ctx.ids_items, ctx.seqs = ids_items, seqs
 

@@ -44,9 +44,15 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample", type=int, default=32, help="sequences per CPU-baseline step (bounded sample)")
     ap.add_argument("--dense-table", action="store_true", help="dense Adam over the whole table (reference-style)")
+    ap.add_argument("--table-sync", default="auto", choices=["auto", "sparse", "dense", "sharded"],
+                    help="multi-GPU table strategy (engine.Trainer); 'sharded' = row-sharded table + all-to-all (config 4)")
+    ap.add_argument("--items", type=int, default=V_ITEMS, help="table rows V (config 4: 20000002)")
     ap.add_argument("--precision", default="bf16", choices=["fp32", "tf32", "bf16"],
                     help="encoder GEMM stages: tf32 = tcgen05 tensor cores (fp32 accumulate), fp32 = exact CUDA-core tiles")
-    return ap.parse_args()
+    a = ap.parse_args()
+    global V_ITEMS
+    V_ITEMS = a.items
+    return a
 
 
 def workload_name(a):
@@ -386,7 +392,8 @@ def run_ours(a):
     model = SASRec(user_length=0, user_emb_dim=D, item_length=V_ITEMS, item_emb_dim=D, seq_len=L, hid_dim=HID, bs=Bg,
                    isInC=False, isItC=True, threshold1=0.5, threshold2=0.4, isDR=a.dr).cuda().train()
     model.cfg.precision = a.precision
-    tr = Trainer(model, lr=5e-4, dist=dctx, sparse_table=not a.dense_table, rows_per_step_hint=B * (2 * L + C))
+    tr = Trainer(model, lr=5e-4, dist=dctx, sparse_table=not a.dense_table, rows_per_step_hint=B * (2 * L + C),
+                 table_sync=a.table_sync)
     rng = np.random.default_rng(100 + rank)
     n_pool = 4
     host = [{k: v.pin_memory() for k, v in synth_batch(rng, B, L, C, V_ITEMS).items()} for _ in range(n_pool)]
@@ -485,6 +492,8 @@ def run_ours(a):
                            "unit": "GB/s", "frac": gat["frac"], "traffic": None, "peak_source": pk["src"],
                            "timing": "inside the train step (per-kernel events, serialised streams)"}
         try:
+            if tr.table_sync == "sharded":
+                raise RuntimeError("row-sharded table: the isolated gather runs on the replicated layout only")
             gbs, us = gather_gbs(model, a)
             roofline_gather.update(achieved=gbs, frac=gbs / pk["hbm"], us_per_launch=us, in_step_gbs=gat["achieved"],
                                    timing="back-to-back launches on rotating uniform-random id batches (CUDA events); "

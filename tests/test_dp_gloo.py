@@ -109,3 +109,83 @@ def test_dp_decomposition_world2_gloo():
         p.join(timeout=60)
     for rank, msg in res:
         assert msg == "ok", f"rank {rank}: {msg}"
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Row-sharded item table (BASELINE config 4): the all-to-all routing of amid_b200/sharded.py on two gloo ranks.
+# The owner-side row gather is injected as a torch index (test scaffolding for the HOST logic only; on a GPU the
+# class uses the CUDA gather kernel and refuses CPU tensors).
+# ---------------------------------------------------------------------------------------------------------------
+def _sharded_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from amid_b200 import _abi
+        from amid_b200.sharded import ShardedTable
+        V = 101                                             # not a multiple of the world size
+        gen = torch.Generator().manual_seed(17)
+        table = torch.randn(V, D, generator=gen)            # same on every rank
+        sh = ShardedTable.from_full(table, rank, world, gather=lambda shard, idx: shard[idx])
+        assert sh.shard.shape == ((V + world - 1) // world, D)
+        assert torch.equal(sh.shard[:len(table[rank::world])], table[rank::world])
+        # the default gather refuses CPU tensors: no silent fallback
+        try:
+            ShardedTable.from_full(table, rank, world).lookup(torch.zeros(3, dtype=torch.int64))
+            raise AssertionError("CPU lookup must be refused")
+        except _abi.AmidError:
+            pass
+        dist.barrier()
+        # each rank asks for its own ragged, duplicate-heavy id list (pad-row style hot id 7)
+        g2 = torch.Generator().manual_seed(100 + rank)
+        ids = torch.cat((torch.randint(0, V, (37 + 5 * rank,), generator=g2), torch.full((20,), 7)))
+        route = sh.lookup(ids)
+        assert torch.equal(route.rows[route.virtual_ids], table[ids])               # every position gets its row
+        U = len(torch.unique(ids))
+        assert route.rows.shape == (U, D) and sum(route.send_splits) == U
+        assert int(route.virtual_ids.max()) == U - 1
+        # requests this owner received are its own rows, in rank order
+        owned_global = route.recv_local * world + rank
+        assert bool((owned_global < V).all())
+        # backward: one gradient row per step-table row -> owners; scatter-add must equal the global dense gradient
+        pos_grads = torch.randn(len(ids), D, generator=g2)
+        step_grads = torch.zeros(U, D).index_add_(0, route.virtual_ids, pos_grads)
+        recv = sh.push_grads(route, step_grads)
+        assert recv.shape == (route.recv_local.numel(), D)
+        mine = torch.zeros(sh.Vs, D).index_add_(0, route.recv_local, recv)           # owner-side reduction
+        parts = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(parts, mine)
+        got = torch.stack(parts, 1).reshape(sh.Vs * world, D)[:V]
+        # reference: all ranks' position gradients scattered into a dense [V,128]
+        all_ids, all_g = [None] * world, [None] * world
+        dist.all_gather_object(all_ids, ids)
+        dist.all_gather_object(all_g, pos_grads)
+        want = torch.zeros(V, D)
+        for i, gr in zip(all_ids, all_g):
+            want.index_add_(0, i, gr)
+        np.testing.assert_allclose(got.numpy(), want.numpy(), rtol=1e-5, atol=1e-5)
+        # checkpoint view
+        assert torch.equal(sh.full_table(), table)
+        # empty request list on one rank must not dead-lock the collectives
+        r2 = sh.lookup(ids[:0] if rank == 1 else ids[:5])
+        assert r2.rows.shape[0] == (0 if rank == 1 else len(torch.unique(ids[:5])))
+        q.put((rank, "ok"))
+    except Exception:  # pragma: no cover
+        import traceback
+        q.put((rank, traceback.format_exc()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_table_routing_world2_gloo():
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_sharded_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=240) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    for rank, msg in res:
+        assert msg == "ok", f"rank {rank}: {msg}"
