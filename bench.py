@@ -32,6 +32,7 @@ D, HID = 128, 32
 
 
 def parse():
+    global V_ITEMS
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=30)
@@ -50,7 +51,6 @@ def parse():
     ap.add_argument("--precision", default="bf16", choices=["fp32", "tf32", "bf16"],
                     help="encoder GEMM stages: tf32 = tcgen05 tensor cores (fp32 accumulate), fp32 = exact CUDA-core tiles")
     a = ap.parse_args()
-    global V_ITEMS
     V_ITEMS = a.items
     return a
 
