@@ -37,9 +37,12 @@ def main():
     mode = os.environ.get("AMID_TABLE_SYNC", "sparse")
     tr = Trainer(build(), lr=1e-3, dist=DistCtx(), table_sync=mode)
     losses = []
+    g_first = None
     for b in batches:
         shard = {k: v[rank * Bl:(rank + 1) * Bl].cuda().contiguous() for k, v in b.items()}
         losses.append(tr.step(shard).clone())
+        if g_first is None:
+            g_first = tr.flat_g.clone()             # all-reduced dense gradients of the first step
     tr.flush()
     full = tr.full_table() if mode == "sharded" else None      # collective: every rank takes part
     torch.cuda.synchronize()
@@ -48,6 +51,12 @@ def main():
         ref = Trainer(build(), lr=1e-3)
         for i, b in enumerate(batches):
             l = ref.step({k: v.cuda().contiguous() for k, v in b.items()})
+            if i == 0:
+                # the gradients themselves agree to fp32 summation-order noise ...
+                gr = (g_first - ref.flat_g).norm().item() / max(ref.flat_g.norm().item(), 1e-12)
+                if gr > 1e-5:
+                    print(f"dense gradient mismatch after step 1: rel {gr}")
+                    ok = False
             if abs(l[0].item() - losses[i][0].item()) > 1e-5 * max(1.0, abs(l[0].item())):
                 print(f"loss mismatch step {i}: dp {losses[i][0].item()} single {l[0].item()}")
                 ok = False
@@ -56,12 +65,20 @@ def main():
         if mode == "sharded":                      # rank-local shard -> compare the reassembled table
             pd["item_emb_layer.emb_item.weight"] = full
         for n in pd:
-            # Adam moves every element by ~lr per step whatever the gradient's size, so an element whose
-            # gradient is at fp32-noise level can differ by a fraction of lr; hold elements to 0.1*lr and
-            # the tensor as a whole to 1e-5 relative
-            err = (pd[n].detach() - ps[n].detach()).abs().max().item()
-            rel = (pd[n].detach() - ps[n].detach()).norm().item() / max(ps[n].detach().norm().item(), 1e-12)
-            if err > 1e-4 or rel > 1e-5:
+            # ... while Adam moves every element by ~lr per step whatever the gradient's size, so an element whose
+            # gradient is at fp32-noise level can differ by a fraction of lr after a few steps; hold elements to
+            # 0.1*lr and the tensor as a whole to 1e-4 relative
+            a_, b_ = pd[n].detach(), ps[n].detach()
+            err = (a_ - b_).abs().max().item()
+            if n.endswith("in_proj_bias"):
+                # the key bias has an analytically ZERO gradient (softmax is invariant to a per-query shift of the
+                # scores), so what Adam normalises there is pure rounding noise: +-lr-sized steps whose signs depend on
+                # the summation order.  Hold that slice to the element bound only.
+                keep = torch.ones_like(a_, dtype=torch.bool)
+                keep[128:256] = False
+                a_, b_ = a_[keep], b_[keep]
+            rel = (a_ - b_).norm().item() / max(b_.norm().item(), 1e-12)
+            if err > 1e-4 or rel > 1e-4:
                 print(f"param mismatch {n}: {err}")
                 ok = False
     # all replicas must hold identical parameters
