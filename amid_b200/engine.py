@@ -259,3 +259,64 @@ class Trainer:
         """The whole [V,128] item table on every rank (checkpoint / state_dict); pending lazy-Adam rows are flushed."""
         self.flush()
         return self.sharded.full_table() if self.sharded is not None else self.table.data[:self.V]
+
+    # ------------------------------------------------------------------ checkpoint / resume (SURVEY.md 8f-4)
+    def checkpoint(self) -> Dict[str, object]:
+        """Everything needed to resume bit-exactly: parameters by their reference state-dict names (pending lazy-Adam
+        rows flushed first; a row-sharded table is saved as this rank's shard), both optimizers' moments and step
+        counters, and the dropout seed state.  The reference's own checkpointing is commented out
+        (train_sr.py:181-186, 327-332); the only contract inherited from it is the state-dict naming."""
+        self.flush()
+        ck = {"format": 1, "table_sync": self.table_sync, "world": self.world,
+              "rank": self.dist.rank if self.dist is not None else 0,
+              "params": {n: p.detach().clone() for n, p in self.P.items()},
+              "opt": [{"m": st.m.clone(), "v": st.v.clone(), "tm": st.tm.clone(), "tv": st.tv.clone(),
+                       "last": st.last.clone(), "step": st.step} for st in self.opt],
+              "active_opt": self.active_opt, "seed": self._seed, "seed_base": self.model._seed_base}
+        return ck
+
+    def load_checkpoint(self, ck: Dict[str, object]) -> None:
+        if ck.get("format") != 1:
+            raise _abi.AmidError("unknown checkpoint format")
+        if ck["table_sync"] != self.table_sync or ck["world"] != self.world:
+            raise _abi.AmidError(f"checkpoint was written with table_sync={ck['table_sync']} on {ck['world']} rank(s); "
+                                 f"this trainer runs table_sync={self.table_sync} on {self.world}")
+        if len(ck["opt"]) != len(self.opt):
+            raise _abi.AmidError("checkpoint and model disagree on isDR (number of optimizers)")
+        for n, p in self.P.items():
+            src = ck["params"][n]
+            if tuple(src.shape) != tuple(p.shape):
+                raise _abi.AmidError(f"checkpoint tensor {n} has shape {tuple(src.shape)}, expected {tuple(p.shape)}")
+            p.copy_(src)
+        for st, s in zip(self.opt, ck["opt"]):
+            st.m.copy_(s["m"]); st.v.copy_(s["v"]); st.tm.copy_(s["tm"]); st.tv.copy_(s["tv"]); st.last.copy_(s["last"])
+            st.step = int(s["step"])
+        self.active_opt = int(ck["active_opt"])
+        self._seed = int(ck["seed"])
+        self.model._seed_base = int(ck["seed_base"])
+
+    # ------------------------------------------------------------------ opt-in fast epoch loop (SURVEY.md 8f-2)
+    def train_epoch(self, loader, phase: int = 1, log_every: int = 0, log=print) -> float:
+        """The inner loop of train() (train_sr.py:189-219 / train_sr_dr.py:189-229, 362-402) over the reference's
+        collated batches: one fused step per batch, no per-step host synchronisation (the running loss is read back
+        once at the end, or every ``log_every`` steps).  Returns the epoch's mean loss as the reference's AverageMeter
+        would report it (mean of the per-batch loss of the phase)."""
+        self.model.train()
+        acc = None
+        n = 0
+        col = 0 if (phase == 1 and not self.cfg.isDR) else None
+        for i, host in enumerate(loader):
+            losses = self.step(self.to_device(host), phase=phase)
+            if col is not None:
+                cur = losses[col]
+            elif phase == 1:
+                cur = losses[0] + self.dr_e_w * losses[1]            # train_sr_dr.py:221
+            else:
+                cur = losses[2]                                       # :394
+            acc = cur.double() if acc is None else acc + cur.double()
+            n += 1
+            if log_every and i % log_every == 0:
+                log(f"train total loss:{float(acc) / n}")
+        if n == 0:
+            raise ValueError("train_epoch(): empty loader")
+        return float(acc) / n

@@ -202,3 +202,43 @@ def evaluate_full_catalogue(P, cfg, cat: Catalogue, batches, dist=None) -> Dict[
         if len(ranks):
             res[k] = metrics_from_ranks(ranks)
     return res
+
+
+# --------------------------------------------------------------------------------------------------
+# Opt-in fast driver loop: test() of train_sr.py:31-128 without the per-field .cuda() calls,
+# the D2H of every score matrix and the O(N^2) np.append bookkeeping -- same return tuple.
+# --------------------------------------------------------------------------------------------------
+_METRIC_ORDER_OVERLAP = ("d1_ov", "d1_no", "d2_ov", "d2_no", "d1", "d2")
+
+
+@torch.no_grad()
+def test(trainer, loader, overlap: bool = False):
+    """Drop-in for ``test(model, args, valLoader)``: returns ``(loss, loss_cls, <7 metrics per list>...)`` in the
+    reference's order -- lists (d1, d2) when ``overlap`` is false (train_sr.py:114-118), otherwise
+    (d1_ov, d1_no, d2_ov, d2_no, d1, d2) (:119-128).  ``loader`` yields the reference's collated batches
+    (dataset_seq.collate_fn_enhance); the last partial batch is expected to be dropped by the loader as in
+    train_sr.py:455."""
+    from . import hotpath
+    was_training = trainer.model.training
+    trainer.model.eval()
+    trainer.flush()
+    p1s, p2s, doms, ovs, losses = [], [], [], [], []
+    for host in loader:
+        b = trainer.to_device(host)
+        probs = trainer.scores(b)
+        B = probs.shape[2]
+        l, _ = hotpath.loss_fwd_bwd(probs[:1].contiguous(), b["label"], b["domain_id"], None, 0, 0.0, B * trainer.world)
+        losses.append(l[:1])
+        p1s.append(probs[0, 0]); p2s.append(probs[0, 1]); doms.append(b["domain_id"])
+        if overlap:
+            ovs.append(b["overlap_label"])
+    if was_training:
+        trainer.model.train()
+    if not p1s:
+        raise ValueError("test(): empty loader")
+    loss = float(np.mean(torch.cat(losses).cpu().numpy().astype(np.float64)))   # AverageMeter of loss.item()
+    res = evaluate_lists(torch.cat(p1s), torch.cat(p2s), torch.cat(doms), torch.cat(ovs) if overlap else None)
+    out = [loss, loss]
+    for k in (_METRIC_ORDER_OVERLAP if overlap else ("d1", "d2")):
+        out += list(res.get(k, (0.0,) * 7))
+    return tuple(out)

@@ -516,3 +516,101 @@ def test_c3_size_properties():
     k = int(n1.item())
     assert torch.equal(u1[:k], u3[:k]) and (u1[:k][1:] > u1[:k][:-1]).all()
     assert_close(g3[:k], g1[:k] + g2[:k], 1e-4, 1e-5)
+
+
+# ------------------------------------------------------------------ checkpoint / resume
+@pytest.mark.parametrize("isDR", [False, True])
+def test_checkpoint_resume_is_bit_exact(isDR):
+    """Stop after two steps, restore into a fresh trainer, continue: identical bits to the uninterrupted run
+    (dropout on, lazy row-Adam with pending rows at the time of the checkpoint, both optimizers when isDR)."""
+    import io
+    from amid_b200.engine import Trainer
+    B, L, C, V = 8, 12, 2, 301
+    rng = np.random.default_rng(5)
+    P = make_params(44, V, D, L, HID, B, isDR=isDR)
+    batches = [to_cuda(random_batch(rng, B, L, C, V)) for _ in range(5)]
+    phases = [1, 2, 1, 1, 2] if isDR else [1] * 5
+
+    def fresh():
+        torch.manual_seed(1234)
+        return Trainer(build_model(P, V, L, B, ts2=0.3, isDR=isDR, drop_p=0.5).train(), lr=1e-3, lr2=0.5)
+
+    a = fresh()
+    for b, ph in zip(batches[:2], phases[:2]):
+        a.step(b, phase=ph)
+    buf = io.BytesIO()
+    torch.save(a.checkpoint(), buf)                   # through serialisation, as a real resume would
+    for b, ph in zip(batches[2:], phases[2:]):
+        a.step(b, phase=ph)
+    a.flush()
+    r = fresh()
+    buf.seek(0)
+    r.load_checkpoint(torch.load(buf, weights_only=False))
+    for b, ph in zip(batches[2:], phases[2:]):
+        r.step(b, phase=ph)
+    r.flush()
+    for n in a.P:
+        assert torch.equal(a.P[n], r.P[n]), n
+    for sa, sr in zip(a.opt, r.opt):
+        assert sa.step == sr.step and torch.equal(sa.m, sr.m) and torch.equal(sa.tv, sr.tv)
+    with pytest.raises(Exception):
+        bad = a.checkpoint()
+        bad["world"] = 4
+        r.load_checkpoint(bad)
+
+
+# ------------------------------------------------------------------ opt-in fast driver loops (SURVEY.md 8f-2)
+def test_fast_test_loop_matches_reference_bookkeeping():
+    """evaluate.test() == test() of train_sr.py:31-128 on the three real C1 eval batches of the golden fixture:
+    same tuple layout, metrics identical to the list bookkeeping applied to the same scores, loss = the mean of the
+    per-batch BCE means."""
+    from amid_b200 import evaluate
+    from amid_b200.engine import Trainer
+    z = load("c1_eval_rank.npz")
+    P = make_params(12, int(z["V"]), D, 20, HID, 256)
+    tr = Trainer(build_model(P, int(z["V"]), 20, 256, ts2=0.4).eval())
+    keys = ("i_node", "neg_samples", "seq_d1", "seq_d2", "domain_id", "overlap_label")
+    loader = []
+    for i in range(3):
+        hb = {k: T(z[f"b{i}_{k}"]).float() for k in keys}                      # the reference collate yields float32
+        C = hb["neg_samples"].shape[1] + 1
+        hb["label"] = torch.cat((torch.ones(256, 1), torch.zeros(256, C - 1)), 1)
+        loader.append(hb)
+    out = evaluate.test(tr, loader, overlap=True)
+    assert len(out) == 2 + 6 * 7
+    # same scores through the list bookkeeping
+    devb = [tr.to_device(h) for h in loader]
+    probs = [tr.scores(b) for b in devb]
+    p1, p2 = torch.cat([p[0, 0] for p in probs]), torch.cat([p[0, 1] for p in probs])
+    dom, ov = torch.cat([b["domain_id"] for b in devb]), torch.cat([b["overlap_label"] for b in devb])
+    res = evaluate.evaluate_lists(p1, p2, dom, ov)
+    flat = []
+    for k in ("d1_ov", "d1_no", "d2_ov", "d2_no", "d1", "d2"):
+        flat += list(res[k])
+    assert tuple(flat) == out[2:]
+    # loss: mean over batches of mean(BCE(p_d1) * (1 - dom) + BCE(p_d2) * dom)  (train_sr.py:205-212)
+    want = np.mean([float(O.loss_cls(probs[i][0, 0].cpu(), probs[i][0, 1].cpu(), devb[i]["label"].cpu(),
+                                     devb[i]["domain_id"].cpu())) for i in range(3)])
+    assert abs(out[0] - want) < 1e-6 and out[0] == out[1]
+    short = evaluate.test(tr, loader, overlap=False)
+    assert len(short) == 2 + 2 * 7 and short[2:] == out[-14:]
+
+
+def test_fast_train_epoch_equals_manual_steps():
+    from amid_b200.engine import Trainer
+    B, L, C, V = 8, 12, 2, 97
+    rng = np.random.default_rng(8)
+    P = make_params(51, V, D, L, HID, B)
+    host = [random_batch(rng, B, L, C, V) for _ in range(4)]
+
+    def fresh():
+        torch.manual_seed(77)
+        return Trainer(build_model(P, V, L, B, ts2=0.3, drop_p=0.5).train(), lr=1e-3)
+
+    a, b = fresh(), fresh()
+    mean = a.train_epoch([{k: v.float() if k != "label" else v for k, v in h.items()} for h in host])
+    ls = [float(b.step(to_cuda(h))[0]) for h in host]
+    a.flush(); b.flush()
+    for n in a.P:
+        assert torch.equal(a.P[n], b.P[n]), n
+    assert abs(mean - float(np.mean(ls))) < 1e-6
