@@ -43,6 +43,19 @@ class HeadTensors(C.Structure):
     _fields_ = [("w0", c_void_p), ("b0", c_void_p), ("w2", c_void_p), ("b2", c_void_p)]
 
 
+class BatchSource(C.Structure):
+    _fields_ = [("hist_d1_vals", c_void_p), ("hist_d1_offs", c_void_p), ("hist_d2_vals", c_void_p), ("hist_d2_offs", c_void_p),
+                ("excl_vals", c_void_p), ("excl_offs", c_void_p), ("target", c_void_p), ("user", c_void_p),
+                ("domain", c_void_p), ("overlap", c_void_p), ("pool_d1", c_void_p), ("pool_d2", c_void_p),
+                ("n_pool_d1", c_int64), ("n_pool_d2", c_int64), ("n_rows", c_int64)]
+
+
+class BatchOut(C.Structure):
+    _fields_ = [("seq_d1", c_void_p), ("seq_d2", c_void_p), ("i_node", c_void_p), ("user_node", c_void_p),
+                ("domain_id", c_void_p), ("overlap_label", c_void_p), ("long_tail_mask_d1", c_void_p),
+                ("long_tail_mask_d2", c_void_p), ("neg_samples", c_void_p)]
+
+
 P = c_void_p
 _SIGS = {
     "amid_version": (c_int32, []),
@@ -90,6 +103,8 @@ _SIGS = {
     "amid_adam_rows_lazy": (c_int32, [P, P, P, P, P, P, P, c_int64, c_int32, c_float, c_float, c_float, c_float, P]),
     "amid_adam_rows_flush": (c_int32, [P, P, P, P, c_int64, c_int32, c_float, c_float, c_float, c_float, P]),
     "amid_rank_counts": (c_int32, [P, c_int64, c_int32, c_float, P, P, P]),
+    "amid_batch_build": (c_int32, [POINTER(BatchSource), P, c_int32, c_int32, c_int32, c_int32, c_int64, c_uint64,
+                                  POINTER(BatchOut), P]),
     "amid_catalogue_item_proj": (c_int32, [P, c_int64, P, c_int64, P, P, c_int32, P, P]),
     "amid_catalogue_user_proj": (c_int32, [P, P, c_int32, P, c_int32, P, P]),
     "amid_catalogue_rank": (c_int32, [P, P, c_int32, c_int32, P, c_int32, c_int32, P, P, P, c_float, P, P, P]),

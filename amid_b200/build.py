@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libamid_b200.so")
-SOURCES = ["abi.cu", "gather.cu", "encoder.cu", "mim.cu", "score.cu", "catalogue.cu", "embgrad.cu", "tc_test.cu"]
+SOURCES = ["abi.cu", "gather.cu", "encoder.cu", "mim.cu", "score.cu", "catalogue.cu", "pipeline.cu", "embgrad.cu", "tc_test.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC"]
 

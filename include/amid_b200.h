@@ -267,6 +267,31 @@ int amid_catalogue_scores(const float* A, const int32_t* user_rows, int32_t n_us
                           int32_t i_lo, int32_t i_hi, const int32_t* pos_idx, const float* w2, const float* b2,
                           float* s_pos, float* scores, amid_stream_t stream);
 
+/* ---- a11: batch construction on the device (dataset_seq.py:177-236 __getitem__, :252-274 collate) ----
+ * Histories are tokenised once into CSR arrays (amid_b200/pipeline.py): hist_dk = the history the encoder sees
+ * (for the row's own domain: target and its earlier occurrences removed, :189-195), excl = the sorted unique items
+ * of the row's full own-domain sequence (the set the negatives avoid, :188), pools = sorted item ids per domain
+ * (:141-142, 151-158).  One launch writes a whole batch; ids are int64 throughout. */
+typedef struct {
+    const int64_t *hist_d1_vals, *hist_d1_offs;   /* offs: [n_rows+1] */
+    const int64_t *hist_d2_vals, *hist_d2_offs;
+    const int64_t *excl_vals, *excl_offs;
+    const int64_t *target, *user;                 /* [n_rows] */
+    const int32_t *domain, *overlap;              /* [n_rows] */
+    const int64_t *pool_d1, *pool_d2;
+    int64_t n_pool_d1, n_pool_d2, n_rows;
+} amid_batch_source;
+typedef struct {
+    int64_t *seq_d1, *seq_d2;                     /* [B,L] last L items, left-padded with pad_id (:12-22) */
+    int64_t *i_node, *user_node, *domain_id, *overlap_label, *long_tail_mask_d1, *long_tail_mask_d2;   /* [B] */
+    int64_t *neg_samples;                         /* [B,K] or NULL (replay mode: the caller supplies negatives) */
+} amid_batch_out;
+/* rows[b] selects the dataset row of batch position b.  K > 0 with neg_samples != NULL draws K distinct negatives
+ * per row from the target domain's pool minus the row's exclusion list (seeded, reproducible); an exhausted pool or
+ * a row index out of range raises the gather error flag (amid_gather_error_host_sync). */
+int amid_batch_build(const amid_batch_source* src, const int64_t* rows, int32_t B, int32_t L, int32_t K,
+                     int32_t long_length, int64_t pad_id, uint64_t seed, const amid_batch_out* out, amid_stream_t stream);
+
 /* ---- test support: the keep-mask a dropout site uses (for oracle mask injection) ---- */
 /* feature site: out[r*128+c] for r<rows; attention site: out[((b*8+h)*L+i)*L+j]. */
 int amid_dropout_mask_feature(const amid_dropout* drop, uint32_t site, int64_t rows, uint8_t* out, amid_stream_t stream);

@@ -614,3 +614,46 @@ def test_fast_train_epoch_equals_manual_steps():
     for n in a.P:
         assert torch.equal(a.P[n], b.P[n]), n
     assert abs(mean - float(np.mean(ls))) < 1e-6
+
+
+# ------------------------------------------------------------------ flag matrix, training direction
+@pytest.mark.parametrize("isInC,isItC,isDR", [(True, True, False), (True, False, False), (False, False, False),
+                                              (True, True, True)])
+def test_flag_matrix_train_grads_vs_oracle(isInC, isItC, isDR):
+    """InnerComp in front of the encoders (model_seq.py:399-402, 422-424: positional table and attention over 2L),
+    with / without InterComp, with / without the DR heads: probabilities, loss and every gradient (dropout off)."""
+    hp = _hp()
+    B, L, C, V = 6, 10, 3, 89
+    Le = 2 * L if isInC else L
+    rng = np.random.default_rng(17 + 2 * isInC + isItC)
+    P = make_params(61, V, D, Le, HID, B, isInC=isInC, isItC=isItC, isDR=isDR)
+    ts = 0.12
+    m = build_model(P, V, L, B, isInC=isInC, isItC=isItC, ts1=ts, ts2=ts, isDR=isDR, drop_p=0.0).train()
+    b = to_cuda(random_batch(rng, B, L, C, V))
+    probs, ctx = hp.forward(m.param_dict(), m.cfg, b["i_node"], b["neg_samples"], b["seq_d1"], b["seq_d2"], train=True, seed=1)
+    Po = {k: v.clone().requires_grad_(True) for k, v in P.items()}
+    col = {}
+    outs = oracle_forward(Po, b, isInC=isInC, isItC=isItC, ts1=ts, ts2=ts, isDR=isDR, collect=col)
+    if isItC:
+        pj = torch.softmax(O.mim_scores(col["enc1"], col["enc2"]), 0)
+        if (pj - ts).abs().min() < 1e-4:
+            pytest.skip("gate margin too small")
+    for i, o in enumerate(outs):
+        assert_close(probs[i // 2, i % 2], o, 0, 3e-5, f"out {i}")
+    mode = 1 if isDR else 0
+    losses, dprobs = hp.loss_fwd_bwd(probs, b["label"], b["domain_id"], b["ob_label"], mode, 0.01, B)
+    lab, dom = b["label"].cpu(), b["domain_id"].cpu()
+    lo = O.loss_cls(outs[0], outs[1], lab, dom)
+    assert_close(losses[0], lo, 3e-5, 0)
+    if isDR:
+        lo = lo + 0.01 * O.loss_dr_e(*outs, lab, dom)
+    lo.backward()
+    G, ids_all, rows_all = hp.backward(m.param_dict(), m.cfg, ctx, dprobs)
+    for k, v in Po.items():
+        if v.grad is None:
+            continue
+        if k == "item_emb_layer.emb_item.weight":
+            uid, ug, nu = hp.segreduce(ids_all, rows_all, V)
+            assert_close(hp.dense_table_grad(uid, ug, nu, V), v.grad, 1e-3, grad_tol(v.grad), k)
+        else:
+            assert_close(G[k], v.grad, 1e-3, grad_tol(v.grad), k)

@@ -1,0 +1,53 @@
+"""Sample construction (dataset_seq.py:177-236): the oracle restatement against the fixture produced by executing the
+reference dataset + collate, and the host-side CSR preparation of amid_b200.pipeline against the oracle."""
+import numpy as np
+
+from common import load
+from oracle import amid_oracle as O
+
+
+def _rows(z):
+    out = []
+    for i in range(int(z["n_rows"])):
+        s1 = z["in_seq_d1_vals"][z["in_seq_d1_offs"][i]:z["in_seq_d1_offs"][i + 1]].tolist()
+        s2 = z["in_seq_d2_vals"][z["in_seq_d2_offs"][i]:z["in_seq_d2_offs"][i + 1]].tolist()
+        out.append((int(z["in_user"][i]), s1, s2, int(z["in_domain"][i])))
+    return out
+
+
+def test_oracle_sample_construction_matches_reference_dataset():
+    z = load("dataset_small.npz")
+    L, ll, pad = int(z["seq_len"]), int(z["long_length"]), int(z["pad_id"])
+    for tag in ("train", "eval"):
+        pools = [set(z[f"{tag}_pool_d1"].tolist()), set(z[f"{tag}_pool_d2"].tolist())]
+        for i, (u, s1, s2, dom) in enumerate(_rows(z)):
+            s = O.build_sample(s1, s2, dom, L, ll, pad)
+            assert s["i_node"] == z[f"{tag}_i_node"][i]
+            assert s["seq_d1"] == z[f"{tag}_seq_d1"][i].tolist() and s["seq_d2"] == z[f"{tag}_seq_d2"][i].tolist()
+            assert s["long_tail_mask_d1"] == z[f"{tag}_long_tail_mask_d1"][i]
+            assert s["long_tail_mask_d2"] == z[f"{tag}_long_tail_mask_d2"][i]
+            assert s["domain_id"] == z[f"{tag}_domain_id"][i] and s["overlap_label"] == z[f"{tag}_overlap_label"][i]
+            # the reference's negatives come from pool - own sequence, without replacement
+            negs = z[f"{tag}_neg_samples"][i].astype(np.int64).tolist()
+            assert len(set(negs)) == len(negs)
+            assert all(n in pools[dom] and n not in s["exclude"] for n in negs)
+        assert z[f"{tag}_label"].shape[1] == z[f"{tag}_neg_samples"].shape[1] + 1
+        assert (z[f"{tag}_label"][:, 0] == 1).all() and (z[f"{tag}_label"][:, 1:] == 0).all()
+
+
+def test_host_csr_preparation_matches_oracle():
+    from amid_b200.pipeline import prepare_rows
+    z = load("dataset_small.npz")
+    rows = _rows(z)
+    prep = prepare_rows([r[0] for r in rows], [r[1] for r in rows], [r[2] for r in rows], [r[3] for r in rows])
+    assert sorted(prep["pool_d1"].tolist()) == z["train_pool_d1"].tolist()
+    assert sorted(prep["pool_d2"].tolist()) == z["train_pool_d2"].tolist()
+    for i, (u, s1, s2, dom) in enumerate(rows):
+        s = O.build_sample(s1, s2, dom, 10**6, 1, -1)       # no truncation: the whole processed histories
+        for k, name in ((1, "seq_d1"), (2, "seq_d2")):
+            got = prep[f"hist_d{k}_vals"][prep[f"hist_d{k}_offs"][i]:prep[f"hist_d{k}_offs"][i + 1]].tolist()
+            assert got == [x for x in s[name] if x != -1]
+        ex = prep["excl_vals"][prep["excl_offs"][i]:prep["excl_offs"][i + 1]].tolist()
+        assert ex == sorted(s["exclude"])
+        assert prep["target"][i] == s["i_node"] and prep["domain"][i] == s["domain_id"]
+        assert prep["overlap"][i] == s["overlap_label"]
