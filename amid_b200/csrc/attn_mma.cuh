@@ -108,17 +108,26 @@ __device__ __forceinline__ float quad_sum(float v) {
 // Dropout keep bits of an accumulator fragment whose ROWS are query rows (a = row g, b = row g+8) and
 // whose columns are the keys n0+2t, n0+2t+1.  The two threads of a pair (t, t^1) share one 4-key hash
 // group, so each computes one of the two rows and they exchange.  rb4_* = (bh*L + row) * Lp / 4.
+// The index space of an attention site is B*8*L*ceil(L/4) 4-key groups; the launchers require it to fit 32 bits,
+// so the hash input is a 32-bit index (rng4 sees a zero high word: identical bits to the 64-bit form the mask
+// export and the fp32 kernels use).
 struct RowKeep {
-    uint64_t rb4_a, rb4_b;
+    uint32_t rb4_a, rb4_b;
 };
-__device__ __forceinline__ void keep_rows(const DropCfg& dc, uint32_t site, const RowKeep& rk, int n0, int t, bool (&kp)[4]) {
-    const uint64_t idx4 = ((t & 1) ? rk.rb4_b : rk.rb4_a) + (uint32_t)((n0 >> 2) + (t >> 1));
-    const uint32_t mine = rng4(dc.seed, site, idx4);
+// byte-lane test without the shift: (r & (0xFF << 8*lane)) >= (thr << 8*lane)
+struct ByteLane {
+    uint32_t mask, thr;
+    __device__ __forceinline__ ByteLane(int lane4, uint32_t thr8) : mask(0xFFu << (8 * lane4)), thr(thr8 << (8 * lane4)) {}
+    __device__ __forceinline__ bool keep(uint32_t r) const { return (r & mask) >= thr; }
+};
+__device__ __forceinline__ void keep_rows(const DropCfg& dc, uint32_t site, const RowKeep& rk, const ByteLane& b0,
+                                          const ByteLane& b1, int n0, int t, bool (&kp)[4]) {
+    const uint32_t idx4 = ((t & 1) ? rk.rb4_b : rk.rb4_a) + (uint32_t)((n0 >> 2) + (t >> 1));
+    const uint32_t mine = rng4(dc.seed, site, (uint64_t)idx4);
     const uint32_t other = __shfl_xor_sync(0xffffffffu, mine, 1);
     const uint32_t ra = (t & 1) ? other : mine, rb = (t & 1) ? mine : other;
-    const int l0 = 2 * (t & 1);
-    kp[0] = rng_keep(ra, l0, dc.thr16); kp[1] = rng_keep(ra, l0 + 1, dc.thr16);
-    kp[2] = rng_keep(rb, l0, dc.thr16); kp[3] = rng_keep(rb, l0 + 1, dc.thr16);
+    kp[0] = b0.keep(ra); kp[1] = b1.keep(ra);
+    kp[2] = b0.keep(rb); kp[3] = b1.keep(rb);
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -139,6 +148,7 @@ k_attn_fwd_mma(const float* __restrict__ q, const float* __restrict__ k, const f
     stage(vs, v + base, L, Lpad);
     __syncthreads();
     const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    const ByteLane bl0(2 * (t & 1), dc.thr16), bl1(2 * (t & 1) + 1, dc.thr16);   // this thread's two key columns
     const uint64_t bhL = (uint64_t)bh * L;
     for (;;) {
         const int item = next_item(&queue, lane);
@@ -151,8 +161,8 @@ k_attn_fwd_mma(const float* __restrict__ q, const float* __restrict__ k, const f
         float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
         const int row_a = r0 + g, row_b = r0 + g + 8;
         RowKeep rk;
-        rk.rb4_a = (bhL + min(row_a, L - 1)) * (uint64_t)(Lp >> 2);
-        rk.rb4_b = (bhL + min(row_b, L - 1)) * (uint64_t)(Lp >> 2);
+        rk.rb4_a = ((uint32_t)bhL + (uint32_t)min(row_a, L - 1)) * (uint32_t)(Lp >> 2);
+        rk.rb4_b = ((uint32_t)bhL + (uint32_t)min(row_b, L - 1)) * (uint32_t)(Lp >> 2);
         const int kend = min(r0 + 16, L);         // keys [0, kend) can be visible to this tile
         for (int kb = 0; kb < kend; kb += 32) {
             float s[4][4];
@@ -193,7 +203,7 @@ k_attn_fwd_mma(const float* __restrict__ q, const float* __restrict__ k, const f
                 l0 += p[0] + p[1]; l1 += p[2] + p[3];
                 if (dc.train) {
                     bool kp[4];
-                    keep_rows(dc, site, rk, n0, t, kp);
+                    keep_rows(dc, site, rk, bl0, bl1, n0, t, kp);
 #pragma unroll
                     for (int e = 0; e < 4; ++e) p[e] = kp[e] ? p[e] : 0.f;      // 1/(1-p) folded into the final scale
                 }
@@ -256,6 +266,7 @@ k_attn_bwd_mma(const float* __restrict__ q, const float* __restrict__ k, const f
     }
     __syncthreads();
     const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    const ByteLane bl0(2 * (t & 1), dc.thr16), bl1(2 * (t & 1) + 1, dc.thr16);   // this thread's two key columns
     const uint64_t bhL = (uint64_t)bh * L;
     // Work items, heaviest first: item 2n = pass A on query tile ntile-1-n, item 2n+1 = pass B on key tile n.
     for (;;) {
@@ -270,8 +281,8 @@ k_attn_bwd_mma(const float* __restrict__ q, const float* __restrict__ k, const f
             const int row_a = r0 + g, row_b = r0 + g + 8;
             const float la = ls[row_a], lb = ls[row_b], Da = Dv[row_a], Db = Dv[row_b];
             RowKeep rk;
-            rk.rb4_a = (bhL + min(row_a, L - 1)) * (uint64_t)(Lp >> 2);
-            rk.rb4_b = (bhL + min(row_b, L - 1)) * (uint64_t)(Lp >> 2);
+            rk.rb4_a = ((uint32_t)bhL + (uint32_t)min(row_a, L - 1)) * (uint32_t)(Lp >> 2);
+            rk.rb4_b = ((uint32_t)bhL + (uint32_t)min(row_b, L - 1)) * (uint32_t)(Lp >> 2);
             float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
             const int kend = min(r0 + 16, L);
             for (int n0 = 0; n0 < kend; n0 += 8) {
@@ -280,7 +291,7 @@ k_attn_bwd_mma(const float* __restrict__ q, const float* __restrict__ k, const f
                 mma_xt(dp, ag, vs, n0, g, t);
                 if (dc.train) {
                     bool kp[4];
-                    keep_rows(dc, site, rk, n0, t, kp);
+                    keep_rows(dc, site, rk, bl0, bl1, n0, t, kp);
 #pragma unroll
                     for (int e = 0; e < 4; ++e) dp[e] = kp[e] ? dp[e] : 0.f;
                 }
@@ -312,6 +323,7 @@ k_attn_bwd_mma(const float* __restrict__ q, const float* __restrict__ k, const f
             const int hsel = g & 3;
             const uint32_t grp_a = (uint32_t)(key_a >> 2), grp_b = (uint32_t)(key_b >> 2);
             const int src_base = lane & ~12;
+            const ByteLane bka(key_a & 3, dc.thr16), bkb(key_b & 3, dc.thr16);
             for (int i0 = j0; i0 < L; i0 += 8) {        // queries i >= key, 8 at a time
                 float st[4] = {0.f, 0.f, 0.f, 0.f}, dpt[4] = {0.f, 0.f, 0.f, 0.f};
                 mma_xt(st, ak, qs, i0, g, t);           // st[key][query] = k_key . q_query (log2 domain)
@@ -329,14 +341,14 @@ k_attn_bwd_mma(const float* __restrict__ q, const float* __restrict__ k, const f
                 float pd[4] = {p[0], p[1], p[2], p[3]};
                 if (dc.train) {
                     const int qsel = min((hsel & 1) ? qb : qa, L - 1);
-                    const uint64_t idx4 = (bhL + qsel) * (uint64_t)(Lp >> 2) + ((hsel & 2) ? grp_b : grp_a);
-                    const uint32_t mine = rng4(dc.seed, site, idx4);
+                    const uint32_t idx4 = ((uint32_t)bhL + (uint32_t)qsel) * (uint32_t)(Lp >> 2) + ((hsel & 2) ? grp_b : grp_a);
+                    const uint32_t mine = rng4(dc.seed, site, (uint64_t)idx4);
                     uint32_t r[4];
 #pragma unroll
                     for (int h4 = 0; h4 < 4; ++h4) r[h4] = __shfl_sync(0xffffffffu, mine, src_base | (h4 << 2));
                     // r[0]=(qa,key_a) r[1]=(qb,key_a) r[2]=(qa,key_b) r[3]=(qb,key_b); lane inside the group = key & 3
-                    const bool k0 = rng_keep(r[0], key_a & 3, dc.thr16), k1 = rng_keep(r[1], key_a & 3, dc.thr16);
-                    const bool k2 = rng_keep(r[2], key_b & 3, dc.thr16), k3 = rng_keep(r[3], key_b & 3, dc.thr16);
+                    const bool k0 = bka.keep(r[0]), k1 = bka.keep(r[1]);
+                    const bool k2 = bkb.keep(r[2]), k3 = bkb.keep(r[3]);
                     pd[0] = k0 ? p[0] : 0.f; pd[1] = k1 ? p[1] : 0.f;
                     pd[2] = k2 ? p[2] : 0.f; pd[3] = k3 ? p[3] : 0.f;
                     dpt[0] = k0 ? dpt[0] : 0.f; dpt[1] = k1 ? dpt[1] : 0.f;

@@ -734,6 +734,8 @@ static int check_encoder_args(int B, int L) {
     AMID_REQUIRE(B > 0 && L > 0, "encoder: B=%d L=%d must be positive", B, L);
     AMID_REQUIRE(L <= 512, "encoder: L=%d > 512 unsupported (per-CTA shared-memory attention)", L);
     AMID_REQUIRE((int64_t)B * L < (1ll << 31) / D, "encoder: B*L too large");
+    // the tensor-core attention kernels index the dropout stream of a site with 32 bits
+    AMID_REQUIRE((int64_t)B * 8 * L * ((L + 3) / 4) < (1ll << 32), "encoder: B*8*L*ceil(L/4) must be below 2^32");
     return 0;
 }
 
