@@ -109,34 +109,6 @@ __device__ __forceinline__ void warp_load32(float* buf, int lane, const float* _
     }
     __syncwarp();
 }
-// Split form of warp_load32: pf_issue only issues the 8 global loads (so they can fly across an MMA wait
-// or a barrier), pf_consume moves them through the warp stage into one-row-per-lane registers.
-struct Pf {
-    float4 x[8];
-};
-template <bool CG>
-__device__ __forceinline__ void pf_issue(Pf& pf, const float* g, int rows_valid, int lane) {
-#pragma unroll
-    for (int it = 0; it < 8; ++it) {
-        const int r = it * 4 + (lane >> 3), u = lane & 7;
-        pf.x[it] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (r < rows_valid) {
-            const float4* p = reinterpret_cast<const float4*>(g + (size_t)r * D + u * 4);
-            pf.x[it] = CG ? __ldcg(p) : __ldg(p);
-        }
-    }
-}
-__device__ __forceinline__ void pf_consume(float* buf, int lane, const Pf& pf, float (&v)[32]) {
-#pragma unroll
-    for (int it = 0; it < 8; ++it) *reinterpret_cast<float4*>(buf + ws_off(it * 4 + (lane >> 3), lane & 7)) = pf.x[it];
-    __syncwarp();
-#pragma unroll
-    for (int u = 0; u < 8; ++u) {
-        const float4 x = *reinterpret_cast<const float4*>(buf + ws_off(lane, u));
-        v[4 * u] = x.x; v[4 * u + 1] = x.y; v[4 * u + 2] = x.z; v[4 * u + 3] = x.w;
-    }
-    __syncwarp();
-}
 // the same for data written earlier in this kernel by other threads (coherent L2 loads)
 __device__ __forceinline__ void warp_load32_cg(float* buf, int lane, const float* g, int rows_valid, float (&v)[32]) {
 #pragma unroll

@@ -94,9 +94,8 @@ class ShardedTable:
     def lookup(self, ids: torch.Tensor) -> Route:
         if ids.dtype != torch.int64 or ids.dim() != 1:
             raise ValueError("ids must be a flat int64 tensor")
-        if ids.numel() and (int(ids.min()) < 0 or int(ids.max()) >= self.V):
-            raise IndexError("sharded lookup: item id out of range")
         G = self.world
+        oob = ((ids < 0) | (ids >= self.V)).any().to(torch.int64).reshape(1)   # read back together with the bucket sizes
         uniq, inv = torch.unique(ids, return_inverse=True)                 # sorted ascending
         dest = uniq % G
         order = torch.argsort(dest, stable=True)                           # bucket by owner, ascending id inside
@@ -104,7 +103,10 @@ class ShardedTable:
         send_counts = torch.bincount(dest, minlength=G)
         recv_counts = torch.empty_like(send_counts)
         self.dist.all_to_all_single(recv_counts, send_counts, group=self.group)
-        send_splits, recv_splits = send_counts.tolist(), recv_counts.tolist()
+        host = torch.cat((send_counts, recv_counts, oob)).tolist()             # the one device->host read of a lookup
+        send_splits, recv_splits = host[:G], host[G:2 * G]
+        if host[-1]:
+            raise IndexError("sharded lookup: item id out of range")
         recv_local = torch.empty(sum(recv_splits), device=ids.device, dtype=torch.int64)
         self.dist.all_to_all_single(recv_local, send_local, recv_splits, send_splits, group=self.group)
         out_rows = self._gather(self.shard, recv_local)                    # owner side: csrc/gather.cu
