@@ -222,16 +222,21 @@ class Trainer:
         tdist.all_gather_into_tensor(self.table_padded, self.shard_p, group=self.dist.group)
 
     def _exchange_table_grads(self, uid, ug, nu):
-        """Replicated table under DP: all-gather every rank's pre-reduced (row id, gradient row)
-        list (unused slots carry the sentinel id V-1 with a zero row) and reduce again in rank
-        order, so every replica applies the identical update."""
+        """Replicated table under DP: all-gather every rank's pre-reduced (row id, gradient row) list and reduce again
+        in rank order, so every replica applies the identical update.  The lists are cut to the largest per-rank count
+        (one small all-gather + host read per step) -- on real data a step touches a few per cent of its positions'
+        worth of distinct rows (the pad row dominates), so the exchange is megabytes, not the 210 MB of a full-length
+        list; unused slots carry the sentinel id V-1 with a zero row."""
         n = uid.numel()
         dev = ug.device
-        uid, ug = pad_for_exchange(uid, ug, nu, self.V)
-        all_ids = torch.empty(n * self.world, device=dev, dtype=torch.int64)
-        all_rows = torch.empty(n * self.world, D, device=dev, dtype=torch.float32)
-        self.dist.all_gather_into(all_ids, uid)
-        self.dist.all_gather_into(all_rows, ug)
+        nu_all = torch.empty(self.world, device=dev, dtype=torch.int32)
+        self.dist.all_gather_into(nu_all, nu.reshape(1).to(torch.int32))
+        cap = min(n, max(256, (int(nu_all.max()) + 255) // 256 * 256))
+        uid, ug = pad_for_exchange(uid[:cap], ug[:cap], nu, self.V)
+        all_ids = torch.empty(cap * self.world, device=dev, dtype=torch.int64)
+        all_rows = torch.empty(cap * self.world, D, device=dev, dtype=torch.float32)
+        self.dist.all_gather_into(all_ids, uid.contiguous())
+        self.dist.all_gather_into(all_rows, ug.contiguous())
         return hotpath.segreduce(all_ids, all_rows, self.V)
 
     # ------------------------------------------------------------------ evaluation forward

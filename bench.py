@@ -32,7 +32,7 @@ D, HID = 128, 32
 
 
 def parse():
-    global V_ITEMS
+    global V_ITEMS, REALISTIC
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=30)
@@ -47,36 +47,46 @@ def parse():
     ap.add_argument("--dense-table", action="store_true", help="dense Adam over the whole table (reference-style)")
     ap.add_argument("--table-sync", default="auto", choices=["auto", "sparse", "dense", "sharded"],
                     help="multi-GPU table strategy (engine.Trainer); 'sharded' = row-sharded table + all-to-all (config 4)")
+    ap.add_argument("--ids", default="uniform", choices=["uniform", "realistic"],
+                    help="uniform = roofline variant (default); realistic = short left-padded histories (SURVEY 8d)")
     ap.add_argument("--items", type=int, default=V_ITEMS, help="table rows V (config 4: 20000002)")
     ap.add_argument("--precision", default="bf16", choices=["fp32", "tf32", "bf16"],
                     help="encoder GEMM stages: tf32 = tcgen05 tensor cores (fp32 accumulate), fp32 = exact CUDA-core tiles")
     a = ap.parse_args()
     V_ITEMS = a.items
+    REALISTIC = a.ids == "realistic"
     return a
 
 
 def workload_name(a):
     return (f"C3 synthetic train step: per-GPU batch {a.batch}, L={a.seq_len}, d={D}, hid={HID}, C={1 + a.neg}, "
-            f"V={V_ITEMS}, SASRec+ItC(ts2=0.4){'+DR' if a.dr else ''}, dropout 0.5, uniform ids (roofline variant), "
+            f"V={V_ITEMS}, SASRec+ItC(ts2=0.4){'+DR' if a.dr else ''}, dropout 0.5, {'uniform ids (roofline variant)' if a.ids == 'uniform' else 'realistic ids (median-5 histories, left-padded)'}, "
             f"{'exact-fp32 path' if a.precision == 'fp32' else 'tcgen05 ' + a.precision.upper() + ' GEMM stages, fp32 accumulate/storage'}")
 
 
+REALISTIC = False
+
+
 def synth_batch(rng, B, L, C, V):
-    """Uniform-random ids over [0,V), no padding (SURVEY.md section 8d roofline variant)."""
+    """Uniform-random ids over [0,V), no padding (SURVEY.md section 8d roofline variant).  With --ids realistic the
+    histories have min(L, Geometric) real items (median 5, as on cloth_sport) left-padded with the id V//2 + 1."""
+    def seqs():
+        s = rng.integers(0, V, (B, L))
+        if REALISTIC:
+            lens = np.minimum(L, rng.geometric(1.0 - 0.5 ** (1.0 / 5.0), B))
+            s[np.arange(L)[None, :] < (L - lens)[:, None]] = V // 2 + 1
+        return torch.from_numpy(s)
     return {
         "i_node": torch.from_numpy(rng.integers(0, V, B)),
         "neg_samples": torch.from_numpy(rng.integers(0, V, (B, C - 1))),
-        "seq_d1": torch.from_numpy(rng.integers(0, V, (B, L))),
-        "seq_d2": torch.from_numpy(rng.integers(0, V, (B, L))),
+        "seq_d1": seqs(),
+        "seq_d2": seqs(),
         "domain_id": torch.from_numpy(rng.integers(0, 2, B)),
         "ob_label": torch.from_numpy(rng.integers(0, 2, B)),
         "label": torch.cat((torch.ones(B, 1), torch.zeros(B, C - 1)), 1),
     }
 
 
-# ------------------------------------------------------------------------------------------------
-# CPU arm: the oracle port of the reference path + torch.optim.Adam, on the host cores
-# ------------------------------------------------------------------------------------------------
 def cpu_reference_steps(a, steps, warmup, sample):
     """Times `steps` CPU train steps on `sample` sequences of the workload; returns seq/s."""
     from common import make_keep_masks, make_params
@@ -392,7 +402,9 @@ def run_ours(a):
     model = SASRec(user_length=0, user_emb_dim=D, item_length=V_ITEMS, item_emb_dim=D, seq_len=L, hid_dim=HID, bs=Bg,
                    isInC=False, isItC=True, threshold1=0.5, threshold2=0.4, isDR=a.dr).cuda().train()
     model.cfg.precision = a.precision
-    tr = Trainer(model, lr=5e-4, dist=dctx, sparse_table=not a.dense_table, rows_per_step_hint=B * (2 * L + C),
+    # distinct table rows a rank touches per step: every position for uniform ids, ~8 real items per history otherwise
+    hint = B * (2 * L + C) if a.ids == "uniform" else B * (2 * 8 + C)
+    tr = Trainer(model, lr=5e-4, dist=dctx, sparse_table=not a.dense_table, rows_per_step_hint=hint,
                  table_sync=a.table_sync)
     rng = np.random.default_rng(100 + rank)
     n_pool = 4
