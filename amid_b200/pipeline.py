@@ -35,7 +35,7 @@ def _csr(lists: Sequence[Sequence[int]]):
 
 
 def prepare_rows(user_ids: Sequence[int], seq_d1: Sequence[Sequence[int]], seq_d2: Sequence[Sequence[int]],
-                 domain_id: Sequence[int]) -> Dict[str, np.ndarray]:
+                 domain_id: Sequence[int], ob_label: Optional[Sequence[int]] = None) -> Dict[str, np.ndarray]:
     """One pass over the table (host, once per dataset): the deterministic part of __getitem__.
     For the row's own domain the target is the last item and it is removed from the history together with all its
     earlier occurrences (dataset_seq.py:189-195 / 207-213); the other domain's history is used whole; negatives must
@@ -68,6 +68,10 @@ def prepare_rows(user_ids: Sequence[int], seq_d1: Sequence[Sequence[int]], seq_d
            "pool_d1": np.asarray(sorted(pool1), dtype=np.int64), "pool_d2": np.asarray(sorted(pool2), dtype=np.int64)}
     for name, lists in (("hist_d1", h1), ("hist_d2", h2), ("excl", ex)):
         out[name + "_vals"], out[name + "_offs"] = _csr(lists)
+    if ob_label is not None:                       # DualDomainSeqDatasetDR (dataset_seq.py:453, 498, 551): copied per row
+        if len(ob_label) != n:
+            raise ValueError("prepare_rows: ob_label length differs")
+        out["ob_label"] = np.asarray(ob_label, dtype=np.int64)
     return out
 
 
@@ -76,7 +80,7 @@ def prepare_csv(csv_path: str) -> Dict[str, np.ndarray]:
     import pandas as pd
     df = pd.read_csv(csv_path)
     return prepare_rows(df["user_id"].tolist(), [json.loads(s) for s in df["seq_d1"]], [json.loads(s) for s in df["seq_d2"]],
-                        df["domain_id"].tolist())
+                        df["domain_id"].tolist(), df["ob_label"].tolist() if "ob_label" in df.columns else None)
 
 
 class DeviceDataset:
@@ -130,6 +134,8 @@ class DeviceDataset:
             if code:
                 raise IndexError("batch: row index out of range or item pool exhausted by the exclusion list")
         out["neg_samples"] = neg
+        if "ob_label" in self.t:                   # the DR drivers' extra field (train_sr_dr.py:201, 374)
+            out["ob_label"] = self.t["ob_label"][rows]
         out["label"] = torch.cat((torch.ones(B, 1, device=self.dev), torch.zeros(B, K, device=self.dev)), 1)
         return out
 

@@ -80,6 +80,18 @@ def main():
             save[f"{tag}_{k}"] = v.numpy()
         save[f"{tag}_pool_d1"] = np.array(sorted(ds.item_pool_d1), dtype=np.int64)
         save[f"{tag}_pool_d2"] = np.array(sorted(ds.item_pool_d2), dtype=np.int64)
+    # the doubly-robust variant (DualDomainSeqDatasetDR, dataset_seq.py:443-591): one more column, ob_label
+    rng = np.random.default_rng(3)
+    ob = rng.integers(0, 2, len(data))
+    csv_dr = "/tmp/amid_dataset_golden_dr.csv"
+    pd.DataFrame({"user_id": [r[0] for r in data], "seq_d1": [json.dumps(r[1]) for r in data],
+                  "seq_d2": [json.dumps(r[2]) for r in data], "domain_id": [r[3] for r in data], "ob_label": ob}).to_csv(csv_dr, index=False)
+    save["in_ob_label"] = ob.astype(np.int64)
+    random.seed(12)
+    ds = dataset_seq.DualDomainSeqDatasetDR(SEQ_LEN, True, 1, LONG_LEN, PAD, csv_dr)
+    batch = dataset_seq.collate_fn_enhanceDR([ds[i] for i in range(len(data))])
+    for k, v in batch.items():
+        save[f"dr_{k}"] = v.numpy()
     np.savez_compressed(os.path.join(HERE, "dataset_small.npz"), **save)
     print("wrote dataset_small.npz", {k: np.asarray(v).shape for k, v in save.items()})
 

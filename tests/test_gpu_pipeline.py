@@ -102,3 +102,18 @@ def test_epoch_iterator_feeds_the_trainer():
     other = [b["i_node"].clone() for b in ds.epoch(B, seed=6)]
     assert all(torch.equal(x, y) for x, y in zip(first, again))
     assert any(not torch.equal(x, y) for x, y in zip(first, other))
+
+
+def test_dr_variant_replay_matches_reference_batch():
+    """DualDomainSeqDatasetDR + collate_fn_enhanceDR (dataset_seq.py:443-591): the same fields plus ob_label."""
+    from amid_b200.pipeline import DeviceDataset, prepare_rows
+    z = load("dataset_small.npz")
+    n = int(z["n_rows"])
+    s1 = [z["in_seq_d1_vals"][z["in_seq_d1_offs"][i]:z["in_seq_d1_offs"][i + 1]].tolist() for i in range(n)]
+    s2 = [z["in_seq_d2_vals"][z["in_seq_d2_offs"][i]:z["in_seq_d2_offs"][i + 1]].tolist() for i in range(n)]
+    prep = prepare_rows(z["in_user"].tolist(), s1, s2, z["in_domain"].tolist(), z["in_ob_label"].tolist())
+    ds = DeviceDataset(prep, int(z["seq_len"]), int(z["long_length"]), int(z["pad_id"]))
+    b = ds.batch(torch.arange(n), negatives=torch.from_numpy(z["dr_neg_samples"]).long(), check=True)
+    for k in ("user_node", "i_node", "seq_d1", "seq_d2", "long_tail_mask_d1", "long_tail_mask_d2", "domain_id",
+              "overlap_label", "ob_label", "neg_samples", "label"):
+        assert np.array_equal(b[k].cpu().numpy().astype(np.float64), z[f"dr_{k}"].astype(np.float64)), k

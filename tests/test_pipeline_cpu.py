@@ -51,3 +51,19 @@ def test_host_csr_preparation_matches_oracle():
         assert ex == sorted(s["exclude"])
         assert prep["target"][i] == s["i_node"] and prep["domain"][i] == s["domain_id"]
         assert prep["overlap"][i] == s["overlap_label"]
+
+
+def test_dr_dataset_variant_only_adds_ob_label():
+    """DualDomainSeqDatasetDR (dataset_seq.py:443-591) builds the same sample plus the row's ob_label."""
+    from amid_b200.pipeline import prepare_rows
+    z = load("dataset_small.npz")
+    L, ll, pad = int(z["seq_len"]), int(z["long_length"]), int(z["pad_id"])
+    rows = _rows(z)
+    for i, (u, s1, s2, dom) in enumerate(rows):
+        s = O.build_sample(s1, s2, dom, L, ll, pad)
+        assert s["i_node"] == z["dr_i_node"][i] and s["seq_d1"] == z["dr_seq_d1"][i].tolist()
+        assert s["seq_d2"] == z["dr_seq_d2"][i].tolist() and s["overlap_label"] == z["dr_overlap_label"][i]
+    assert np.array_equal(z["dr_ob_label"].astype(np.int64), z["in_ob_label"])
+    prep = prepare_rows([r[0] for r in rows], [r[1] for r in rows], [r[2] for r in rows], [r[3] for r in rows],
+                        z["in_ob_label"].tolist())
+    assert np.array_equal(prep["ob_label"], z["in_ob_label"])
