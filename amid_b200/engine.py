@@ -241,16 +241,28 @@ class Trainer:
 
     # ------------------------------------------------------------------ evaluation forward
     @torch.no_grad()
-    def scores(self, batch: Dict[str, torch.Tensor]) -> torch.Tensor:
-        """Eval-mode probabilities [n_heads, 2, B, C] for a batch (model.eval() semantics)."""
+    def scores(self, batch: Dict[str, torch.Tensor], local: bool = False) -> torch.Tensor:
+        """Eval-mode probabilities [n_heads, 2, B, C] for a batch (model.eval() semantics).  By default the batch is
+        this rank's slice of a global batch (the multi-interest module couples the whole batch).  ``local=True`` scores a
+        WHOLE batch on this rank alone -- how evaluation shards work across ranks (every rank takes different whole
+        batches); it needs the replicated table."""
+        dist = self.dist
+        if local and self.world > 1:
+            if self.sharded is not None:
+                raise _abi.AmidError("local scoring needs the replicated table; with table_sync='sharded' every rank "
+                                     "has to take part in the lookup")
+            dist = None
         probs, _ = hotpath.forward(self.P, self.cfg, batch["i_node"], batch["neg_samples"], batch["seq_d1"],
-                                   batch["seq_d2"], train=False, seed=0, dist=self.dist, need_ctx=False)
+                                   batch["seq_d2"], train=False, seed=0, dist=dist, need_ctx=False)
         return probs
 
     # ------------------------------------------------------------------ full-catalogue evaluation (config 5)
     def catalogue(self, pool_d1: torch.Tensor, pool_d2: torch.Tensor):
         """Item halves of the scorer for both domain pools; pending lazy-Adam rows are flushed first."""
         from . import evaluate
+        if self.sharded is not None:
+            raise _abi.AmidError("full-catalogue evaluation reads the replicated table; with table_sync='sharded' rebuild "
+                                 "one with full_table() and evaluate through a replicated-table Trainer")
         self.flush()
         return evaluate.Catalogue(self.P, self.cfg, pool_d1, pool_d2)
 

@@ -217,7 +217,8 @@ def test(trainer, loader, overlap: bool = False):
     reference's order -- lists (d1, d2) when ``overlap`` is false (train_sr.py:114-118), otherwise
     (d1_ov, d1_no, d2_ov, d2_no, d1, d2) (:119-128).  ``loader`` yields the reference's collated batches
     (dataset_seq.collate_fn_enhance); the last partial batch is expected to be dropped by the loader as in
-    train_sr.py:455."""
+    train_sr.py:455.  Under data parallelism each rank evaluates the whole batches of ITS loader on its own replica and
+    gets the metrics of those batches (shard the eval set across ranks and combine the rank lists if needed)."""
     from . import hotpath
     was_training = trainer.model.training
     trainer.model.eval()
@@ -225,9 +226,9 @@ def test(trainer, loader, overlap: bool = False):
     p1s, p2s, doms, ovs, losses = [], [], [], [], []
     for host in loader:
         b = trainer.to_device(host)
-        probs = trainer.scores(b)
+        probs = trainer.scores(b, local=True)
         B = probs.shape[2]
-        l, _ = hotpath.loss_fwd_bwd(probs[:1].contiguous(), b["label"], b["domain_id"], None, 0, 0.0, B * trainer.world)
+        l, _ = hotpath.loss_fwd_bwd(probs[:1].contiguous(), b["label"], b["domain_id"], None, 0, 0.0, B)
         losses.append(l[:1])
         p1s.append(probs[0, 0]); p2s.append(probs[0, 1]); doms.append(b["domain_id"])
         if overlap:
