@@ -67,3 +67,32 @@ def test_dr_dataset_variant_only_adds_ob_label():
     prep = prepare_rows([r[0] for r in rows], [r[1] for r in rows], [r[2] for r in rows], [r[3] for r in rows],
                         z["in_ob_label"].tolist())
     assert np.array_equal(prep["ob_label"], z["in_ob_label"])
+
+
+def test_prepare_csv_reads_the_reference_layout(tmp_path):
+    """The reference's CSV columns (dataset_seq.py:140-146, DR variant :446-453): JSON-encoded histories."""
+    import json
+    import pandas as pd
+    from amid_b200.pipeline import prepare_csv, prepare_rows
+    rows = [(7, [1, 2, 3], [50], 0, 1), (8, [], [51, 52], 1, 0), (9, [3, 3, 4], [], 0, 1)]
+    p = tmp_path / "toy.csv"
+    pd.DataFrame({"user_id": [r[0] for r in rows], "seq_d1": [json.dumps(r[1]) for r in rows],
+                  "seq_d2": [json.dumps(r[2]) for r in rows], "domain_id": [r[3] for r in rows],
+                  "ob_label": [r[4] for r in rows]}).to_csv(p, index=False)
+    a = prepare_csv(str(p))
+    b = prepare_rows([r[0] for r in rows], [r[1] for r in rows], [r[2] for r in rows], [r[3] for r in rows], [r[4] for r in rows])
+    assert set(a) == set(b)
+    for k in a:
+        assert np.array_equal(a[k], b[k]), k
+    assert a["target"].tolist() == [3, 52, 4]
+    assert a["hist_d1_vals"].tolist() == [1, 2] + [] + [3, 3]          # row 2: target 4 removed, earlier 3s stay
+    assert a["overlap"].tolist() == [1, 0, 0]
+
+
+def test_device_dataset_refuses_cpu():
+    import pytest
+    from amid_b200 import _abi
+    from amid_b200.pipeline import DeviceDataset, prepare_rows
+    prep = prepare_rows([1], [[1, 2]], [[5]], [0])
+    with pytest.raises(_abi.AmidError):
+        DeviceDataset(prep, 4, 2, 0, device="cpu")
