@@ -94,3 +94,24 @@ def test_dropin_module_importable_as_model_seq():
     finally:
         sys.path.pop(0)
         sys.modules.pop("model_seq", None)
+
+
+def test_bench_and_entry_points_compile_and_parse(monkeypatch):
+    """bench.py / __graft_entry__.py are driver contracts: they must at least compile and parse their flags on a
+    machine without a GPU (a module-level SyntaxError would only surface at round end otherwise)."""
+    import importlib
+    import py_compile
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for f in ("bench.py", "__graft_entry__.py", "tests/dp_check.py", "tests/eager_gpu_baseline.py"):
+        py_compile.compile(os.path.join(root, f), doraise=True)
+    sys.path.insert(0, root)
+    bench = importlib.import_module("bench")
+    monkeypatch.setattr(sys, "argv", ["bench.py", "--gpus", "2", "--steps", "5", "--warmup", "3", "--impl", "reference"])
+    a = bench.parse()
+    assert (a.gpus, a.steps, a.warmup, a.impl, a.precision, a.table_sync, a.ids) == (2, 5, 3, "reference", "bf16", "auto", "uniform")
+    w = bench.kernel_work("k_attn_bwd_mma", 1024, 200, 2)
+    assert w["byte"] == 8 * 1024 * 200 * 128 * 4 and w["flop"] > 0
+    rng = np.random.default_rng(0)
+    b = bench.synth_batch(rng, 4, 6, 2, 100)
+    assert b["seq_d1"].shape == (4, 6) and b["label"].shape == (4, 2)
