@@ -657,3 +657,31 @@ def test_flag_matrix_train_grads_vs_oracle(isInC, isItC, isDR):
             assert_close(hp.dense_table_grad(uid, ug, nu, V), v.grad, 1e-3, grad_tol(v.grad), k)
         else:
             assert_close(G[k], v.grad, 1e-3, grad_tol(v.grad), k)
+
+
+def test_inc_itc_dr_training_direction_reference_golden():
+    """The same fixture that pins the oracle (tests/golden/make_inc_train_golden.py): InnerComp + InterComp + DR heads
+    in training direction, executed by the reference -- outputs, phase-1 losses and gradients through the C ABI."""
+    hp = _hp()
+    z = load("inc_train_small.npz")
+    V, ts, B, L = int(z["V"]), float(z["ts"]), 8, 6
+    P = make_params(19, V, D, 2 * L, HID, B, isInC=True, isItC=True, isDR=True)
+    m = build_model(P, V, L, B, isInC=True, isItC=True, ts1=ts, ts2=ts, isDR=True, drop_p=0.0).train()
+    b = batch_from(z)
+    probs, ctx = hp.forward(m.param_dict(), m.cfg, b["i_node"], b["neg_samples"], b["seq_d1"], b["seq_d2"], train=True, seed=3)
+    for i, n in enumerate(("p1", "p2", "ips1", "ips2", "g1", "g2")):
+        assert_close(probs[i // 2, i % 2], z[n], 0, 3e-5, n)
+    losses, dprobs = hp.loss_fwd_bwd(probs, b["label"], b["domain_id"], b["ob_label"], 1, 0.01, B)
+    assert_close(losses[0], z["loss_cls"], 3e-5, 0)
+    assert_close(losses[1], z["loss_dr_e"], 3e-5, 1e-7)
+    G, ids_all, rows_all = hp.backward(m.param_dict(), m.cfg, ctx, dprobs)
+    n_checked = 0
+    for k in z:
+        if k.startswith("grad/"):
+            assert_close(G[k.split("/", 1)[1]], z[k], 1e-3, grad_tol(z[k]), k)
+            n_checked += 1
+    assert n_checked == int(z["n_grad_tensors"])
+    uid, ug, nu = hp.segreduce(ids_all, rows_all, V)
+    want = np.zeros((V, D), dtype=np.float32)
+    want[z["gtab_idx"]] = z["gtab_rows"]
+    assert_close(hp.dense_table_grad(uid, ug, nu, V), want, 1e-3, grad_tol(want), "table")

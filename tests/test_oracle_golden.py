@@ -188,3 +188,34 @@ def test_train_p0_trajectory():
     for k in z:
         if k.startswith("after3/"):
             np.testing.assert_allclose(P[k[7:]].detach().numpy(), z[k], rtol=0, atol=3e-5, err_msg=k)
+
+
+def test_inc_itc_dr_training_direction_golden():
+    """F9 (tests/golden/make_inc_train_golden.py): InnerComp + InterComp + DR heads, dropout off, executed by the
+    reference -- six outputs, both phase-1 losses and the gradients through inc_d*/itc_d*/predict* and the table."""
+    z = load("inc_train_small.npz")
+    V, ts = int(z["V"]), float(z["ts"])
+    P = {k: v.clone().requires_grad_(True)
+         for k, v in make_params(19, V, D, 12, HID, 8, isInC=True, isItC=True, isDR=True).items()}
+    outs = _fwd(P, z, isInC=True, isItC=True, ts1=ts, ts2=ts, isDR=True)
+    for n, t in zip(("p1", "p2", "ips1", "ips2", "g1", "g2"), outs):
+        np.testing.assert_allclose(t.detach().numpy(), z[n], rtol=0, atol=2e-6, err_msg=n)
+    lab, dom = T(z["in_label"]).float(), T(z["in_domain_id"])
+    lc = O.loss_cls(outs[0], outs[1], lab, dom)
+    le = O.loss_dr_e(*outs, lab, dom)
+    np.testing.assert_allclose(lc.detach().numpy(), z["loss_cls"], rtol=2e-5)
+    np.testing.assert_allclose(le.detach().numpy(), z["loss_dr_e"], rtol=2e-5)
+    (lc + 0.01 * le).backward()
+    n_checked = 0
+    for k in z:
+        if k.startswith("grad/"):
+            g = z[k]
+            np.testing.assert_allclose(P[k.split("/", 1)[1]].grad.numpy(), g, rtol=1e-3,
+                                       atol=1e-7 + 1e-4 * np.abs(g).max(), err_msg=k)
+            n_checked += 1
+    assert n_checked == int(z["n_grad_tensors"]) and n_checked >= 20
+    assert np.abs(z["grad/inc_d1.trans_nn.weight"]).max() > 0          # the InnerComp gates were open
+    gt = torch.zeros(V, D)
+    gt[T(z["gtab_idx"])] = T(z["gtab_rows"])
+    got = P["item_emb_layer.emb_item.weight"].grad
+    np.testing.assert_allclose(got.numpy(), gt.numpy(), rtol=1e-3, atol=1e-7 + 1e-4 * float(gt.abs().max()))
