@@ -12,6 +12,7 @@
 #include "encoder_tc.cuh"
 #include "attn_mma.cuh"
 #include "encoder_tc16.cuh"
+#include "x3.cuh"
 
 namespace amid {
 
@@ -1121,3 +1122,5 @@ extern "C" int amid_encoder_bwd_bf16(const amid_encoder_tensors* P, const float*
                                      int64_t workspace_bytes, amid_stream_t stream) {
     return encoder_bwd_impl(P, x0, tmask, B, L, drop, S, enc_out, d_enc, G, dx0, workspace, workspace_bytes, stream, 2);
 }
+
+#include "x3_test.cuh"

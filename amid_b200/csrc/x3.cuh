@@ -1,0 +1,375 @@
+// Split-operand tensor-core arithmetic at fp32-level accuracy (precision = "x3", the parity-grade default).
+//
+// tcgen05 has no fp32 MMA.  An fp32 operand x is therefore carried as a short sum of 16-bit pieces and the
+// product of two operands as the sum of the piece products that matter, accumulated in fp32 in TMEM:
+//
+//   chain GEMMs (token tile x weight):  x = s^-1 (h0 + h1), h = FP16, s = a power of two chosen per ROW of the
+//     token tile (row max -> [2^14, 2^15)) and per weight matrix.  22 mantissa bits per operand; the products
+//     h0 w0 + h1 w0 + h0 w1 leave a relative error of 2^-22 (the dropped h1 w1 term), i.e. fp32 level.  Three
+//     kind::f16 MMAs at the full 16-bit rate cost half of a 3xTF32 split and the pieces are half the bytes, which is
+//     what lets TWO CTAs share an SM: the token-tile pieces live in TENSOR MEMORY (64 columns each, written by the
+//     epilogue threads with tcgen05.st and read by tcgen05.mma as the A operand), the weight pieces arrive in
+//     shared memory as ONE bulk copy (cp.async.bulk, completion on an mbarrier) of an image that the weight prep
+//     kernel stored pre-swizzled in the canonical K-major SWIZZLE_128B layout.
+//   weight gradients (tokens are the contraction index, so no per-row scale can be factored out):
+//     x = b0 + b1 + b2, b = BF16 (full fp32 range, 24 bits), six products b0b0 + b0b1 + b1b0 + b0b2 + b1b1 + b2b0.
+//
+// TMEM map of a chain CTA (256 columns): [0,128) fp32 accumulator, [128,192) A piece 0, [192,256) A piece 1
+// (row = lane, two consecutive k per 32-bit column).
+#pragma once
+#include <cuda_fp16.h>
+
+#include "encoder_tc16.cuh"
+
+namespace amid {
+namespace x3 {
+using namespace tc;
+using tcenc::align1k;
+using tcenc::Epi;
+using tcenc::rows_valid;
+using tcenc::warp_colsum32;
+using tcenc::warp_load32;
+using tcenc::warp_load32_cg;
+using tcenc::warp_store32;
+using tcenc::WSTAGE_FLOATS;
+
+constexpr int PIECE_BYTES = TILE16_BYTES;            // one 16-bit piece of a [128][128] tile: 32 KB
+constexpr int WIMG_BYTES = 2 * PIECE_BYTES;          // both pieces of a weight: 64 KB, contiguous in global memory
+constexpr uint32_t ACC_COL = 0, A0_COL = 128, A1_COL = 192;
+constexpr int CHAIN_TMEM_COLS = 256;
+constexpr size_t CHAINX_SMEM = (size_t)WIMG_BYTES + 8 * WSTAGE_FLOATS * 4 + 1024;   // 97 KB -> two CTAs per SM
+
+// ---- instruction descriptor: kind::f16 with FP16 operands, fp32 accumulate, M = 128
+__host__ __device__ constexpr uint32_t idesc_f16(int n, bool a_mn, bool b_mn) {
+    return (1u << 4) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) | ((uint32_t)(n >> 3) << 17) | ((128u >> 4) << 24);
+}
+// D[tmem] (+)= A[tmem] * B[smem desc]
+__device__ __forceinline__ void mma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+    asm volatile(
+        "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n}"
+        ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
+}
+__device__ __forceinline__ void mma_f16_ss(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+    asm volatile(
+        "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
+}
+// registers -> TMEM: this warp's 32 lanes x 16 consecutive columns
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+          "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]) : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// ---- bulk asynchronous copy global -> shared (TMA engine, 1-D), completion counted in bytes on an mbarrier
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+// ---- the FP16 pair split
+// scale = 2^k with amax * scale in [2^14, 2^15) (clamped so that scale and 1/scale are both normal floats)
+__device__ __forceinline__ void pow2_scale(float amax, float& scale, float& inv) {
+    const int e = (int)((__float_as_uint(amax) >> 23) & 0xFFu);
+    int sb = e == 0 ? 127 : 268 - e;
+    sb = min(max(sb, 1), 253);
+    scale = __uint_as_float((uint32_t)sb << 23);
+    inv = __uint_as_float((uint32_t)(254 - sb) << 23);
+}
+// (a, b) already scaled -> packed FP16 pairs: p0 = {h0(a), h0(b)}, p1 = {h1(a), h1(b)}; low half = a
+__device__ __forceinline__ void split_f16x2(float a, float b, uint32_t& p0, uint32_t& p1) {
+    const __half2 h = __floats2half2_rn(a, b);
+    const float2 f = __half22float2(h);
+    const __half2 r = __floats2half2_rn(a - f.x, b - f.y);
+    p0 = *reinterpret_cast<const uint32_t*>(&h);
+    p1 = *reinterpret_cast<const uint32_t*>(&r);
+}
+__device__ __forceinline__ float absmax32(const float (&v)[32], float m) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) m = fmaxf(m, fabsf(v[i]));
+    return m;
+}
+// 32 consecutive columns [c0, c0+32) of this thread's row (already multiplied by the row scale) -> both A pieces in TMEM
+__device__ __forceinline__ void put_a32(uint32_t tmem_lane, int c0, const float (&v)[32], float scale) {
+    uint32_t p0[16], p1[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) split_f16x2(v[2 * i] * scale, v[2 * i + 1] * scale, p0[i], p1[i]);
+    tmem_st16(tmem_lane + A0_COL + (c0 >> 1), p0);
+    tmem_st16(tmem_lane + A1_COL + (c0 >> 1), p1);
+}
+
+struct SharedX {
+    uint64_t bar_mma;           // tcgen05.commit of the current GEMM
+    uint64_t bar_w;             // bulk copy of the current weight image
+    uint32_t tmem;
+    float xch[3][2][128];       // [slot][half][row]
+    float lnacc[8][2][64];      // [warp][dw|db][col in half]
+};
+__device__ __forceinline__ void setup(SharedX& sh, int tmem_cols) {
+    if ((threadIdx.x >> 5) == 0) tmem_alloc(&sh.tmem, tmem_cols);
+    if (threadIdx.x == 0) { mbar_init(&sh.bar_mma, 1); mbar_init(&sh.bar_w, 1); fence_barrier_init(); }
+}
+__device__ __forceinline__ void teardown(SharedX& sh, int tmem_cols) {
+    fence_before();
+    __syncthreads();
+    if ((threadIdx.x >> 5) == 0) tmem_dealloc(sh.tmem, tmem_cols);
+}
+// combine a per-thread partial over the two threads that share a row
+__device__ __forceinline__ float row_sum(SharedX& sh, const Epi& e, int slot, float partial) {
+    sh.xch[slot][e.cb >> 6][e.row] = partial;
+    __syncthreads();
+    return sh.xch[slot][0][e.row] + sh.xch[slot][1][e.row];
+}
+__device__ __forceinline__ float row_max(SharedX& sh, const Epi& e, int slot, float partial) {
+    sh.xch[slot][e.cb >> 6][e.row] = partial;
+    __syncthreads();
+    return fmaxf(sh.xch[slot][0][e.row], sh.xch[slot][1][e.row]);
+}
+__device__ __forceinline__ void flush_ln_partials(SharedX& sh, float* __restrict__ part_tile) {
+    __syncthreads();
+    const int t = threadIdx.x, arr = t >> 7, c = t & 127, hb = c >> 6, cc = c & 63;
+    float s = 0.f;
+#pragma unroll
+    for (int rg = 0; rg < 4; ++rg) s += sh.lnacc[hb * 4 + rg][arr][cc];
+    part_tile[arr * D + c] = s;
+}
+// one thread: fetch the 64 KB image of a weight (both pieces) into the W buffer
+__device__ __forceinline__ void load_w_bulk(SharedX& sh, uint8_t* Wbuf, const uint8_t* __restrict__ img) {
+    if (threadIdx.x == 0) {
+        mbar_expect_tx(&sh.bar_w, WIMG_BYTES);
+        bulk_g2s(Wbuf, img, PIECE_BYTES, &sh.bar_w);
+        bulk_g2s(Wbuf + PIECE_BYTES, img + PIECE_BYTES, PIECE_BYTES, &sh.bar_w);
+    }
+}
+// acc[ACC_COL + acc_off] (+)= A(tmem pieces) * W^T : 8 k-steps x {a0 w0, a1 w0, a0 w1}
+__device__ __forceinline__ void issue_gemm_x3(uint32_t tmem, uint32_t acc_off, uint32_t w_addr, bool accumulate) {
+    constexpr uint32_t id = idesc_f16(128, false, false);
+#pragma unroll
+    for (int ks = 0; ks < 8; ++ks) {
+        const uint64_t w0 = desc16_k(w_addr, ks >> 2, ks & 3), w1 = desc16_k(w_addr + PIECE_BYTES, ks >> 2, ks & 3);
+        const uint32_t a0 = tmem + A0_COL + 8 * ks, a1 = tmem + A1_COL + 8 * ks;
+        mma_f16_ts(tmem + ACC_COL + acc_off, a0, w0, id, (accumulate || ks) ? 1u : 0u);
+        mma_f16_ts(tmem + ACC_COL + acc_off, a1, w0, id, 1u);
+        mma_f16_ts(tmem + ACC_COL + acc_off, a0, w1, id, 1u);
+    }
+}
+// every thread has stored its share of the A pieces: publish them, run the GEMM against the weight image whose bulk
+// copy is in flight, wait for the accumulator.  The weight buffer is free again on return.
+__device__ __forceinline__ void run_gemm_x3(SharedX& sh, uint32_t acc_off, const uint8_t* Wbuf, bool accumulate,
+                                            uint32_t& ph_mma, uint32_t& ph_w) {
+    tmem_st_wait();
+    fence_before();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        mbar_wait(&sh.bar_w, ph_w);
+        fence_after();
+        issue_gemm_x3(sh.tmem, acc_off, smem_u32(Wbuf), accumulate);
+        mma_commit(&sh.bar_mma);
+    }
+    ph_w ^= 1;
+    mbar_wait(&sh.bar_mma, ph_mma);
+    ph_mma ^= 1;
+    fence_after();
+}
+
+// ---- weight preparation: fp32 [128][128] (optionally transposed) -> per-matrix power-of-two scale + FP16 pair image,
+// pre-swizzled (canonical K-major SWIZZLE_128B, piece 0 then piece 1).  One CTA per matrix.
+struct PrepJobsX {
+    const float* src[12];
+};
+__global__ void __launch_bounds__(256)
+k_prep_wx3(PrepJobsX jobs, uint8_t* __restrict__ img /*[n][64 KB]*/, float* __restrict__ inv_scale /*[n]*/, int transpose) {
+    __shared__ float red[8];
+    __shared__ float s_scale;
+    const float* __restrict__ s = jobs.src[blockIdx.x];
+    uint8_t* out = img + (size_t)blockIdx.x * WIMG_BYTES;
+    float m = 0.f;
+    for (int i = threadIdx.x; i < D * D / 4; i += 256) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(s) + i);
+        m = fmaxf(fmaxf(m, fmaxf(fabsf(v.x), fabsf(v.y))), fmaxf(fabsf(v.z), fabsf(v.w)));
+    }
+    m = warp_max(m);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float r = red[0];
+        for (int w = 1; w < 8; ++w) r = fmaxf(r, red[w]);
+        float sc, inv;
+        pow2_scale(r, sc, inv);
+        s_scale = sc;
+        inv_scale[blockIdx.x] = inv;
+    }
+    __syncthreads();
+    const float sc = s_scale;
+    // output element (n, k) = W[n][k] (or W[k][n] when transposing); 16-byte unit = 8 consecutive k
+    for (int idx = threadIdx.x; idx < 128 * 16; idx += 256) {
+        const int n = transpose ? (idx & 127) : (idx >> 4), u = transpose ? (idx >> 7) : (idx & 15);
+        uint32_t p0[4], p1[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int k = u * 8 + 2 * j;
+            const float a = transpose ? s[(size_t)k * D + n] : s[(size_t)n * D + k];
+            const float b = transpose ? s[(size_t)(k + 1) * D + n] : s[(size_t)n * D + k + 1];
+            split_f16x2(a * sc, b * sc, p0[j], p1[j]);
+        }
+        const uint32_t off = tile16_off8(n, u);
+        *reinterpret_cast<uint4*>(out + off) = make_uint4(p0[0], p0[1], p0[2], p0[3]);
+        *reinterpret_cast<uint4*>(out + PIECE_BYTES + off) = make_uint4(p1[0], p1[1], p1[2], p1[3]);
+    }
+}
+
+// ================================================================================================
+// weight gradients with BF16 triples: dW[n][k] = sum_m dY[m][n] X[m][k] through MN-major views of the row-major token
+// tiles; 64-token sub-tiles, double buffered (the MMAs of one sub-tile run while the next one is loaded and split).
+// ================================================================================================
+constexpr int SUB_ROWS = 64;
+constexpr int SUBP_BYTES = SUB_ROWS * 128 * 2;       // one BF16 piece of a [64][128] sub-tile: 16 KB (2 chunks of 8 KB)
+constexpr int SUB_CHUNK = SUB_ROWS * 128;            // bytes between the two 64-feature chunks
+constexpr int WG_BUF_BYTES = 6 * SUBP_BYTES;         // dY pieces 0..2, X pieces 0..2
+constexpr int ONESX_BYTES = 16 * 128;                // [16 rows][64 tokens] BF16 ones, K-major
+constexpr size_t WGRADX_SMEM = 2 * (size_t)WG_BUF_BYTES + ONESX_BYTES + 1024;    // 195 KB
+__device__ __forceinline__ uint32_t sub_off8(int r, int u) {
+    return (uint32_t)((u >> 3) * SUB_CHUNK + (r >> 3) * 1024 + (r & 7) * 128 + (((u & 7) ^ (r & 7)) << 4));
+}
+__device__ __forceinline__ uint64_t desc_sub_mn(uint32_t tile_addr, int kstep) {
+    return make_desc(tile_addr + kstep * 2048, SUB_CHUNK, 1024);
+}
+// x = b0 + b1 + b2 (each rounded to nearest BF16; the residuals are exact in fp32)
+__device__ __forceinline__ void split_bf16x3(float a, float b, uint32_t& p0, uint32_t& p1, uint32_t& p2) {
+    p0 = pack_bf16(a, b);
+    const float ra = a - __uint_as_float(p0 << 16), rb = b - __uint_as_float(p0 & 0xFFFF0000u);
+    p1 = pack_bf16(ra, rb);
+    const float sa = ra - __uint_as_float(p1 << 16), sb = rb - __uint_as_float(p1 & 0xFFFF0000u);
+    p2 = pack_bf16(sa, sb);
+}
+// rows [row0, row0+64) of g[M,128] -> three BF16 piece sub-tiles at dst, dst + 16 KB, dst + 32 KB
+__device__ __forceinline__ void fill_sub3(uint8_t* dst, const float4 (&v)[8]) {
+    const int c4 = threadIdx.x & 31, rb = threadIdx.x >> 5;
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+        const int r = it * 8 + rb;
+        uint32_t a0, a1, a2, b0, b1, b2;
+        split_bf16x3(v[it].x, v[it].y, a0, a1, a2);
+        split_bf16x3(v[it].z, v[it].w, b0, b1, b2);
+        const uint32_t off = sub_off8(r, c4 >> 1) + (c4 & 1) * 8;
+        *reinterpret_cast<uint2*>(dst + off) = make_uint2(a0, b0);
+        *reinterpret_cast<uint2*>(dst + SUBP_BYTES + off) = make_uint2(a1, b1);
+        *reinterpret_cast<uint2*>(dst + 2 * SUBP_BYTES + off) = make_uint2(a2, b2);
+    }
+}
+__device__ __forceinline__ void load_sub(float4 (&v)[8], const float* __restrict__ g, int row0, int M) {
+    const int c4 = threadIdx.x & 31, rb = threadIdx.x >> 5;
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+        const int r = row0 + it * 8 + rb;
+        v[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (r < M) v[it] = __ldg(reinterpret_cast<const float4*>(g + (size_t)r * D) + c4);
+    }
+}
+struct WgradJobsX {
+    const float* dY[6];
+    const float* X[6];
+};
+__global__ void __launch_bounds__(256, 1)
+k_wgrad_x3(WgradJobsX jobs, int M, float* __restrict__ wpart /*[6][S][128*128]*/, float* __restrict__ bpart /*[6][S][128]*/) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ uint64_t bars[2];
+    __shared__ uint32_t tmem_s;
+    uint8_t* buf0 = align1k(smem_raw);
+    uint8_t* Ones = buf0 + 2 * WG_BUF_BYTES;
+    const float* __restrict__ dY = jobs.dY[blockIdx.y];
+    const float* __restrict__ X = jobs.X[blockIdx.y];
+    const int S = gridDim.x;
+    if ((threadIdx.x >> 5) == 0) tmem_alloc(&tmem_s, 256);
+    if (threadIdx.x == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); fence_barrier_init(); }
+    for (int i = threadIdx.x; i < ONESX_BYTES / 4; i += 256) reinterpret_cast<uint32_t*>(Ones)[i] = 0x3F803F80u;
+    fence_async_smem();
+    fence_before();
+    __syncthreads();
+    fence_after();
+    const uint32_t tmem = tmem_s;
+    const int subs = (M + SUB_ROWS - 1) / SUB_ROWS;
+    uint32_t phase[2] = {0u, 0u};
+    constexpr uint32_t id_w = idesc_bf16(128, true, true);
+    constexpr uint32_t id_b = idesc_bf16(16, true, false);
+    int it = 0;
+    // sub-tiles are dealt in pairs so that a CTA streams 128 consecutive tokens at a time
+    for (int t = blockIdx.x; 2 * t < subs; t += S) {
+        for (int half = 0; half < 2; ++half) {
+            const int sidx = 2 * t + half;
+            if (sidx >= subs) break;
+            const int b = it & 1;
+            float4 vy[8], vx[8];
+            load_sub(vy, dY, sidx * SUB_ROWS, M);
+            load_sub(vx, X, sidx * SUB_ROWS, M);
+            if (it >= 2) { mbar_wait(&bars[b], phase[b]); phase[b] ^= 1; }      // MMAs that read this buffer are done
+            uint8_t* buf = buf0 + b * WG_BUF_BYTES;
+            fill_sub3(buf, vy);
+            fill_sub3(buf + 3 * SUBP_BYTES, vx);
+            fence_async_smem();
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                fence_after();
+                const uint32_t a = smem_u32(buf), x = a + 3 * SUBP_BYTES, o = smem_u32(Ones);
+#pragma unroll
+                for (int ks = 0; ks < SUB_ROWS / 16; ++ks) {
+                    const uint32_t acc = (it || ks) ? 1u : 0u;
+                    const uint64_t a0 = desc_sub_mn(a, ks), a1 = desc_sub_mn(a + SUBP_BYTES, ks), a2 = desc_sub_mn(a + 2 * SUBP_BYTES, ks);
+                    const uint64_t x0 = desc_sub_mn(x, ks), x1 = desc_sub_mn(x + SUBP_BYTES, ks), x2 = desc_sub_mn(x + 2 * SUBP_BYTES, ks);
+                    const uint64_t on = make_desc(o + ks * 32, 16, 1024);
+                    mma_bf16(tmem, a0, x0, id_w, acc);
+                    mma_bf16(tmem, a0, x1, id_w, 1u);
+                    mma_bf16(tmem, a1, x0, id_w, 1u);
+                    mma_bf16(tmem, a0, x2, id_w, 1u);
+                    mma_bf16(tmem, a1, x1, id_w, 1u);
+                    mma_bf16(tmem, a2, x0, id_w, 1u);
+                    mma_bf16(tmem + 128, a0, on, id_b, acc);
+                    mma_bf16(tmem + 128, a1, on, id_b, 1u);
+                    mma_bf16(tmem + 128, a2, on, id_b, 1u);
+                }
+                mma_commit(&bars[b]);
+            }
+            ++it;
+        }
+    }
+    // drain: the last one or two commits
+    if (it >= 2) { const int b = it & 1; mbar_wait(&bars[b], phase[b]); phase[b] ^= 1; }
+    if (it >= 1) { const int b = (it - 1) & 1; mbar_wait(&bars[b], phase[b]); phase[b] ^= 1; }
+    fence_after();
+    Epi e;
+    float* wp = wpart + ((size_t)blockIdx.y * S + blockIdx.x) * D * D;
+#pragma unroll 1
+    for (int half = 0; half < 2; ++half) {
+        float a[32];
+        const int c0 = e.cb + half * 32;
+        if (it) {
+            tmem_ld32(tmem + e.lane_addr + c0, a);
+        } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) a[i] = 0.f;
+        }
+#pragma unroll
+        for (int i = 0; i < 32; i += 4)
+            *reinterpret_cast<float4*>(wp + (size_t)e.row * D + c0 + i) = make_float4(a[i], a[i + 1], a[i + 2], a[i + 3]);
+    }
+    if (e.cb == 0) {
+        float a[32];
+        if (it) {
+            tmem_ld32(tmem + e.lane_addr + 128, a);
+        } else {
+            a[0] = 0.f;
+        }
+        bpart[((size_t)blockIdx.y * S + blockIdx.x) * D + e.row] = a[0];
+    }
+    fence_before();
+    __syncthreads();
+    if ((threadIdx.x >> 5) == 0) tmem_dealloc(tmem, 256);
+}
+
+}  // namespace x3
+}  // namespace amid

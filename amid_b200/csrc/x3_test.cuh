@@ -1,0 +1,83 @@
+// Bring-up / unit-test entry points of the split-operand ("x3") pipeline (x3.cuh); included by encoder.cu.
+#pragma once
+#include "x3.cuh"
+
+// ---- split-operand ("x3") bring-up: y = x w^T + b with FP16 pair pieces, the token tile in TENSOR MEMORY (tcgen05.st +
+// A-from-TMEM MMA), the weight image fetched with one bulk copy; and the BF16-triple weight-gradient kernel.
+
+namespace amid {
+__global__ void __launch_bounds__(256, 2)
+k_x3_linear(const float* __restrict__ x, const uint8_t* __restrict__ wimg, const float* __restrict__ winv,
+            const float* __restrict__ b, int M, float* __restrict__ y) {
+    using namespace x3;
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ SharedX sh;
+    uint8_t* Wb = align1k(smem_raw);
+    float* stage = reinterpret_cast<float*>(Wb + WIMG_BYTES) + (threadIdx.x >> 5) * WSTAGE_FLOATS;
+    const int row0 = blockIdx.x * 128;
+    setup(sh, CHAIN_TMEM_COLS);
+    fence_before();
+    __syncthreads();
+    fence_after();
+    load_w_bulk(sh, Wb, wimg);
+    Epi e;
+    const int rv = rows_valid(row0, e, M);
+    const size_t wbase = (size_t)(row0 + e.wrow0) * D;
+    float v[2][32];
+    float am = 0.f;
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        warp_load32(stage, e.lane, x + wbase + e.cb + half * 32, rv, v[half]);
+        am = absmax32(v[half], am);
+    }
+    float sc, inv;
+    pow2_scale(row_max(sh, e, 2, am), sc, inv);
+    const uint32_t tl = sh.tmem + e.lane_addr;
+    put_a32(tl, e.cb, v[0], sc);
+    put_a32(tl, e.cb + 32, v[1], sc);
+    uint32_t ph_mma = 0, ph_w = 0;
+    run_gemm_x3(sh, 0, Wb, false, ph_mma, ph_w);
+    const float f = inv * __ldg(winv);
+#pragma unroll 1
+    for (int half = 0; half < 2; ++half) {
+        float a[32];
+        const int c0 = e.cb + half * 32;
+        tmem_ld32(tl + ACC_COL + c0, a);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) a[i] = fmaf(a[i], f, __ldg(b + c0 + i));
+        warp_store32(stage, e.lane, a, y + wbase + c0, rv);
+    }
+    teardown(sh, CHAIN_TMEM_COLS);
+}
+}  // namespace amid
+
+// scratch: >= 64 KB + 4 B device buffer for the weight image and its inverse scale
+extern "C" int amid_x3_linear_test(const float* x, const float* w, const float* b, int32_t M, float* y, void* scratch,
+                                   amid_stream_t s_) {
+    AMID_REQUIRE(x && w && b && y && scratch && M > 0, "x3_linear_test: bad argument");
+    cudaError_t e = cudaFuncSetAttribute((const void*)k_x3_linear, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)x3::CHAINX_SMEM);
+    if (e != cudaSuccess) return set_error(-3, "x3_linear_test: smem attribute: %s", cudaGetErrorString(e));
+    x3::PrepJobsX pj;
+    pj.src[0] = w;
+    uint8_t* img = (uint8_t*)scratch;
+    float* inv = (float*)(img + x3::WIMG_BYTES);
+    AMID_K("k_prep_wx3", s_);
+    x3::k_prep_wx3<<<1, 256, 0, (cudaStream_t)s_>>>(pj, img, inv, 0);
+    AMID_LAUNCH_CHECK("k_prep_wx3");
+    AMID_K("k_x3_linear", s_);
+    k_x3_linear<<<(M + 127) / 128, 256, x3::CHAINX_SMEM, (cudaStream_t)s_>>>(x, img, inv, b, M, y);
+    AMID_LAUNCH_CHECK("k_x3_linear");
+    return 0;
+}
+extern "C" int amid_x3_wgrad_test(const float* dy, const float* x, int32_t M, float* wpart, float* bpart, int32_t n_ctas,
+                                  amid_stream_t s_) {
+    AMID_REQUIRE(dy && x && wpart && bpart && M > 0 && n_ctas > 0, "x3_wgrad_test: bad argument");
+    cudaError_t e = cudaFuncSetAttribute((const void*)x3::k_wgrad_x3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)x3::WGRADX_SMEM);
+    if (e != cudaSuccess) return set_error(-3, "x3_wgrad_test: smem attribute: %s", cudaGetErrorString(e));
+    x3::WgradJobsX j;
+    for (int i = 0; i < 6; ++i) { j.dY[i] = dy; j.X[i] = x; }
+    AMID_K("k_wgrad_x3", s_);
+    x3::k_wgrad_x3<<<dim3(n_ctas, 1), 256, x3::WGRADX_SMEM, (cudaStream_t)s_>>>(j, M, wpart, bpart);
+    AMID_LAUNCH_CHECK("k_wgrad_x3");
+    return 0;
+}

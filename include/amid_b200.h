@@ -306,6 +306,14 @@ int amid_tc_linear_test(const float* x, const float* w, const float* b, int32_t 
 int amid_tc_linear16_test(const float* x, const float* w, const float* b, int32_t M, float* y, amid_stream_t stream);
 int amid_tc_wgrad16_test(const float* dy, const float* x, int32_t M, float* part, int32_t n_ctas, amid_stream_t stream);
 
+/* Split-operand ("x3") bring-up: the same linear layer at fp32-level accuracy from FP16 pair pieces (token tile in
+ * tensor memory, pre-swizzled weight image fetched by one bulk copy; scratch >= 65,540 bytes), and the weight-gradient
+ * kernel with BF16 triples: sum over cta of wpart[cta] = dy^T x, sum over cta of bpart[cta] = column sums of dy. */
+int amid_x3_linear_test(const float* x, const float* w, const float* b, int32_t M, float* y, void* scratch,
+                        amid_stream_t stream);
+int amid_x3_wgrad_test(const float* dy, const float* x, int32_t M, float* wpart, float* bpart, int32_t n_ctas,
+                       amid_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

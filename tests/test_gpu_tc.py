@@ -167,3 +167,45 @@ def test_train_dropout_tc_vs_oracle(precision):
     for k, v in Po.items():
         if k != "item_emb_layer.emb_item.weight":
             assert_grad_tc(G[k], v.grad, k, precision)
+
+
+# ------------------------------------------------------------------ split-operand ("x3") primitives: fp32-level accuracy
+@pytest.mark.parametrize("M,scale", [(128, 1.0), (1, 1.0), (200, 1e-6), (1000, 300.0), (4096 + 77, 1.0)])
+def test_x3_linear_fp16_pairs_tmem_operand(M, scale):
+    from amid_b200 import hotpath as hp
+    from amid_b200._abi import call
+    g = torch.Generator().manual_seed(M)
+    x = torch.randn(M, D, generator=g) * scale
+    x[:, 5] *= 1e-4                      # columns far below the row maximum keep their relative accuracy
+    if M > 3:
+        x[3] = 0.0                       # an all-zero row
+    x = x.cuda()
+    w = (torch.randn(D, D, generator=g) / 11.3).cuda()
+    b = (torch.randn(D, generator=g) * scale).cuda()
+    y = torch.full((M, D), float("nan"), device="cuda")
+    scratch = torch.empty(65536 + 64, dtype=torch.uint8, device="cuda")
+    call("amid_x3_linear_test", hp._ptr(x), hp._ptr(w), hp._ptr(b), M, hp._ptr(y), hp._ptr(scratch), hp._stream())
+    torch.cuda.synchronize()
+    ref = x.double() @ w.double().T + b.double()
+    assert torch.isfinite(y).all()
+    err = (y.double() - ref).abs().max().item()
+    fp32 = ((x @ w.T + b).double() - ref).abs().max().item()     # what an fp32 GEMM leaves
+    assert err < 2e-6 * ref.abs().max().item(), (err, fp32)
+
+
+@pytest.mark.parametrize("M,ctas", [(64, 1), (128, 1), (130, 2), (1000, 3), (5000, 24)])
+def test_x3_wgrad_bf16_triples(M, ctas):
+    from amid_b200 import hotpath as hp
+    from amid_b200._abi import call
+    g = torch.Generator().manual_seed(M)
+    dy = (torch.randn(M, D, generator=g) * torch.logspace(-6, 2, M).view(M, 1)).cuda()     # rows over 8 decades
+    x = torch.randn(M, D, generator=g).cuda()
+    wpart = torch.full((ctas, D, D), float("nan"), device="cuda")
+    bpart = torch.full((ctas, D), float("nan"), device="cuda")
+    call("amid_x3_wgrad_test", hp._ptr(dy), hp._ptr(x), M, hp._ptr(wpart), hp._ptr(bpart), ctas, hp._stream())
+    torch.cuda.synchronize()
+    ref = dy.double().T @ x.double()
+    got = wpart.double().sum(0)
+    assert (got - ref).abs().max().item() < 2e-6 * ref.abs().max().item()
+    refb = dy.double().sum(0)
+    assert (bpart.double().sum(0) - refb).abs().max().item() < 2e-6 * refb.abs().max().item()
