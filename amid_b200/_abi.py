@@ -82,6 +82,10 @@ _SIGS = {
                                         POINTER(EncoderSaved), P, P, c_int64, P]),
     "amid_encoder_bwd_bf16": (c_int32, [POINTER(EncoderTensors), P, P, c_int32, c_int32, POINTER(Dropout),
                                         POINTER(EncoderSaved), P, P, POINTER(EncoderTensors), P, P, c_int64, P]),
+    "amid_encoder_fwd_x3": (c_int32, [POINTER(EncoderTensors), P, P, c_int32, c_int32, POINTER(Dropout),
+                                      POINTER(EncoderSaved), P, P, c_int64, P]),
+    "amid_encoder_bwd_x3": (c_int32, [POINTER(EncoderTensors), P, P, c_int32, c_int32, POINTER(Dropout),
+                                      POINTER(EncoderSaved), P, P, POINTER(EncoderTensors), P, P, c_int64, P]),
     "amid_mim_scores": (c_int32, [P, P, c_int32, c_int32, P, P]),
     "amid_mim_scores_tc": (c_int32, [P, P, c_int32, c_int32, P, P]),
     "amid_mim_gate": (c_int32, [P, P, c_int32, c_float, P, P, P, P, P, P, P]),

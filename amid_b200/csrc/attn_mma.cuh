@@ -35,6 +35,25 @@ __device__ __forceinline__ float ex2(float x) {
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
+// 3xTF32 split (precision "x3"): x = hi + lo with both halves rounded to TF32; products hi*hi + lo*hi + hi*lo
+__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(x));
+    const float r = x - __uint_as_float(hi);
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(r));
+}
+// A fragments of a 16 x 16 block (2 k-steps); lo is used by the 3xTF32 variants only
+struct AFrag {
+    uint32_t hi[2][4], lo[2][4];
+};
+template <bool X3>
+__device__ __forceinline__ void finish_a(AFrag& a) {
+    if (X3) {
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) split_tf32(__uint_as_float(a.hi[ks][i]), a.hi[ks][i], a.lo[ks][i]);
+    }
+}
 // dynamic work queue of a CTA: warps take items in order (callers order items by decreasing cost)
 __device__ __forceinline__ int next_item(int* counter, int lane) {
     int it = 0;
@@ -76,21 +95,50 @@ __device__ __forceinline__ void load_a16_g(uint32_t (&a)[2][4], const float* __r
     }
 }
 // D[16 x 8] = A[16 x 16] * X[n0..n0+8][16]^T   (X rows are the n index; k = feature)
-__device__ __forceinline__ void mma_xt(float (&d)[4], const uint32_t (&a)[2][4], const float* x, int n0, int g, int t) {
+template <bool X3>
+__device__ __forceinline__ void mma_xt(float (&d)[4], const AFrag& a, const float* x, int n0, int g, int t) {
     const float* p = x + (n0 + g) * LDS + t;
-    mma_tf32(d, a[0], fbits(p[0]), fbits(p[4]));
-    mma_tf32(d, a[1], fbits(p[8]), fbits(p[12]));
+    if (X3) {
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) {
+            uint32_t bh0, bl0, bh1, bl1;
+            split_tf32(p[8 * ks], bh0, bl0);
+            split_tf32(p[8 * ks + 4], bh1, bl1);
+            mma_tf32(d, a.lo[ks], bh0, bh1);
+            mma_tf32(d, a.hi[ks], bl0, bl1);
+            mma_tf32(d, a.hi[ks], bh0, bh1);
+        }
+    } else {
+        mma_tf32(d, a.hi[0], fbits(p[0]), fbits(p[4]));
+        mma_tf32(d, a.hi[1], fbits(p[8]), fbits(p[12]));
+    }
 }
 // acc[dt][..] += P[16 x 8 (relabelled)] * X[n0..n0+8][16]   (X rows are the k index, permuted 2t / 2t+1).
 // The output features are permuted too -- n index g of n-tile dt is feature 2g+dt -- so the B operands of both
 // n-tiles come from one 64-bit load per key row and a thread ends up owning the four consecutive features
 // 4t..4t+3 of its rows: {acc[0][0], acc[1][0], acc[0][1], acc[1][1]} (row g) and the [..][2], [..][3] set (row g+8).
+template <bool X3>
 __device__ __forceinline__ void mma_px(float (&acc)[2][4], const float (&p)[4], const float* x, int n0, int g, int t) {
-    const uint32_t a[4] = {fbits(p[0]), fbits(p[2]), fbits(p[1]), fbits(p[3])};
     const float* pa = x + (n0 + 2 * t) * LDS + 2 * g;
     const float2 u = *reinterpret_cast<const float2*>(pa), w = *reinterpret_cast<const float2*>(pa + LDS);
-    mma_tf32(acc[0], a, fbits(u.x), fbits(w.x));
-    mma_tf32(acc[1], a, fbits(u.y), fbits(w.y));
+    if (X3) {
+        uint32_t ah[4], al[4];
+        split_tf32(p[0], ah[0], al[0]); split_tf32(p[2], ah[1], al[1]);
+        split_tf32(p[1], ah[2], al[2]); split_tf32(p[3], ah[3], al[3]);
+        uint32_t uh, ul, wh, wl;
+        split_tf32(u.x, uh, ul); split_tf32(w.x, wh, wl);
+        mma_tf32(acc[0], al, uh, wh);
+        mma_tf32(acc[0], ah, ul, wl);
+        mma_tf32(acc[0], ah, uh, wh);
+        split_tf32(u.y, uh, ul); split_tf32(w.y, wh, wl);
+        mma_tf32(acc[1], al, uh, wh);
+        mma_tf32(acc[1], ah, ul, wl);
+        mma_tf32(acc[1], ah, uh, wh);
+    } else {
+        const uint32_t a[4] = {fbits(p[0]), fbits(p[2]), fbits(p[1]), fbits(p[3])};
+        mma_tf32(acc[0], a, fbits(u.x), fbits(w.x));
+        mma_tf32(acc[1], a, fbits(u.y), fbits(w.y));
+    }
 }
 // features 4t..4t+3 of row g (hi = 0) or g+8 (hi = 1) out of a mma_px accumulator, scaled
 __device__ __forceinline__ float4 px_row(const float (&acc)[2][4], int hi, float sc) {
@@ -133,6 +181,7 @@ __device__ __forceinline__ void keep_rows(const DropCfg& dc, uint32_t site, cons
 // ----------------------------------------------------------------------------------------------
 // forward
 // ----------------------------------------------------------------------------------------------
+template <bool X3>
 __global__ void __launch_bounds__(NW * 32)
 k_attn_fwd_mma(const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v,
                float* __restrict__ o, float* __restrict__ lse, int L, DropCfg dc, uint32_t site) {
@@ -155,8 +204,9 @@ k_attn_fwd_mma(const float* __restrict__ q, const float* __restrict__ k, const f
         if (item >= ntile) break;
         const int rt = ntile - 1 - item;          // heaviest (last) row tile first
         const int r0 = rt * 16;
-        uint32_t aq[2][4];
-        load_a16_g(aq, q + base, r0, L, g, t, LOG2E);          // scores in the log2 domain
+        AFrag aq;
+        load_a16_g(aq.hi, q + base, r0, L, g, t, LOG2E);       // scores in the log2 domain
+        finish_a<X3>(aq);
         float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
         float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
         const int row_a = r0 + g, row_b = r0 + g + 8;
@@ -172,7 +222,7 @@ k_attn_fwd_mma(const float* __restrict__ q, const float* __restrict__ k, const f
                 const int n0 = kb + 8 * nt;
                 if (n0 < kend) {                                  // warp-uniform
                     s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
-                    mma_xt(s[nt], aq, ks, n0, g, t);
+                    mma_xt<X3>(s[nt], aq, ks, n0, g, t);
                     if (n0 + 8 > r0 + 1 || n0 + 8 > L) {          // diagonal / ragged block: apply the mask
                         const int c = n0 + 2 * t;
                         if (!(c <= row_a && c < L)) s[nt][0] = -INFINITY;
@@ -207,7 +257,7 @@ k_attn_fwd_mma(const float* __restrict__ q, const float* __restrict__ k, const f
 #pragma unroll
                     for (int e = 0; e < 4; ++e) p[e] = kp[e] ? p[e] : 0.f;      // 1/(1-p) folded into the final scale
                 }
-                mma_px(acc, p, vs, n0, g, t);
+                mma_px<X3>(acc, p, vs, n0, g, t);
             }
         }
         l0 = quad_sum(l0); l1 = quad_sum(l1);
@@ -228,6 +278,7 @@ k_attn_fwd_mma(const float* __restrict__ q, const float* __restrict__ k, const f
 // backward: pass A (query tiles -> dq), pass B (key tiles -> dk, dv); P recomputed from lse.
 // q is staged pre-multiplied by log2(e) (scores in the log2 domain); dk is rescaled at the store.
 // ----------------------------------------------------------------------------------------------
+template <bool X3>
 __global__ void __launch_bounds__(NWB * 32)
 k_attn_bwd_mma(const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v,
                const float* __restrict__ o, const float* __restrict__ lse, const float* __restrict__ dO,
@@ -275,9 +326,11 @@ k_attn_bwd_mma(const float* __restrict__ q, const float* __restrict__ k, const f
         if ((item & 1) == 0) {
             // ---------------- pass A: dq[i] = 0.25 * sum_j dS_ij k_j
             const int r0 = (ntile - 1 - (item >> 1)) * 16;
-            uint32_t aq[2][4], ag[2][4];
-            load_a16(aq, qs, r0, g, t);
-            load_a16(ag, gs, r0, g, t);
+            AFrag aq, ag;
+            load_a16(aq.hi, qs, r0, g, t);
+            load_a16(ag.hi, gs, r0, g, t);
+            finish_a<X3>(aq);
+            finish_a<X3>(ag);
             const int row_a = r0 + g, row_b = r0 + g + 8;
             const float la = ls[row_a], lb = ls[row_b], Da = Dv[row_a], Db = Dv[row_b];
             RowKeep rk;
@@ -287,8 +340,8 @@ k_attn_bwd_mma(const float* __restrict__ q, const float* __restrict__ k, const f
             const int kend = min(r0 + 16, L);
             for (int n0 = 0; n0 < kend; n0 += 8) {
                 float s[4] = {0.f, 0.f, 0.f, 0.f}, dp[4] = {0.f, 0.f, 0.f, 0.f};
-                mma_xt(s, aq, ks, n0, g, t);
-                mma_xt(dp, ag, vs, n0, g, t);
+                mma_xt<X3>(s, aq, ks, n0, g, t);
+                mma_xt<X3>(dp, ag, vs, n0, g, t);
                 if (dc.train) {
                     bool kp[4];
                     keep_rows(dc, site, rk, bl0, bl1, n0, t, kp);
@@ -305,16 +358,18 @@ k_attn_bwd_mma(const float* __restrict__ q, const float* __restrict__ k, const f
                     if (!(c <= row_b && c < L)) ds[2] = 0.f;
                     if (!(c + 1 <= row_b && c + 1 < L)) ds[3] = 0.f;
                 }
-                mma_px(acc, ds, ks, n0, g, t);
+                mma_px<X3>(acc, ds, ks, n0, g, t);
             }
             if (row_a < L) *reinterpret_cast<float4*>(dq + base + (size_t)row_a * D + 4 * t) = px_row(acc, 0, 0.25f);
             if (row_b < L) *reinterpret_cast<float4*>(dq + base + (size_t)row_b * D + 4 * t) = px_row(acc, 1, 0.25f);
         } else {
             // ---------------- pass B: key tile; S^T = K Q^T so that P^T / dS^T land in accumulator layout
             const int j0 = (item >> 1) * 16;
-            uint32_t ak[2][4], av[2][4];
-            load_a16(ak, ks, j0, g, t);
-            load_a16(av, vs, j0, g, t);
+            AFrag ak, av;
+            load_a16(ak.hi, ks, j0, g, t);
+            load_a16(av.hi, vs, j0, g, t);
+            finish_a<X3>(ak);
+            finish_a<X3>(av);
             const int key_a = j0 + g, key_b = j0 + g + 8;
             float dka[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
             float dva[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
@@ -326,8 +381,8 @@ k_attn_bwd_mma(const float* __restrict__ q, const float* __restrict__ k, const f
             const ByteLane bka(key_a & 3, dc.thr16), bkb(key_b & 3, dc.thr16);
             for (int i0 = j0; i0 < L; i0 += 8) {        // queries i >= key, 8 at a time
                 float st[4] = {0.f, 0.f, 0.f, 0.f}, dpt[4] = {0.f, 0.f, 0.f, 0.f};
-                mma_xt(st, ak, qs, i0, g, t);           // st[key][query] = k_key . q_query (log2 domain)
-                mma_xt(dpt, av, gs, i0, g, t);          // dpt[key][query] = v_key . dO_query
+                mma_xt<X3>(st, ak, qs, i0, g, t);       // st[key][query] = k_key . q_query (log2 domain)
+                mma_xt<X3>(dpt, av, gs, i0, g, t);      // dpt[key][query] = v_key . dO_query
                 const int qa = i0 + 2 * t, qb = qa + 1;
                 const float lqa = ls[qa], lqb = ls[qb], Dqa = Dv[qa], Dqb = Dv[qb];
                 float p[4];
@@ -357,8 +412,8 @@ k_attn_bwd_mma(const float* __restrict__ q, const float* __restrict__ k, const f
                 float ds[4];
                 ds[0] = p[0] * (dpt[0] - Dqa); ds[1] = p[1] * (dpt[1] - Dqb);
                 ds[2] = p[2] * (dpt[2] - Dqa); ds[3] = p[3] * (dpt[3] - Dqb);
-                mma_px(dva, pd, gs, i0, g, t);          // dv[key] += Pd^T[key][query] dO[query]
-                mma_px(dka, ds, qs, i0, g, t);          // dk[key] += dS^T[key][query] q[query] (q carries log2e)
+                mma_px<X3>(dva, pd, gs, i0, g, t);      // dv[key] += Pd^T[key][query] dO[query]
+                mma_px<X3>(dka, ds, qs, i0, g, t);      // dk[key] += dS^T[key][query] q[query] (q carries log2e)
             }
             if (key_a < L) {
                 *reinterpret_cast<float4*>(dk + base + (size_t)key_a * D + 4 * t) = px_row(dka, 0, LN2);

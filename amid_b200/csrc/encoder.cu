@@ -753,7 +753,7 @@ static int wgrad_chunks(int M, int* rows_per_cta) {
 
 using namespace amid;
 
-extern "C" int64_t amid_encoder_fwd_workspace_bytes(int32_t, int32_t) { return (int64_t)12 * D * D * sizeof(float); }
+extern "C" int64_t amid_encoder_fwd_workspace_bytes(int32_t, int32_t) { return (int64_t)(12 * D * D + 64) * sizeof(float); }
 
 static int encoder_fwd_impl(const amid_encoder_tensors* P, const float* x0, const uint32_t* tmask, int32_t B,
                             int32_t L, const amid_dropout* drop, amid_encoder_saved* S, float* enc_out,
@@ -770,11 +770,55 @@ static int encoder_fwd_impl(const amid_encoder_tensors* P, const float* x0, cons
     const size_t attn_smem = (size_t)2 * L * DH * sizeof(float);
     if (int rc = ensure_smem((const void*)k_attn_fwd, attn_smem)) return rc;
     const int attn_threads = (int)round_up((L + 1) / 2, 32);
+    if (mode == 3) {   // split-operand fp32-accurate path (x3.cuh): FP16-pair weight images, token tile in tensor memory
+        if (int rc = ensure_smem((const void*)x3::k_ln_qkv_x3, x3::CHAINX_SMEM)) return rc;
+        if (int rc = ensure_smem((const void*)x3::k_proj_ffn_x3, x3::CHAINX_SMEM)) return rc;
+        const size_t mma_smem = (size_t)2 * ((L + 15) / 16 * 16) * attn::LDS * sizeof(float);
+        if (int rc = ensure_smem((const void*)attn::k_attn_fwd_mma<true>, mma_smem)) return rc;
+        uint8_t* img = (uint8_t*)workspace;
+        float* winv = (float*)(img + (size_t)12 * x3::WIMG_BYTES);
+        x3::PrepJobsX pj;
+        for (int i = 0; i < 2; ++i) {
+            pj.src[i * 6 + 0] = P->in_w[i];
+            pj.src[i * 6 + 1] = P->in_w[i] + D * D;
+            pj.src[i * 6 + 2] = P->in_w[i] + 2 * D * D;
+            pj.src[i * 6 + 3] = P->out_w[i];
+            pj.src[i * 6 + 4] = P->c1_w[i];
+            pj.src[i * 6 + 5] = P->c2_w[i];
+        }
+        AMID_K("k_prep_wx3", stream);
+        x3::k_prep_wx3<<<12, 256, 0, stream>>>(pj, img, winv, 0);
+        AMID_LAUNCH_CHECK("k_prep_wx3");
+        const float* xin = x0;
+        for (int i = 0; i < 2; ++i) {
+            const uint8_t* W = img + (size_t)i * 6 * x3::WIMG_BYTES;
+            const float* wi = winv + i * 6;
+            AMID_K("k_ln_qkv_x3", stream);
+            x3::k_ln_qkv_x3<<<tiles, 256, x3::CHAINX_SMEM, stream>>>(xin, M, P->ln1_w[i], P->ln1_b[i], W, W + x3::WIMG_BYTES,
+                                                                    W + 2 * x3::WIMG_BYTES, wi, P->in_b[i], S->qn[i], S->st1[i],
+                                                                    S->q[i], S->k[i], S->v[i]);
+            AMID_LAUNCH_CHECK("k_ln_qkv_x3");
+            AMID_K("k_attn_fwd_mma3", stream);
+            attn::k_attn_fwd_mma<true><<<B * H, attn::NW * 32, mma_smem, stream>>>(S->q[i], S->k[i], S->v[i], S->o[i], S->lse[i], L,
+                                                                                   dc, dc.site_base + site_attn(i));
+            AMID_LAUNCH_CHECK("k_attn_fwd_mma3");
+            const bool last = i == 1;
+            AMID_K("k_proj_ffn_x3", stream);
+            x3::k_proj_ffn_x3<<<tiles, 256, x3::CHAINX_SMEM, stream>>>(
+                S->o[i], S->qn[i], M, W + 3 * x3::WIMG_BYTES, W + 4 * x3::WIMG_BYTES, W + 5 * x3::WIMG_BYTES, wi + 3, P->out_b[i],
+                P->ln2_w[i], P->ln2_b[i], P->c1_b[i], P->c2_b[i], tmask, dc, dc.site_base + site_ffn1(i),
+                dc.site_base + site_ffn2(i), S->x1[i], S->st2[i], S->y[i], S->h[i], S->xout[i], last ? P->ln3_w : nullptr,
+                last ? P->ln3_b : nullptr, last ? enc_out : nullptr, last ? S->st3 : nullptr);
+            AMID_LAUNCH_CHECK("k_proj_ffn_x3");
+            xin = S->xout[i];
+        }
+        return 0;
+    }
     if (mode == 2) {   // BF16 operands: convert the 12 weight matrices once, then 2 CTAs/SM chain kernels
         if (int rc = ensure_smem((const void*)tc16::k_ln_qkv_16, tc16::CHAIN16_SMEM)) return rc;
         if (int rc = ensure_smem((const void*)tc16::k_proj_ffn_16, tc16::CHAIN16_SMEM)) return rc;
         const size_t mma_smem = (size_t)2 * ((L + 15) / 16 * 16) * attn::LDS * sizeof(float);
-        if (int rc = ensure_smem((const void*)attn::k_attn_fwd_mma, mma_smem)) return rc;
+        if (int rc = ensure_smem((const void*)attn::k_attn_fwd_mma<false>, mma_smem)) return rc;
         uint16_t* w16 = (uint16_t*)workspace;
         tc16::PrepJobs pj;
         for (int i = 0; i < 2; ++i) {
@@ -797,7 +841,7 @@ static int encoder_fwd_impl(const amid_encoder_tensors* P, const float* x0, cons
                                                                          S->q[i], S->k[i], S->v[i]);
             AMID_LAUNCH_CHECK("k_ln_qkv_16");
             AMID_K("k_attn_fwd_mma", stream);
-            attn::k_attn_fwd_mma<<<B * H, attn::NW * 32, mma_smem, stream>>>(S->q[i], S->k[i], S->v[i], S->o[i], S->lse[i], L,
+            attn::k_attn_fwd_mma<false><<<B * H, attn::NW * 32, mma_smem, stream>>>(S->q[i], S->k[i], S->v[i], S->o[i], S->lse[i], L,
                                                                              dc, dc.site_base + site_attn(i));
             AMID_LAUNCH_CHECK("k_attn_fwd_mma");
             const bool last = i == 1;
@@ -816,7 +860,7 @@ static int encoder_fwd_impl(const amid_encoder_tensors* P, const float* x0, cons
         if (int rc = ensure_smem((const void*)tcenc::k_ln_qkv_tc, tcenc::CHAIN_SMEM)) return rc;
         if (int rc = ensure_smem((const void*)tcenc::k_proj_ffn_tc, tcenc::CHAIN_SMEM)) return rc;
         const size_t mma_smem = (size_t)2 * ((L + 15) / 16 * 16) * attn::LDS * sizeof(float);
-        if (int rc = ensure_smem((const void*)attn::k_attn_fwd_mma, mma_smem)) return rc;
+        if (int rc = ensure_smem((const void*)attn::k_attn_fwd_mma<false>, mma_smem)) return rc;
         const float* xin = x0;
         for (int i = 0; i < 2; ++i) {
             AMID_K("k_ln_qkv_tc", stream);
@@ -825,7 +869,7 @@ static int encoder_fwd_impl(const amid_encoder_tensors* P, const float* x0, cons
                 S->qn[i], S->st1[i], S->q[i], S->k[i], S->v[i]);
             AMID_LAUNCH_CHECK("k_ln_qkv_tc");
             AMID_K("k_attn_fwd_mma", stream);
-            attn::k_attn_fwd_mma<<<B * H, attn::NW * 32, mma_smem, stream>>>(S->q[i], S->k[i], S->v[i], S->o[i], S->lse[i], L,
+            attn::k_attn_fwd_mma<false><<<B * H, attn::NW * 32, mma_smem, stream>>>(S->q[i], S->k[i], S->v[i], S->o[i], S->lse[i], L,
                                                                              dc, dc.site_base + site_attn(i));
             AMID_LAUNCH_CHECK("k_attn_fwd_mma");
             const bool last = i == 1;
@@ -895,6 +939,12 @@ extern "C" int amid_encoder_fwd_bf16(const amid_encoder_tensors* P, const float*
     return encoder_fwd_impl(P, x0, tmask, B, L, drop, S, enc_out, workspace, workspace_bytes, stream, 2);
 }
 
+extern "C" int amid_encoder_fwd_x3(const amid_encoder_tensors* P, const float* x0, const uint32_t* tmask, int32_t B,
+                                   int32_t L, const amid_dropout* drop, amid_encoder_saved* S, float* enc_out,
+                                   void* workspace, int64_t workspace_bytes, amid_stream_t stream) {
+    return encoder_fwd_impl(P, x0, tmask, B, L, drop, S, enc_out, workspace, workspace_bytes, stream, 3);
+}
+
 constexpr int WG_TC_S = 24;   // CTAs per weight-gradient job on the tensor-core path (6 jobs -> 144 CTAs)
 
 extern "C" int64_t amid_encoder_bwd_workspace_bytes(int32_t B, int32_t L) {
@@ -906,7 +956,7 @@ extern "C" int64_t amid_encoder_bwd_workspace_bytes(int32_t B, int32_t L) {
     int64_t fl = 9 * M * D;                  // dxa, dxb, do2, dhpre, dx1, dO, dq, dk, dv
     fl += (int64_t)6 * S * (D * D + D);      // weight / bias partials
     fl += 2 * tiles * 2 * D;                 // LN partials (two in flight)
-    fl += (int64_t)12 * D * D;               // transposed weights (tensor-core path)
+    fl += (int64_t)12 * D * D + 64;          // transposed weights / weight images + inverse scales (tensor-core paths)
     return fl * (int64_t)sizeof(float) + 256;
 }
 
@@ -929,6 +979,7 @@ static int encoder_bwd_impl(const amid_encoder_tensors* P, const float* x0, cons
     const int SWmax = SW < 2 * WG_TC_S ? 2 * WG_TC_S : SW;
     if (use_tc) SW = tiles < WG_TC_S ? tiles : WG_TC_S;
     if (mode == 2) SW = tiles < 2 * WG_TC_S ? tiles : 2 * WG_TC_S;   // 2 CTAs/SM -> 48 x 6 CTAs
+    if (mode == 3) SW = tiles < WG_TC_S ? tiles : WG_TC_S;           // 1 CTA/SM (192 KB of piece buffers) -> 24 x 6 CTAs
     float* w = (float*)workspace;
     const size_t MD = (size_t)M * D;
     float* dxa = w;            // gradient of the current block output
@@ -945,7 +996,25 @@ static int encoder_bwd_impl(const amid_encoder_tensors* P, const float* x0, cons
     float* lnp0 = bpart + (size_t)6 * SWmax * D;
     float* lnp1 = lnp0 + (size_t)tiles * 2 * D;
     float* wtr = lnp1 + (size_t)tiles * 2 * D;   // 12 transposed weights: per block W2t, W1t, Wot, Wqt, Wkt, Wvt
-    if (mode == 2) {
+    uint8_t* ximg = (uint8_t*)wtr;
+    float* xwinv = (float*)(ximg + (size_t)12 * x3::WIMG_BYTES);
+    if (mode == 3) {
+        if (int rc = ensure_smem((const void*)x3::k_ffn_bwd_x3, x3::CHAINX_SMEM)) return rc;
+        if (int rc = ensure_smem((const void*)x3::k_qkv_bwd_x3, x3::CHAINX_SMEM)) return rc;
+        if (int rc = ensure_smem((const void*)x3::k_wgrad_x3, x3::WGRADX_SMEM)) return rc;
+        x3::PrepJobsX pj;
+        for (int i = 0; i < 2; ++i) {
+            pj.src[i * 6 + 0] = P->c2_w[i];
+            pj.src[i * 6 + 1] = P->c1_w[i];
+            pj.src[i * 6 + 2] = P->out_w[i];
+            pj.src[i * 6 + 3] = P->in_w[i];
+            pj.src[i * 6 + 4] = P->in_w[i] + D * D;
+            pj.src[i * 6 + 5] = P->in_w[i] + 2 * D * D;
+        }
+        AMID_K("k_prep_wx3", stream);
+        x3::k_prep_wx3<<<12, 256, 0, stream>>>(pj, ximg, xwinv, 1);
+        AMID_LAUNCH_CHECK("k_prep_wx3");
+    } else if (mode == 2) {
         if (int rc = ensure_smem((const void*)tc16::k_ffn_bwd_16, tc16::CHAIN16_SMEM)) return rc;
         if (int rc = ensure_smem((const void*)tc16::k_qkv_bwd_16, tc16::CHAIN16_SMEM)) return rc;
         if (int rc = ensure_smem((const void*)tc16::k_wgrad_16, tc16::WGRAD16_SMEM)) return rc;
@@ -998,7 +1067,14 @@ static int encoder_bwd_impl(const amid_encoder_tensors* P, const float* x0, cons
         const float* xin = i == 0 ? x0 : S->xout[0];
         float* dxin = i == 0 ? dx0 : dxb;
         const float* Wt = wtr + (size_t)i * 6 * D * D;
-        if (mode == 2) {
+        if (mode == 3) {
+            const uint8_t* W = ximg + (size_t)i * 6 * x3::WIMG_BYTES;
+            AMID_K("k_ffn_bwd_x3", stream);
+            x3::k_ffn_bwd_x3<<<tiles, 256, x3::CHAINX_SMEM, stream>>>(
+                dxa, S->h[i], S->x1[i], S->st2[i], tmask, M, W, W + x3::WIMG_BYTES, W + 2 * x3::WIMG_BYTES, xwinv + i * 6,
+                P->ln2_w[i], dc, dc.site_base + site_ffn1(i), dc.site_base + site_ffn2(i), do2, dhp, dx1, dO, lnp0);
+            AMID_LAUNCH_CHECK("k_ffn_bwd_x3");
+        } else if (mode == 2) {
             const uint16_t* W16 = (const uint16_t*)wtr + (size_t)i * 6 * D * D;
             AMID_K("k_ffn_bwd_16", stream);
             tc16::k_ffn_bwd_16<<<tiles, 256, tc16::CHAIN16_SMEM, stream>>>(
@@ -1022,11 +1098,18 @@ static int encoder_bwd_impl(const amid_encoder_tensors* P, const float* x0, cons
         AMID_K("k_reduce_ln", stream);
         k_reduce_ln<<<16, 1024, 0, stream>>>(lnp0, tiles, G->ln2_w[i], G->ln2_b[i]);
         AMID_LAUNCH_CHECK("k_reduce_ln");
-        if (use_tc) {
+        if (mode == 3) {
             const size_t mma_smem = (size_t)((L + 15) / 16 * 16) * (4 * attn::LDS + 2) * sizeof(float);
-            if (int rc = ensure_smem((const void*)attn::k_attn_bwd_mma, mma_smem)) return rc;
+            if (int rc = ensure_smem((const void*)attn::k_attn_bwd_mma<true>, mma_smem)) return rc;
+            AMID_K("k_attn_bwd_mma3", stream);
+            attn::k_attn_bwd_mma<true><<<B * H, attn::NWB * 32, mma_smem, stream>>>(S->q[i], S->k[i], S->v[i], S->o[i], S->lse[i], dO,
+                                                                                    dq, dk, dv, L, dc, dc.site_base + site_attn(i));
+            AMID_LAUNCH_CHECK("k_attn_bwd_mma3");
+        } else if (use_tc) {
+            const size_t mma_smem = (size_t)((L + 15) / 16 * 16) * (4 * attn::LDS + 2) * sizeof(float);
+            if (int rc = ensure_smem((const void*)attn::k_attn_bwd_mma<false>, mma_smem)) return rc;
             AMID_K("k_attn_bwd_mma", stream);
-            attn::k_attn_bwd_mma<<<B * H, attn::NWB * 32, mma_smem, stream>>>(S->q[i], S->k[i], S->v[i], S->o[i], S->lse[i], dO,
+            attn::k_attn_bwd_mma<false><<<B * H, attn::NWB * 32, mma_smem, stream>>>(S->q[i], S->k[i], S->v[i], S->o[i], S->lse[i], dO,
                                                                              dq, dk, dv, L, dc, dc.site_base + site_attn(i));
             AMID_LAUNCH_CHECK("k_attn_bwd_mma");
         } else {
@@ -1035,7 +1118,14 @@ static int encoder_bwd_impl(const amid_encoder_tensors* P, const float* x0, cons
                                                                dv, L, dc, dc.site_base + site_attn(i));
         AMID_LAUNCH_CHECK("k_attn_bwd");
         }
-        if (mode == 2) {
+        if (mode == 3) {
+            const uint8_t* W = ximg + (size_t)(i * 6 + 3) * x3::WIMG_BYTES;
+            AMID_K("k_qkv_bwd_x3", stream);
+            x3::k_qkv_bwd_x3<<<tiles, 256, x3::CHAINX_SMEM, stream>>>(dq, dk, dv, dx1, xin, S->st1[i], M, W, W + x3::WIMG_BYTES,
+                                                                     W + 2 * x3::WIMG_BYTES, xwinv + i * 6 + 3, P->ln1_w[i], dxin,
+                                                                     lnp1);
+            AMID_LAUNCH_CHECK("k_qkv_bwd_x3");
+        } else if (mode == 2) {
             const uint16_t* W16 = (const uint16_t*)wtr + (size_t)i * 6 * D * D;
             AMID_K("k_qkv_bwd_16", stream);
             tc16::k_qkv_bwd_16<<<tiles, 256, tc16::CHAIN16_SMEM, stream>>>(dq, dk, dv, dx1, xin, S->st1[i], M, W16 + 3 * D * D,
@@ -1066,7 +1156,13 @@ static int encoder_bwd_impl(const amid_encoder_tensors* P, const float* x0, cons
         wj.dY[3] = dq;  wj.X[3] = S->qn[i];
         wj.dY[4] = dk;  wj.X[4] = xin;
         wj.dY[5] = dv;  wj.X[5] = xin;
-        if (mode == 2) {
+        if (mode == 3) {
+            x3::WgradJobsX wx;
+            for (int j = 0; j < 6; ++j) { wx.dY[j] = wj.dY[j]; wx.X[j] = wj.X[j]; }
+            AMID_K("k_wgrad_x3", stream);
+            x3::k_wgrad_x3<<<dim3(SW, 6), 256, x3::WGRADX_SMEM, stream>>>(wx, M, wpart, bpart);
+            AMID_LAUNCH_CHECK("k_wgrad_x3");
+        } else if (mode == 2) {
             tc16::WgradJobs16 w16;
             for (int j = 0; j < 6; ++j) { w16.dY[j] = wj.dY[j]; w16.X[j] = wj.X[j]; }
             AMID_K("k_wgrad_16", stream);
@@ -1121,6 +1217,12 @@ extern "C" int amid_encoder_bwd_bf16(const amid_encoder_tensors* P, const float*
                                      const float* d_enc, amid_encoder_tensors* G, float* dx0, void* workspace,
                                      int64_t workspace_bytes, amid_stream_t stream) {
     return encoder_bwd_impl(P, x0, tmask, B, L, drop, S, enc_out, d_enc, G, dx0, workspace, workspace_bytes, stream, 2);
+}
+extern "C" int amid_encoder_bwd_x3(const amid_encoder_tensors* P, const float* x0, const uint32_t* tmask, int32_t B,
+                                   int32_t L, const amid_dropout* drop, const amid_encoder_saved* S, const float* enc_out,
+                                   const float* d_enc, amid_encoder_tensors* G, float* dx0, void* workspace,
+                                   int64_t workspace_bytes, amid_stream_t stream) {
+    return encoder_bwd_impl(P, x0, tmask, B, L, drop, S, enc_out, d_enc, G, dx0, workspace, workspace_bytes, stream, 3);
 }
 
 #include "x3_test.cuh"

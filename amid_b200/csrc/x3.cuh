@@ -73,11 +73,12 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
 }
 
 // ---- the FP16 pair split
-// scale = 2^k with amax * scale in [2^14, 2^15) (clamped so that scale and 1/scale are both normal floats)
+// scale = 2^k with amax * scale in [2^14, 2^15); k is clamped to [-60, 60] so that products of a few scales and their
+// inverses stay finite (rows below 2^-46 simply keep fewer bits relative to their own tiny maximum)
 __device__ __forceinline__ void pow2_scale(float amax, float& scale, float& inv) {
     const int e = (int)((__float_as_uint(amax) >> 23) & 0xFFu);
     int sb = e == 0 ? 127 : 268 - e;
-    sb = min(max(sb, 1), 253);
+    sb = min(max(sb, 67), 187);
     scale = __uint_as_float((uint32_t)sb << 23);
     inv = __uint_as_float((uint32_t)(254 - sb) << 23);
 }
@@ -221,6 +222,546 @@ k_prep_wx3(PrepJobsX jobs, uint8_t* __restrict__ img /*[n][64 KB]*/, float* __re
         *reinterpret_cast<uint4*>(out + off) = make_uint4(p0[0], p0[1], p0[2], p0[3]);
         *reinterpret_cast<uint4*>(out + PIECE_BYTES + off) = make_uint4(p1[0], p1[1], p1[2], p1[3]);
     }
+}
+
+// fp32 parking in the accumulator columns (a thread only ever touches its own lane and its own 64 columns)
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const float (&v)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};"
+        ::"r"(taddr), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]), "f"(v[8]),
+          "f"(v[9]), "f"(v[10]), "f"(v[11]), "f"(v[12]), "f"(v[13]), "f"(v[14]), "f"(v[15]), "f"(v[16]), "f"(v[17]),
+          "f"(v[18]), "f"(v[19]), "f"(v[20]), "f"(v[21]), "f"(v[22]), "f"(v[23]), "f"(v[24]), "f"(v[25]), "f"(v[26]),
+          "f"(v[27]), "f"(v[28]), "f"(v[29]), "f"(v[30]), "f"(v[31]) : "memory");
+}
+// the 64 parked values of this thread -> A pieces (after the row scale is known)
+__device__ __forceinline__ void parked_to_a(uint32_t tl, const Epi& e, float sc) {
+    tmem_st_wait();
+#pragma unroll 1
+    for (int half = 0; half < 2; ++half) {
+        float a[32];
+        const int c0 = e.cb + half * 32;
+        tmem_ld32(tl + ACC_COL + c0, a);
+        put_a32(tl, c0, a, sc);
+    }
+}
+// multiply the 64 parked values of this thread by f (a power of two)
+__device__ __forceinline__ void parked_scale(uint32_t tl, const Epi& e, float f) {
+    tmem_st_wait();
+#pragma unroll 1
+    for (int half = 0; half < 2; ++half) {
+        float a[32];
+        const int c0 = e.cb + half * 32;
+        tmem_ld32(tl + ACC_COL + c0, a);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) a[i] *= f;
+        tmem_st32(tl + ACC_COL + c0, a);
+    }
+}
+struct ChainX {
+    uint8_t* W;
+    float* stage;
+    __device__ ChainX(uint8_t* raw) {
+        W = align1k(raw);
+        stage = reinterpret_cast<float*>(W + WIMG_BYTES) + (threadIdx.x >> 5) * WSTAGE_FLOATS;
+    }
+};
+__device__ __forceinline__ void begin(SharedX& sh, uint8_t* Wbuf, const uint8_t* __restrict__ first_img) {
+    setup(sh, CHAIN_TMEM_COLS);
+    fence_before();
+    __syncthreads();
+    fence_after();
+    load_w_bulk(sh, Wbuf, first_img);
+}
+// a token tile from global memory -> A pieces (row scale from the row maximum); returns 1 / scale
+__device__ __forceinline__ float global_to_a(SharedX& sh, const Epi& e, float* stage, uint32_t tl, const float* __restrict__ g,
+                                             size_t wbase, int rv) {
+    float v0[32], v1[32];
+    warp_load32(stage, e.lane, g + wbase + e.cb, rv, v0);
+    warp_load32(stage, e.lane, g + wbase + e.cb + 32, rv, v1);
+    float sc, inv;
+    pow2_scale(row_max(sh, e, 2, absmax32(v1, absmax32(v0, 0.f))), sc, inv);
+    put_a32(tl, e.cb, v0, sc);
+    put_a32(tl, e.cb + 32, v1, sc);
+    return inv;
+}
+__device__ __forceinline__ void ln_stats(SharedX& sh, const Epi& e, const float (&xr)[64], float& mean, float& rstd) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 64; ++i) s += xr[i];
+    mean = row_sum(sh, e, 0, s) * (1.0f / D);
+    float ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < 64; ++i) { const float a = xr[i] - mean; ss = fmaf(a, a, ss); }
+    rstd = 1.0f / sqrtf(row_sum(sh, e, 1, ss) * (1.0f / D) + LN_EPS);
+}
+
+// ----------------------------------------------------------------------------------------------
+// forward 1: k, v from x; q from LN1(x).   wimg = images of Wk, Wv, Wq (in that order), winv their inverse scales
+// ----------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256, 2)
+k_ln_qkv_x3(const float* __restrict__ x, int M, const float* __restrict__ ln_w, const float* __restrict__ ln_b,
+            const uint8_t* __restrict__ img_q, const uint8_t* __restrict__ img_k, const uint8_t* __restrict__ img_v,
+            const float* __restrict__ winv /*q,k,v*/, const float* __restrict__ in_b, float* __restrict__ qn,
+            float* __restrict__ st1, float* __restrict__ q, float* __restrict__ k, float* __restrict__ v) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ SharedX sh;
+    ChainX sm(smem_raw);
+    const int row0 = blockIdx.x * 128;
+    begin(sh, sm.W, img_k);
+    Epi e;
+    const int gr = row0 + e.row;
+    const bool valid = gr < M;
+    const int rv = rows_valid(row0, e, M);
+    const size_t wbase = (size_t)(row0 + e.wrow0) * D;
+    const uint32_t tl = sh.tmem + e.lane_addr;
+    uint32_t ph_mma = 0, ph_w = 0;
+    const float inv_x = global_to_a(sh, e, sm.stage, tl, x, wbase, rv);
+    float* outs[2] = {k, v};
+#pragma unroll 1
+    for (int g = 0; g < 2; ++g) {        // the raw tile stays in tensor memory for both
+        run_gemm_x3(sh, 0, sm.W, false, ph_mma, ph_w);
+        load_w_bulk(sh, sm.W, g == 0 ? img_v : img_q);
+        const float f = inv_x * __ldg(winv + 1 + g);
+#pragma unroll 1
+        for (int half = 0; half < 2; ++half) {
+            float a[32];
+            const int c0 = e.cb + half * 32;
+            tmem_ld32(tl + ACC_COL + c0, a);
+            const float* bb = in_b + (g + 1) * D + c0;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) a[i] = fmaf(a[i], f, __ldg(bb + i));
+            warp_store32(sm.stage, e.lane, a, outs[g] + wbase + c0, rv);
+        }
+    }
+    float inv_qn;
+    {   // LN1 of the fp32 input; the result replaces the operand pieces (the v GEMM has completed)
+        float xr[64];
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            float a[32];
+            warp_load32(sm.stage, e.lane, x + wbase + e.cb + half * 32, rv, a);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) xr[half * 32 + i] = a[i];
+        }
+        float mean, rstd;
+        ln_stats(sh, e, xr, mean, rstd);
+        float am = 0.f;
+#pragma unroll
+        for (int i = 0; i < 64; ++i) {
+            xr[i] = fmaf((xr[i] - mean) * rstd, __ldg(ln_w + e.cb + i), __ldg(ln_b + e.cb + i));
+            am = fmaxf(am, fabsf(xr[i]));
+        }
+        float sc;
+        pow2_scale(row_max(sh, e, 2, am), sc, inv_qn);
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            float a[32];
+            const int c0 = e.cb + half * 32;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) a[i] = xr[half * 32 + i];
+            put_a32(tl, c0, a, sc);
+            warp_store32(sm.stage, e.lane, a, qn + wbase + c0, rv);
+        }
+        if (valid && e.cb == 0) { st1[(size_t)gr * 2] = mean; st1[(size_t)gr * 2 + 1] = rstd; }
+    }
+    run_gemm_x3(sh, 0, sm.W, false, ph_mma, ph_w);
+    {
+        const float f = inv_qn * __ldg(winv);
+#pragma unroll 1
+        for (int half = 0; half < 2; ++half) {
+            float a[32];
+            const int c0 = e.cb + half * 32;
+            tmem_ld32(tl + ACC_COL + c0, a);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) a[i] = fmaf(a[i], f, __ldg(in_b + c0 + i)) * 0.25f;
+            warp_store32(sm.stage, e.lane, a, q + wbase + c0, rv);
+        }
+    }
+    teardown(sh, CHAIN_TMEM_COLS);
+}
+
+// ----------------------------------------------------------------------------------------------
+// forward 2: out-proj + residual + LN2 + FFN + mask (+ last LN).   images / winv: Wo, W1, W2
+// ----------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256, 2)
+k_proj_ffn_x3(const float* __restrict__ o, const float* __restrict__ qn, int M, const uint8_t* __restrict__ img_o,
+              const uint8_t* __restrict__ img_1, const uint8_t* __restrict__ img_2, const float* __restrict__ winv /*o,1,2*/,
+              const float* __restrict__ bo, const float* __restrict__ ln2_w, const float* __restrict__ ln2_b,
+              const float* __restrict__ b1, const float* __restrict__ b2, const uint32_t* __restrict__ tmask, DropCfg dc,
+              uint32_t site1, uint32_t site2, float* __restrict__ x1, float* __restrict__ st2, float* __restrict__ y,
+              float* __restrict__ h, float* __restrict__ xout, const float* __restrict__ ln3_w,
+              const float* __restrict__ ln3_b, float* __restrict__ enc, float* __restrict__ st3) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ SharedX sh;
+    ChainX sm(smem_raw);
+    const int row0 = blockIdx.x * 128;
+    begin(sh, sm.W, img_o);
+    Epi e;
+    const int gr = row0 + e.row;
+    const bool valid = gr < M;
+    const int rv = rows_valid(row0, e, M);
+    const size_t wbase = (size_t)(row0 + e.wrow0) * D;
+    const uint32_t tl = sh.tmem + e.lane_addr;
+    uint32_t ph_mma = 0, ph_w = 0;
+    float inv_a = global_to_a(sh, e, sm.stage, tl, o, wbase, rv);
+    // ---- x1 = Qn + o Wo^T + bo ; y = LN2(x1)
+    run_gemm_x3(sh, 0, sm.W, false, ph_mma, ph_w);
+    load_w_bulk(sh, sm.W, img_1);
+    {
+        const float f = inv_a * __ldg(winv);
+        float xr[64];
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            float a[32], r[32];
+            const int c0 = e.cb + half * 32;
+            tmem_ld32(tl + ACC_COL + c0, a);
+            warp_load32(sm.stage, e.lane, qn + wbase + c0, rv, r);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) a[i] = fmaf(a[i], f, __ldg(bo + c0 + i)) + r[i];
+            warp_store32(sm.stage, e.lane, a, x1 + wbase + c0, rv);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) xr[half * 32 + i] = a[i];
+        }
+        float mean, rstd;
+        ln_stats(sh, e, xr, mean, rstd);
+        float am = 0.f;
+#pragma unroll
+        for (int i = 0; i < 64; ++i) {
+            xr[i] = fmaf((xr[i] - mean) * rstd, __ldg(ln2_w + e.cb + i), __ldg(ln2_b + e.cb + i));
+            am = fmaxf(am, fabsf(xr[i]));
+        }
+        float sc;
+        pow2_scale(row_max(sh, e, 2, am), sc, inv_a);
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            float a[32];
+            const int c0 = e.cb + half * 32;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) a[i] = xr[half * 32 + i];
+            put_a32(tl, c0, a, sc);
+            warp_store32(sm.stage, e.lane, a, y + wbase + c0, rv);
+        }
+        if (valid && e.cb == 0) { st2[(size_t)gr * 2] = mean; st2[(size_t)gr * 2 + 1] = rstd; }
+    }
+    // ---- h = relu(dropout1(y W1^T + b1))
+    run_gemm_x3(sh, 0, sm.W, false, ph_mma, ph_w);
+    load_w_bulk(sh, sm.W, img_2);
+    {
+        const float f = inv_a * __ldg(winv + 1);
+        float am = 0.f;
+#pragma unroll 1
+        for (int half = 0; half < 2; ++half) {
+            float a[32];
+            const int c0 = e.cb + half * 32;
+            tmem_ld32(tl + ACC_COL + c0, a);
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+                const float4 b4 = __ldg(reinterpret_cast<const float4*>(b1 + c0 + i));
+                float4 t = make_float4(fmaf(a[i], f, b4.x), fmaf(a[i + 1], f, b4.y), fmaf(a[i + 2], f, b4.z), fmaf(a[i + 3], f, b4.w));
+                if (dc.train) t = drop4(t, dc, site1, (uint64_t)gr * D + c0 + i);
+                a[i] = fmaxf(t.x, 0.f); a[i + 1] = fmaxf(t.y, 0.f); a[i + 2] = fmaxf(t.z, 0.f); a[i + 3] = fmaxf(t.w, 0.f);
+            }
+            am = absmax32(a, am);
+            tmem_st32(tl + ACC_COL + c0, a);                 // parked until the row scale is known
+            warp_store32(sm.stage, e.lane, a, h + wbase + c0, rv);
+        }
+        float sc;
+        pow2_scale(row_max(sh, e, 2, am), sc, inv_a);
+        parked_to_a(tl, e, sc);
+    }
+    // ---- xout = (dropout2(h W2^T + b2) + y) * ~tmask  (+ last LayerNorm)
+    run_gemm_x3(sh, 0, sm.W, false, ph_mma, ph_w);
+    {
+        const float f = inv_a * __ldg(winv + 2);
+        uint4 tw = make_uint4(0u, 0u, 0u, 0u);
+        if (valid) tw = __ldg(reinterpret_cast<const uint4*>(tmask) + gr);
+        float xr[64];
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            float a[32], yy[32];
+            const int c0 = e.cb + half * 32;
+            tmem_ld32(tl + ACC_COL + c0, a);
+            warp_load32_cg(sm.stage, e.lane, y + wbase + c0, rv, yy);   // written by this CTA above: coherent loads
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+                const float4 b4 = __ldg(reinterpret_cast<const float4*>(b2 + c0 + i));
+                float4 t = make_float4(fmaf(a[i], f, b4.x), fmaf(a[i + 1], f, b4.y), fmaf(a[i + 2], f, b4.z), fmaf(a[i + 3], f, b4.w));
+                if (dc.train) t = drop4(t, dc, site2, (uint64_t)gr * D + c0 + i);
+                t = make_float4(t.x + yy[i], t.y + yy[i + 1], t.z + yy[i + 2], t.w + yy[i + 3]);
+                t = apply_tmask(t, tw, (c0 + i) >> 2);
+                a[i] = t.x; a[i + 1] = t.y; a[i + 2] = t.z; a[i + 3] = t.w;
+            }
+            warp_store32(sm.stage, e.lane, a, xout + wbase + c0, rv);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) xr[half * 32 + i] = a[i];
+        }
+        if (enc) {
+            float mean, rstd;
+            ln_stats(sh, e, xr, mean, rstd);
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                float a[32];
+                const int c0 = e.cb + half * 32;
+#pragma unroll
+                for (int i = 0; i < 32; ++i) a[i] = fmaf((xr[half * 32 + i] - mean) * rstd, __ldg(ln3_w + c0 + i), __ldg(ln3_b + c0 + i));
+                warp_store32(sm.stage, e.lane, a, enc + wbase + c0, rv);
+            }
+            if (valid && e.cb == 0) { st3[(size_t)gr * 2] = mean; st3[(size_t)gr * 2 + 1] = rstd; }
+        }
+    }
+    teardown(sh, CHAIN_TMEM_COLS);
+}
+
+// LayerNorm backward of the row whose upstream gradient dy is PARKED in the accumulator columns.  xhat(c0, out[32]) yields
+// x-hat of 32 columns.  On return the parked values are dx = rstd (dy w - c1 - xhat c2); the per-tile LN parameter
+// partials are in sh.lnacc; returns max |dx| over this thread's 64 columns.
+template <class XHat>
+__device__ __forceinline__ float ln_bwd_parked(SharedX& sh, const Epi& e, uint32_t tl, const float* __restrict__ w, float rstd,
+                                               bool valid, XHat xhat) {
+    float p1 = 0.f, p2 = 0.f;
+    tmem_st_wait();
+#pragma unroll 1
+    for (int half = 0; half < 2; ++half) {
+        float dy[32], xh[32];
+        const int c0 = e.cb + half * 32;
+        tmem_ld32(tl + ACC_COL + c0, dy);
+        xhat(c0, xh);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+            const float dw = dy[i] * __ldg(w + c0 + i);
+            p1 += dw;
+            p2 = fmaf(dw, xh[i], p2);
+        }
+    }
+    const float c1 = row_sum(sh, e, 0, p1) * (1.0f / D);
+    const float c2 = row_sum(sh, e, 1, p2) * (1.0f / D);
+    float am = 0.f;
+#pragma unroll 1
+    for (int half = 0; half < 2; ++half) {
+        float dy[32], xh[32], dx[32];
+        const int c0 = e.cb + half * 32;
+        tmem_ld32(tl + ACC_COL + c0, dy);
+        xhat(c0, xh);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+            dx[i] = valid ? rstd * (dy[i] * __ldg(w + c0 + i) - c1 - xh[i] * c2) : 0.f;
+            xh[i] *= dy[i];                       // dw terms
+        }
+        am = absmax32(dx, am);
+        tmem_st32(tl + ACC_COL + c0, dx);
+        const float sw = warp_colsum32(xh, e.lane);
+        const float sb = warp_colsum32(dy, e.lane);
+        sh.lnacc[e.warp][0][half * 32 + e.lane] = sw;
+        sh.lnacc[e.warp][1][half * 32 + e.lane] = sb;
+    }
+    return am;
+}
+
+// ----------------------------------------------------------------------------------------------
+// backward 1: FFN + LN2 + out-proj input gradient.   images / winv: W2^T, W1^T, Wo^T (transposed images)
+// ----------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256, 2)
+k_ffn_bwd_x3(const float* __restrict__ dxo, const float* __restrict__ h, const float* __restrict__ x1,
+             const float* __restrict__ st2, const uint32_t* __restrict__ tmask, int M, const uint8_t* __restrict__ img_2t,
+             const uint8_t* __restrict__ img_1t, const uint8_t* __restrict__ img_ot, const float* __restrict__ winv /*2,1,o*/,
+             const float* __restrict__ ln2_w, DropCfg dc, uint32_t site1, uint32_t site2, float* __restrict__ do2,
+             float* __restrict__ dhpre, float* __restrict__ dx1, float* __restrict__ dO, float* __restrict__ ln_part) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ SharedX sh;
+    ChainX sm(smem_raw);
+    const int row0 = blockIdx.x * 128;
+    begin(sh, sm.W, img_2t);
+    Epi e;
+    const int gr = row0 + e.row;
+    const bool valid = gr < M;
+    const int rv = rows_valid(row0, e, M);
+    const size_t wbase = (size_t)(row0 + e.wrow0) * D;
+    const uint32_t tl = sh.tmem + e.lane_addr;
+    uint32_t ph_mma = 0, ph_w = 0;
+    const float dsc = dc.train ? dc.scale : 1.0f;
+    uint4 tw = make_uint4(0u, 0u, 0u, 0u);
+    float mean = 0.f, rstd = 0.f;
+    if (valid) { tw = __ldg(reinterpret_cast<const uint4*>(tmask) + gr); mean = st2[(size_t)gr * 2]; rstd = st2[(size_t)gr * 2 + 1]; }
+    float inv_a;
+    {   // A = do2 = dropout2-mask * (dxo * ~tmask)
+        float g[2][32];
+        float am = 0.f;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            const int c0 = e.cb + half * 32;
+            warp_load32(sm.stage, e.lane, dxo + wbase + c0, rv, g[half]);
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+                float4 t = apply_tmask(make_float4(g[half][i], g[half][i + 1], g[half][i + 2], g[half][i + 3]), tw, (c0 + i) >> 2);
+                if (dc.train) t = drop4(t, dc, site2, (uint64_t)gr * D + c0 + i);
+                g[half][i] = t.x; g[half][i + 1] = t.y; g[half][i + 2] = t.z; g[half][i + 3] = t.w;
+            }
+            am = absmax32(g[half], am);
+            warp_store32(sm.stage, e.lane, g[half], do2 + wbase + c0, rv);
+        }
+        float sc;
+        pow2_scale(row_max(sh, e, 2, am), sc, inv_a);
+        put_a32(tl, e.cb, g[0], sc);
+        put_a32(tl, e.cb + 32, g[1], sc);
+    }
+    // ---- dhpre = (do2 W2) * scale * [h > 0]
+    run_gemm_x3(sh, 0, sm.W, false, ph_mma, ph_w);
+    load_w_bulk(sh, sm.W, img_1t);
+    {
+        const float f = inv_a * __ldg(winv) * dsc;
+        float am = 0.f;
+#pragma unroll 1
+        for (int half = 0; half < 2; ++half) {
+            float a[32], hh[32];
+            const int c0 = e.cb + half * 32;
+            tmem_ld32(tl + ACC_COL + c0, a);
+            warp_load32(sm.stage, e.lane, h + wbase + c0, rv, hh);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) a[i] = hh[i] > 0.f ? a[i] * f : 0.f;
+            am = absmax32(a, am);
+            tmem_st32(tl + ACC_COL + c0, a);
+            warp_store32(sm.stage, e.lane, a, dhpre + wbase + c0, rv);
+        }
+        float sc;
+        pow2_scale(row_max(sh, e, 2, am), sc, inv_a);
+        parked_to_a(tl, e, sc);
+    }
+    // ---- dy = dhpre W1 + g ; LN2 backward -> dx1
+    run_gemm_x3(sh, 0, sm.W, false, ph_mma, ph_w);
+    load_w_bulk(sh, sm.W, img_ot);
+    {
+        const float f = inv_a * __ldg(winv + 1);
+#pragma unroll 1
+        for (int half = 0; half < 2; ++half) {          // park dy = acc f + masked upstream gradient
+            float a[32], g[32];
+            const int c0 = e.cb + half * 32;
+            tmem_ld32(tl + ACC_COL + c0, a);
+            warp_load32(sm.stage, e.lane, dxo + wbase + c0, rv, g);
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+                const float4 gm = apply_tmask(make_float4(g[i], g[i + 1], g[i + 2], g[i + 3]), tw, (c0 + i) >> 2);
+                a[i] = fmaf(a[i], f, gm.x); a[i + 1] = fmaf(a[i + 1], f, gm.y);
+                a[i + 2] = fmaf(a[i + 2], f, gm.z); a[i + 3] = fmaf(a[i + 3], f, gm.w);
+            }
+            tmem_st32(tl + ACC_COL + c0, a);
+        }
+        auto xhat = [&](int c0, float (&xh)[32]) {
+            warp_load32(sm.stage, e.lane, x1 + wbase + c0, rv, xh);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) xh[i] = valid ? (xh[i] - mean) * rstd : 0.f;
+        };
+        const float am = ln_bwd_parked(sh, e, tl, ln2_w, rstd, valid, xhat);
+        flush_ln_partials(sh, ln_part + (size_t)blockIdx.x * 2 * D);
+        float sc;
+        pow2_scale(row_max(sh, e, 2, am), sc, inv_a);
+        tmem_st_wait();
+#pragma unroll 1
+        for (int half = 0; half < 2; ++half) {
+            float a[32];
+            const int c0 = e.cb + half * 32;
+            tmem_ld32(tl + ACC_COL + c0, a);
+            put_a32(tl, c0, a, sc);
+            warp_store32(sm.stage, e.lane, a, dx1 + wbase + c0, rv);
+        }
+    }
+    // ---- dO = dx1 Wo
+    run_gemm_x3(sh, 0, sm.W, false, ph_mma, ph_w);
+    {
+        const float f = inv_a * __ldg(winv + 2);
+#pragma unroll 1
+        for (int half = 0; half < 2; ++half) {
+            float a[32];
+            const int c0 = e.cb + half * 32;
+            tmem_ld32(tl + ACC_COL + c0, a);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) a[i] *= f;
+            warp_store32(sm.stage, e.lane, a, dO + wbase + c0, rv);
+        }
+    }
+    teardown(sh, CHAIN_TMEM_COLS);
+}
+
+// ----------------------------------------------------------------------------------------------
+// backward 2: dQn = dx1 + dq Wq ; dx_in = LN1bwd(dQn) + dk Wk + dv Wv.   images / winv: Wq^T, Wk^T, Wv^T
+// One accumulator: the LayerNorm-backward result is parked in it, rescaled (exactly, by powers of two) to the scale of
+// the next GEMM's operands, and the dk / dv products accumulate on top.
+// ----------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256, 2)
+k_qkv_bwd_x3(const float* __restrict__ dq, const float* __restrict__ dk, const float* __restrict__ dv,
+             const float* __restrict__ dx1, const float* __restrict__ xin, const float* __restrict__ st1, int M,
+             const uint8_t* __restrict__ img_qt, const uint8_t* __restrict__ img_kt, const uint8_t* __restrict__ img_vt,
+             const float* __restrict__ winv /*q,k,v*/, const float* __restrict__ ln1_w, float* __restrict__ dxin,
+             float* __restrict__ ln_part) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ SharedX sh;
+    ChainX sm(smem_raw);
+    const int row0 = blockIdx.x * 128;
+    begin(sh, sm.W, img_qt);
+    Epi e;
+    const int gr = row0 + e.row;
+    const bool valid = gr < M;
+    const int rv = rows_valid(row0, e, M);
+    const size_t wbase = (size_t)(row0 + e.wrow0) * D;
+    const uint32_t tl = sh.tmem + e.lane_addr;
+    uint32_t ph_mma = 0, ph_w = 0;
+    float mean = 0.f, rstd = 0.f;
+    if (valid) { mean = st1[(size_t)gr * 2]; rstd = st1[(size_t)gr * 2 + 1]; }
+    const float inv_q = global_to_a(sh, e, sm.stage, tl, dq, wbase, rv);
+    run_gemm_x3(sh, 0, sm.W, false, ph_mma, ph_w);
+    load_w_bulk(sh, sm.W, img_kt);
+    {
+        const float f = inv_q * __ldg(winv);
+#pragma unroll 1
+        for (int half = 0; half < 2; ++half) {          // park dQn = dx1 + dq Wq
+            float a[32], r[32];
+            const int c0 = e.cb + half * 32;
+            tmem_ld32(tl + ACC_COL + c0, a);
+            warp_load32(sm.stage, e.lane, dx1 + wbase + c0, rv, r);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) a[i] = fmaf(a[i], f, r[i]);
+            tmem_st32(tl + ACC_COL + c0, a);
+        }
+        auto xhat = [&](int c0, float (&xh)[32]) {
+            warp_load32(sm.stage, e.lane, xin + wbase + c0, rv, xh);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) xh[i] = valid ? (xh[i] - mean) * rstd : 0.f;
+        };
+        ln_bwd_parked(sh, e, tl, ln1_w, rstd, valid, xhat);
+        flush_ln_partials(sh, ln_part + (size_t)blockIdx.x * 2 * D);
+    }
+    float cur = 1.0f;          // the parked values are (true value) * cur
+    const float* srcs[2] = {dk, dv};
+    float inv_a = 1.0f;
+#pragma unroll 1
+    for (int g = 0; g < 2; ++g) {
+        float v0[32], v1[32];
+        warp_load32(sm.stage, e.lane, srcs[g] + wbase + e.cb, rv, v0);
+        warp_load32(sm.stage, e.lane, srcs[g] + wbase + e.cb + 32, rv, v1);
+        float sc;
+        pow2_scale(row_max(sh, e, 2, absmax32(v1, absmax32(v0, 0.f))), sc, inv_a);
+        const float wi = __ldg(winv + 1 + g);
+        const float target = sc * (1.0f / wi);            // scale of this GEMM's products (powers of two: exact)
+        parked_scale(tl, e, target / cur);
+        cur = target;
+        put_a32(tl, e.cb, v0, sc);
+        put_a32(tl, e.cb + 32, v1, sc);
+        run_gemm_x3(sh, 0, sm.W, true, ph_mma, ph_w);
+        if (g == 0) load_w_bulk(sh, sm.W, img_vt);
+        inv_a *= wi;
+    }
+    {
+#pragma unroll 1
+        for (int half = 0; half < 2; ++half) {
+            float a[32];
+            const int c0 = e.cb + half * 32;
+            tmem_ld32(tl + ACC_COL + c0, a);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) a[i] *= inv_a;
+            warp_store32(sm.stage, e.lane, a, dxin + wbase + c0, rv);
+        }
+    }
+    teardown(sh, CHAIN_TMEM_COLS);
 }
 
 // ================================================================================================

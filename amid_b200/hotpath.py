@@ -33,7 +33,9 @@ class Config:
     isDR: bool
     drop_p: float = 0.5          # model_seq.py:335,350,355 (hard-coded in the reference)
     overlap_encoders: bool = True   # run the two domain encoders on two streams
-    precision: str = "fp32"      # GEMM stages: "fp32" exact CUDA-core tiles | "tf32" / "bf16" tcgen05 tiles, fp32 accumulate
+    # GEMM stages: "fp32" exact CUDA-core tiles | "x3" tcgen05 split-operand tiles at fp32-level accuracy (same
+    # tolerances as "fp32") | "tf32" / "bf16" single-pass tcgen05 tiles (reduced precision, stated tolerances)
+    precision: str = "fp32"
 
     @property
     def enc_len(self) -> int:    # model_seq.py:399-400
@@ -44,8 +46,10 @@ class Config:
         return ["predictModule"] + (["predict_ips", "predict_gfunc"] if self.isDR else [])
 
 
-_ENC_FWD = {"fp32": "amid_encoder_fwd", "tf32": "amid_encoder_fwd_tc", "bf16": "amid_encoder_fwd_bf16"}
-_ENC_BWD = {"fp32": "amid_encoder_bwd", "tf32": "amid_encoder_bwd_tc", "bf16": "amid_encoder_bwd_bf16"}
+_ENC_FWD = {"fp32": "amid_encoder_fwd", "x3": "amid_encoder_fwd_x3", "tf32": "amid_encoder_fwd_tc",
+            "bf16": "amid_encoder_fwd_bf16"}
+_ENC_BWD = {"fp32": "amid_encoder_bwd", "x3": "amid_encoder_bwd_x3", "tf32": "amid_encoder_bwd_tc",
+            "bf16": "amid_encoder_bwd_bf16"}
 
 
 class DistCtx:

@@ -145,6 +145,19 @@ int amid_encoder_bwd_bf16(const amid_encoder_tensors* P, const float* x0, const 
                           const float* enc_out, const float* d_enc, amid_encoder_tensors* G, float* dx0,
                           void* workspace, int64_t workspace_bytes, amid_stream_t stream);
 
+/* Split-operand variants (precision "x3", the parity-grade default): tcgen05 tensor cores at fp32-level accuracy.
+ * Chain GEMMs multiply FP16 pair pieces (row-scaled token tile held in tensor memory x pre-swizzled weight images
+ * fetched by bulk copy; products h0w0 + h1w0 + h0w1, relative error 2^-22), weight gradients multiply BF16 triples
+ * (six products), attention runs 3xTF32.  Same arguments, tensors and tolerances as amid_encoder_fwd / _bwd
+ * (model_seq.py:371-385, torch/nn/functional.py:5849-5856, 6630-6653). */
+int amid_encoder_fwd_x3(const amid_encoder_tensors* P, const float* x0, const uint32_t* tmask,
+                        int32_t B, int32_t L, const amid_dropout* drop, amid_encoder_saved* S,
+                        float* enc_out, void* workspace, int64_t workspace_bytes, amid_stream_t stream);
+int amid_encoder_bwd_x3(const amid_encoder_tensors* P, const float* x0, const uint32_t* tmask,
+                        int32_t B, int32_t L, const amid_dropout* drop, const amid_encoder_saved* S,
+                        const float* enc_out, const float* d_enc, amid_encoder_tensors* G, float* dx0,
+                        void* workspace, int64_t workspace_bytes, amid_stream_t stream);
+
 /* ---- a6: InterComp / InnerComp in closed form (model_seq.py:474-497 / 450-472) ----- */
 /* m[j] = max_{s,t} <a[j,s,:], b[j,t,:]>,  a,b: [B,n,128]  (the [bs,B,n,n] matmul+max of
  * model_seq.py:489-490 without its redundant outer axis). */

@@ -14,10 +14,29 @@ from helpers import (D, HID, O, T, assert_close, batch_from, build_model, grad_t
 
 pytestmark = pytest.mark.gpu
 
+# the two parity-grade modes: exact fp32 CUDA-core tiles, and the split-operand tcgen05 path (same tolerances)
+PRECS = ["fp32", "x3"]
+
 
 def _hp():
     from amid_b200 import hotpath
     return hotpath
+
+
+def _assert_trajectory(got, want, prec, lr, steps, msg):
+    """Parameters after `steps` Adam steps.  fp32 tiles: every element within 3e-5.  Split-operand tiles carry 22-bit
+    operands (the gradients agree to the same 2e-4 max|g| as fp32, checked separately); Adam divides by |g| + 1e-8, so
+    an element whose gradient is within ~1e-9 of zero turns that last-bit noise into a step of up to lr.  Such
+    elements may exceed 3e-5 -- at most 0.02 % of a tensor, never by more than steps * lr."""
+    got = got.detach().cpu().numpy() if torch.is_tensor(got) else np.asarray(got)
+    want = np.asarray(want)
+    diff = np.abs(got - want)
+    if prec == "fp32":
+        assert diff.max() <= 3e-5, (msg, diff.max())
+        return
+    bad = diff > 3e-5
+    assert bad.sum() <= max(1, int(2e-4 * diff.size)), (msg, int(bad.sum()), diff.size)
+    assert diff.max() <= steps * lr * 1.01, (msg, diff.max())
 
 
 # ------------------------------------------------------------------ a1 / a2: gather (bit-exact)
@@ -119,10 +138,11 @@ def test_embed_all_single_launch_bit_exact(B, L, C):
 
 
 # ------------------------------------------------------------------ whole forward vs reference goldens
-def test_forward_c1_golden():
+@pytest.mark.parametrize("prec", PRECS)
+def test_forward_c1_golden(prec):
     z = load("c1_fwd_eval.npz")
     P = make_params(11, int(z["V"]), D, 20, HID, 256)
-    m = build_model(P, int(z["V"]), 20, 256, ts2=0.4).eval()
+    m = build_model(P, int(z["V"]), 20, 256, ts2=0.4, precision=prec).eval()
     b = batch_from(z)
     with torch.no_grad():
         p1, p2 = run_model(m, b)
@@ -177,17 +197,18 @@ def test_rank_with_ties_bit_exact():
     assert len(evaluate.rank_of_positive(torch.empty(0, 5, device="cuda"), 0.0)) == 0
 
 
-def test_inc_and_tmask_goldens():
+@pytest.mark.parametrize("prec", PRECS)
+def test_inc_and_tmask_goldens(prec):
     z = load("inc_small.npz")
     P = make_params(16, int(z["V"]), D, 20, HID, 16, isInC=True)
-    m = build_model(P, int(z["V"]), 10, 16, isInC=True, ts1=0.07, ts2=0.07).eval()
+    m = build_model(P, int(z["V"]), 10, 16, isInC=True, ts1=0.07, ts2=0.07, precision=prec).eval()
     with torch.no_grad():
         p1, p2 = run_model(m, batch_from(z))
     assert_close(p1, z["p1"], 0, 2e-5)
     assert_close(p2, z["p2"], 0, 2e-5)
     z = load("tmask.npz")
     P = make_params(17, int(z["V"]), D, 20, HID, 16, zero_rows=(int(z["pad"]),), zero_pos=(0, 1, 2, 5))
-    m = build_model(P, int(z["V"]), 20, 16, ts2=0.07).eval()
+    m = build_model(P, int(z["V"]), 20, 16, ts2=0.07, precision=prec).eval()
     b = batch_from(z)
     probs, ctx = _hp().forward(m.param_dict(), m.cfg, b["i_node"], b["neg_samples"], b["seq_d1"], b["seq_d2"],
                                train=False)
@@ -196,13 +217,14 @@ def test_inc_and_tmask_goldens():
 
 
 # ------------------------------------------------------------------ train mode, dropout off: direct golden
-def test_train_p0_grads_and_trajectory_golden():
+@pytest.mark.parametrize("prec", PRECS)
+def test_train_p0_grads_and_trajectory_golden(prec):
     from amid_b200.engine import Trainer
     z = load("train_p0.npz")
     V = int(z["V"])
     P = make_params(18, V, D, 20, HID, 16)
     # (1) drop-in autograd path, unchanged-driver style: BCELoss + backward through the module
-    m = build_model(P, V, 20, 16, ts2=0.07, drop_p=0.0).train()
+    m = build_model(P, V, 20, 16, ts2=0.07, drop_p=0.0, precision=prec).train()
     b = batch_from(z, pre="b0_")
     p1, p2 = run_model(m, b)
     crit = torch.nn.BCELoss(reduction="none")
@@ -219,7 +241,7 @@ def test_train_p0_grads_and_trajectory_golden():
     assert_close(named["item_emb_layer.emb_item.weight"].grad, gt, 1e-3, grad_tol(gt))
     # (2) fused engine: 3 Adam steps, sparse table update with exact dense semantics
     for sparse in (True, False):
-        m2 = build_model(P, V, 20, 16, ts2=0.07, drop_p=0.0).train()
+        m2 = build_model(P, V, 20, 16, ts2=0.07, drop_p=0.0, precision=prec).train()
         tr = Trainer(m2, lr=5e-4, sparse_table=sparse)
         for step in range(3):
             losses = tr.step(batch_from(z, pre=f"b{step}_"))
@@ -228,15 +250,16 @@ def test_train_p0_grads_and_trajectory_golden():
         named = dict(m2.named_parameters())
         for k in z:
             if k.startswith("after3/"):
-                assert_close(named[k[7:]], z[k], 0, 3e-5, f"{k} sparse={sparse}")
+                _assert_trajectory(named[k[7:]], z[k], prec, 5e-4, 3, f"{k} sparse={sparse}")
 
 
-def test_dropin_unchanged_driver_loop_with_torch_adam():
+@pytest.mark.parametrize("prec", PRECS)
+def test_dropin_unchanged_driver_loop_with_torch_adam(prec):
     """The reference training loop body (train_sr.py:191-215) driving the drop-in module with
     torch.optim.Adam over model.parameters(): 3 steps must land on the reference's parameters."""
     z = load("train_p0.npz")
     V = int(z["V"])
-    model = build_model(make_params(18, V, D, 20, HID, 16), V, 20, 16, ts2=0.07, drop_p=0.0)
+    model = build_model(make_params(18, V, D, 20, HID, 16), V, 20, 16, ts2=0.07, drop_p=0.0, precision=prec)
     optimizer = torch.optim.Adam(model.parameters(), lr=5e-4)            # train_sr.py:480
     criterion_cls = torch.nn.BCELoss(reduction="none")                   # train_sr.py:184
     model.train()
@@ -269,7 +292,8 @@ def test_dropin_unchanged_driver_loop_with_torch_adam():
     assert sd["item_emb_layer.emb_item.weight"].shape == (V, D)
 
 
-def test_trainer_dr_two_phase_two_adams_vs_oracle():
+@pytest.mark.parametrize("prec", PRECS)
+def test_trainer_dr_two_phase_two_adams_vs_oracle(prec):
     """train_sr_dr.py: phase 1 (loss_cls + dr_e_w * loss_dr_e, `optimizer`) and phase 2 (loss_dr_r,
     `optimizer2` with lr * lr2) interleave on the same parameters, each Adam with its own state and
     dense semantics on the table."""
@@ -277,7 +301,7 @@ def test_trainer_dr_two_phase_two_adams_vs_oracle():
     B, L, C, V = 8, 12, 2, 53
     rng = np.random.default_rng(21)
     P = make_params(33, V, D, L, HID, B, isDR=True)
-    m = build_model(P, V, L, B, ts2=0.3, isDR=True, drop_p=0.0).train()
+    m = build_model(P, V, L, B, ts2=0.3, isDR=True, drop_p=0.0, precision=prec).train()
     tr = Trainer(m, lr=5e-4, lr2=0.5, dr_e_w=0.01)
     Po = {k: v.clone().requires_grad_(True) for k, v in P.items()}
     st = [{k: (torch.zeros_like(v), torch.zeros_like(v)) for k, v in Po.items()} for _ in range(2)]
@@ -311,13 +335,14 @@ def test_trainer_dr_two_phase_two_adams_vs_oracle():
 
 
 # ------------------------------------------------------------------ train mode WITH dropout: oracle + our masks
+@pytest.mark.parametrize("prec", PRECS)
 @pytest.mark.parametrize("B,L,C,isDR", [(6, 9, 2, False), (5, 20, 3, True)])
-def test_train_dropout_vs_oracle_with_exported_masks(B, L, C, isDR):
+def test_train_dropout_vs_oracle_with_exported_masks(B, L, C, isDR, prec):
     hp = _hp()
     rng = np.random.default_rng(B * 100 + L)
     V = 97
     P = make_params(31, V, D, L, HID, B, isDR=isDR)
-    m = build_model(P, V, L, B, ts2=0.2, isDR=isDR).train()
+    m = build_model(P, V, L, B, ts2=0.2, isDR=isDR, precision=prec).train()
     b = to_cuda(random_batch(rng, B, L, C, V))
     seed = 1234567
     probs, ctx = hp.forward(m.param_dict(), m.cfg, b["i_node"], b["neg_samples"], b["seq_d1"], b["seq_d2"],
@@ -363,9 +388,10 @@ def test_train_dropout_vs_oracle_with_exported_masks(B, L, C, isDR):
 
 
 # ------------------------------------------------------------------ eval forward vs oracle, ragged shapes
+@pytest.mark.parametrize("prec", PRECS)
 @pytest.mark.parametrize("B,L,C,isInC,isItC", [(1, 1, 2, False, False), (7, 13, 5, False, True), (3, 130, 2, False, True),
                                               (4, 6, 4, True, True), (9, 200, 2, False, True), (2, 37, 50, True, False)])
-def test_forward_vs_oracle_shapes(B, L, C, isInC, isItC):
+def test_forward_vs_oracle_shapes(B, L, C, isInC, isItC, prec):
     rng = np.random.default_rng(B * 1000 + L)
     V = 211
     Le = 2 * L if isInC else L
@@ -377,7 +403,7 @@ def test_forward_vs_oracle_shapes(B, L, C, isInC, isItC):
         pj = torch.softmax(O.mim_scores(col["enc1"], col["enc2"]), 0)
         if (pj - 0.3).abs().min() < 1e-4:
             pytest.skip("gate margin too small")
-    m = build_model(P, V, L, B, isInC=isInC, isItC=isItC, ts1=0.3, ts2=0.3).eval()
+    m = build_model(P, V, L, B, isInC=isInC, isItC=isItC, ts1=0.3, ts2=0.3, precision=prec).eval()
     with torch.no_grad():
         p1, p2 = run_model(m, to_cuda(b))
     assert_close(p1.reshape(B, C), outs[0], 0, 3e-5)
@@ -617,9 +643,10 @@ def test_fast_train_epoch_equals_manual_steps():
 
 
 # ------------------------------------------------------------------ flag matrix, training direction
+@pytest.mark.parametrize("prec", PRECS)
 @pytest.mark.parametrize("isInC,isItC,isDR", [(True, True, False), (True, False, False), (False, False, False),
                                               (True, True, True)])
-def test_flag_matrix_train_grads_vs_oracle(isInC, isItC, isDR):
+def test_flag_matrix_train_grads_vs_oracle(isInC, isItC, isDR, prec):
     """InnerComp in front of the encoders (model_seq.py:399-402, 422-424: positional table and attention over 2L),
     with / without InterComp, with / without the DR heads: probabilities, loss and every gradient (dropout off)."""
     hp = _hp()
@@ -628,7 +655,7 @@ def test_flag_matrix_train_grads_vs_oracle(isInC, isItC, isDR):
     rng = np.random.default_rng(17 + 2 * isInC + isItC)
     P = make_params(61, V, D, Le, HID, B, isInC=isInC, isItC=isItC, isDR=isDR)
     ts = 0.12
-    m = build_model(P, V, L, B, isInC=isInC, isItC=isItC, ts1=ts, ts2=ts, isDR=isDR, drop_p=0.0).train()
+    m = build_model(P, V, L, B, isInC=isInC, isItC=isItC, ts1=ts, ts2=ts, isDR=isDR, drop_p=0.0, precision=prec).train()
     b = to_cuda(random_batch(rng, B, L, C, V))
     probs, ctx = hp.forward(m.param_dict(), m.cfg, b["i_node"], b["neg_samples"], b["seq_d1"], b["seq_d2"], train=True, seed=1)
     Po = {k: v.clone().requires_grad_(True) for k, v in P.items()}
@@ -659,14 +686,15 @@ def test_flag_matrix_train_grads_vs_oracle(isInC, isItC, isDR):
             assert_close(G[k], v.grad, 1e-3, grad_tol(v.grad), k)
 
 
-def test_inc_itc_dr_training_direction_reference_golden():
+@pytest.mark.parametrize("prec", PRECS)
+def test_inc_itc_dr_training_direction_reference_golden(prec):
     """The same fixture that pins the oracle (tests/golden/make_inc_train_golden.py): InnerComp + InterComp + DR heads
     in training direction, executed by the reference -- outputs, phase-1 losses and gradients through the C ABI."""
     hp = _hp()
     z = load("inc_train_small.npz")
     V, ts, B, L = int(z["V"]), float(z["ts"]), 8, 6
     P = make_params(19, V, D, 2 * L, HID, B, isInC=True, isItC=True, isDR=True)
-    m = build_model(P, V, L, B, isInC=True, isItC=True, ts1=ts, ts2=ts, isDR=True, drop_p=0.0).train()
+    m = build_model(P, V, L, B, isInC=True, isItC=True, ts1=ts, ts2=ts, isDR=True, drop_p=0.0, precision=prec).train()
     b = batch_from(z)
     probs, ctx = hp.forward(m.param_dict(), m.cfg, b["i_node"], b["neg_samples"], b["seq_d1"], b["seq_d2"], train=True, seed=3)
     for i, n in enumerate(("p1", "p2", "ips1", "ips2", "g1", "g2")):
