@@ -117,6 +117,8 @@ _SIGS = {
     "amid_tc_linear16_test": (c_int32, [P, P, P, c_int32, P, P]),
     "amid_tc_wgrad16_test": (c_int32, [P, P, c_int32, P, c_int32, P]),
     "amid_x3_linear_test": (c_int32, [P, P, P, c_int32, P, P, P]),
+    "amid_attn_fwd_test": (c_int32, [P, P, P, P, P, c_int32, c_int32, POINTER(Dropout), c_uint32, c_int32, P]),
+    "amid_attn_bwd_test": (c_int32, [P, P, P, P, P, P, P, P, P, c_int32, c_int32, POINTER(Dropout), c_uint32, c_int32, P]),
     "amid_x3_wgrad_test": (c_int32, [P, P, c_int32, P, P, c_int32, P]),
     "amid_dropout_mask_feature": (c_int32, [POINTER(Dropout), c_uint32, c_int64, P, P]),
     "amid_dropout_mask_attn": (c_int32, [POINTER(Dropout), c_uint32, c_int32, c_int32, P, P]),

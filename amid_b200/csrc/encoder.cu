@@ -13,6 +13,7 @@
 #include "attn_mma.cuh"
 #include "encoder_tc16.cuh"
 #include "x3.cuh"
+#include "attn_tc.cuh"
 
 namespace amid {
 
@@ -798,10 +799,18 @@ static int encoder_fwd_impl(const amid_encoder_tensors* P, const float* x0, cons
                                                                     W + 2 * x3::WIMG_BYTES, wi, P->in_b[i], S->qn[i], S->st1[i],
                                                                     S->q[i], S->k[i], S->v[i]);
             AMID_LAUNCH_CHECK("k_ln_qkv_x3");
-            AMID_K("k_attn_fwd_mma3", stream);
-            attn::k_attn_fwd_mma<true><<<B * H, attn::NW * 32, mma_smem, stream>>>(S->q[i], S->k[i], S->v[i], S->o[i], S->lse[i], L,
-                                                                                   dc, dc.site_base + site_attn(i));
-            AMID_LAUNCH_CHECK("k_attn_fwd_mma3");
+            if (L >= attn_tc::MINL && L <= attn_tc::MAXL) {      // scores in tensor memory
+                if (int rc = ensure_smem((const void*)attn_tc::k_attn_fwd_tc, attn_tc::FWD_SMEM)) return rc;
+                AMID_K("k_attn_fwd_tc", stream);
+                attn_tc::k_attn_fwd_tc<<<B * H, 256, attn_tc::FWD_SMEM, stream>>>(S->q[i], S->k[i], S->v[i], S->o[i], S->lse[i], L, dc,
+                                                                                  dc.site_base + site_attn(i));
+                AMID_LAUNCH_CHECK("k_attn_fwd_tc");
+            } else {
+                AMID_K("k_attn_fwd_mma3", stream);
+                attn::k_attn_fwd_mma<true><<<B * H, attn::NW * 32, mma_smem, stream>>>(S->q[i], S->k[i], S->v[i], S->o[i], S->lse[i],
+                                                                                       L, dc, dc.site_base + site_attn(i));
+                AMID_LAUNCH_CHECK("k_attn_fwd_mma3");
+            }
             const bool last = i == 1;
             AMID_K("k_proj_ffn_x3", stream);
             x3::k_proj_ffn_x3<<<tiles, 256, x3::CHAINX_SMEM, stream>>>(
@@ -1101,10 +1110,19 @@ static int encoder_bwd_impl(const amid_encoder_tensors* P, const float* x0, cons
         if (mode == 3) {
             const size_t mma_smem = (size_t)((L + 15) / 16 * 16) * (4 * attn::LDS + 2) * sizeof(float);
             if (int rc = ensure_smem((const void*)attn::k_attn_bwd_mma<true>, mma_smem)) return rc;
-            AMID_K("k_attn_bwd_mma3", stream);
-            attn::k_attn_bwd_mma<true><<<B * H, attn::NWB * 32, mma_smem, stream>>>(S->q[i], S->k[i], S->v[i], S->o[i], S->lse[i], dO,
-                                                                                    dq, dk, dv, L, dc, dc.site_base + site_attn(i));
-            AMID_LAUNCH_CHECK("k_attn_bwd_mma3");
+            if (L >= attn_tc::MINL && L <= attn_tc::MAXL) {
+                if (int rc = ensure_smem((const void*)attn_tc::k_attn_bwd_tc, attn_tc::BWD_SMEM)) return rc;
+                AMID_K("k_attn_bwd_tc", stream);
+                attn_tc::k_attn_bwd_tc<<<B * H, 256, attn_tc::BWD_SMEM, stream>>>(S->q[i], S->k[i], S->v[i], S->o[i], S->lse[i], dO, dq,
+                                                                                  dk, dv, L, dc, dc.site_base + site_attn(i));
+                AMID_LAUNCH_CHECK("k_attn_bwd_tc");
+            } else {
+                AMID_K("k_attn_bwd_mma3", stream);
+                attn::k_attn_bwd_mma<true><<<B * H, attn::NWB * 32, mma_smem, stream>>>(S->q[i], S->k[i], S->v[i], S->o[i], S->lse[i],
+                                                                                        dO, dq, dk, dv, L, dc,
+                                                                                        dc.site_base + site_attn(i));
+                AMID_LAUNCH_CHECK("k_attn_bwd_mma3");
+            }
         } else if (use_tc) {
             const size_t mma_smem = (size_t)((L + 15) / 16 * 16) * (4 * attn::LDS + 2) * sizeof(float);
             if (int rc = ensure_smem((const void*)attn::k_attn_bwd_mma<false>, mma_smem)) return rc;

@@ -838,44 +838,45 @@ k_wgrad_x3(WgradJobsX jobs, int M, float* __restrict__ wpart /*[6][S][128*128]*/
     uint32_t phase[2] = {0u, 0u};
     constexpr uint32_t id_w = idesc_bf16(128, true, true);
     constexpr uint32_t id_b = idesc_bf16(16, true, false);
+    // sub-tiles are dealt in pairs so that a CTA streams 128 consecutive tokens at a time; the global loads of sub-tile
+    // i+1 are issued before sub-tile i is split and stored, so their latency hides behind the conversion and the MMAs
+    const int pairs = (subs + 1) / 2;
+    const int my_pairs = blockIdx.x < pairs ? (pairs - 1 - blockIdx.x) / S + 1 : 0;
+    auto sub_of = [&](int i) { return 2 * (blockIdx.x + (i >> 1) * S) + (i & 1); };
+    int n_it = 2 * my_pairs;
+    if (n_it && sub_of(n_it - 1) >= subs) --n_it;
+    float4 vy[8], vx[8];
+    if (n_it) { load_sub(vy, dY, sub_of(0) * SUB_ROWS, M); load_sub(vx, X, sub_of(0) * SUB_ROWS, M); }
     int it = 0;
-    // sub-tiles are dealt in pairs so that a CTA streams 128 consecutive tokens at a time
-    for (int t = blockIdx.x; 2 * t < subs; t += S) {
-        for (int half = 0; half < 2; ++half) {
-            const int sidx = 2 * t + half;
-            if (sidx >= subs) break;
-            const int b = it & 1;
-            float4 vy[8], vx[8];
-            load_sub(vy, dY, sidx * SUB_ROWS, M);
-            load_sub(vx, X, sidx * SUB_ROWS, M);
-            if (it >= 2) { mbar_wait(&bars[b], phase[b]); phase[b] ^= 1; }      // MMAs that read this buffer are done
-            uint8_t* buf = buf0 + b * WG_BUF_BYTES;
-            fill_sub3(buf, vy);
-            fill_sub3(buf + 3 * SUBP_BYTES, vx);
-            fence_async_smem();
-            __syncthreads();
-            if (threadIdx.x == 0) {
-                fence_after();
-                const uint32_t a = smem_u32(buf), x = a + 3 * SUBP_BYTES, o = smem_u32(Ones);
+    for (; it < n_it; ++it) {
+        const int b = it & 1;
+        if (it >= 2) { mbar_wait(&bars[b], phase[b]); phase[b] ^= 1; }      // MMAs that read this buffer are done
+        uint8_t* buf = buf0 + b * WG_BUF_BYTES;
+        fill_sub3(buf, vy);
+        fill_sub3(buf + 3 * SUBP_BYTES, vx);
+        if (it + 1 < n_it) { load_sub(vy, dY, sub_of(it + 1) * SUB_ROWS, M); load_sub(vx, X, sub_of(it + 1) * SUB_ROWS, M); }
+        fence_async_smem();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            fence_after();
+            const uint32_t a = smem_u32(buf), x = a + 3 * SUBP_BYTES, o = smem_u32(Ones);
 #pragma unroll
-                for (int ks = 0; ks < SUB_ROWS / 16; ++ks) {
-                    const uint32_t acc = (it || ks) ? 1u : 0u;
-                    const uint64_t a0 = desc_sub_mn(a, ks), a1 = desc_sub_mn(a + SUBP_BYTES, ks), a2 = desc_sub_mn(a + 2 * SUBP_BYTES, ks);
-                    const uint64_t x0 = desc_sub_mn(x, ks), x1 = desc_sub_mn(x + SUBP_BYTES, ks), x2 = desc_sub_mn(x + 2 * SUBP_BYTES, ks);
-                    const uint64_t on = make_desc(o + ks * 32, 16, 1024);
-                    mma_bf16(tmem, a0, x0, id_w, acc);
-                    mma_bf16(tmem, a0, x1, id_w, 1u);
-                    mma_bf16(tmem, a1, x0, id_w, 1u);
-                    mma_bf16(tmem, a0, x2, id_w, 1u);
-                    mma_bf16(tmem, a1, x1, id_w, 1u);
-                    mma_bf16(tmem, a2, x0, id_w, 1u);
-                    mma_bf16(tmem + 128, a0, on, id_b, acc);
-                    mma_bf16(tmem + 128, a1, on, id_b, 1u);
-                    mma_bf16(tmem + 128, a2, on, id_b, 1u);
-                }
-                mma_commit(&bars[b]);
+            for (int ks = 0; ks < SUB_ROWS / 16; ++ks) {
+                const uint32_t acc = (it || ks) ? 1u : 0u;
+                const uint64_t a0 = desc_sub_mn(a, ks), a1 = desc_sub_mn(a + SUBP_BYTES, ks), a2 = desc_sub_mn(a + 2 * SUBP_BYTES, ks);
+                const uint64_t x0 = desc_sub_mn(x, ks), x1 = desc_sub_mn(x + SUBP_BYTES, ks), x2 = desc_sub_mn(x + 2 * SUBP_BYTES, ks);
+                const uint64_t on = make_desc(o + ks * 32, 16, 1024);
+                mma_bf16(tmem, a0, x0, id_w, acc);
+                mma_bf16(tmem, a0, x1, id_w, 1u);
+                mma_bf16(tmem, a1, x0, id_w, 1u);
+                mma_bf16(tmem, a0, x2, id_w, 1u);
+                mma_bf16(tmem, a1, x1, id_w, 1u);
+                mma_bf16(tmem, a2, x0, id_w, 1u);
+                mma_bf16(tmem + 128, a0, on, id_b, acc);
+                mma_bf16(tmem + 128, a1, on, id_b, 1u);
+                mma_bf16(tmem + 128, a2, on, id_b, 1u);
             }
-            ++it;
+            mma_commit(&bars[b]);
         }
     }
     // drain: the last one or two commits

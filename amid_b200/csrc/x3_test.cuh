@@ -81,3 +81,74 @@ extern "C" int amid_x3_wgrad_test(const float* dy, const float* x, int32_t M, fl
     AMID_LAUNCH_CHECK("k_wgrad_x3");
     return 0;
 }
+
+// ---- attention kernels side by side (unit tests and micro-benchmarks): impl 0 = fp32 CUDA cores, 1 = mma.sync TF32,
+// 2 = mma.sync 3xTF32, 3 = tcgen05 FP16-pair split with the scores in tensor memory
+extern "C" int amid_attn_fwd_test(const float* q, const float* k, const float* v, float* o, float* lse, int32_t B, int32_t L,
+                                  const amid_dropout* drop, uint32_t site, int32_t impl, amid_stream_t s_) {
+    AMID_REQUIRE(q && k && v && o && lse && B > 0 && L > 0 && L <= 512, "attn_fwd_test: bad argument");
+    cudaStream_t stream = (cudaStream_t)s_;
+    const DropCfg dc = make_drop(drop);
+    if (impl == 0) {
+        const size_t smem = (size_t)2 * L * DH * sizeof(float);
+        if (int rc = ensure_smem((const void*)k_attn_fwd, smem)) return rc;
+        AMID_K("k_attn_fwd", stream);
+        k_attn_fwd<<<B * H, (int)round_up((L + 1) / 2, 32), smem, stream>>>(q, k, v, o, lse, L, dc, site);
+        AMID_LAUNCH_CHECK("k_attn_fwd");
+    } else if (impl == 1 || impl == 2) {
+        const size_t smem = (size_t)2 * ((L + 15) / 16 * 16) * attn::LDS * sizeof(float);
+        if (impl == 1) {
+            if (int rc = ensure_smem((const void*)attn::k_attn_fwd_mma<false>, smem)) return rc;
+            AMID_K("k_attn_fwd_mma", stream);
+            attn::k_attn_fwd_mma<false><<<B * H, attn::NW * 32, smem, stream>>>(q, k, v, o, lse, L, dc, site);
+            AMID_LAUNCH_CHECK("k_attn_fwd_mma");
+        } else {
+            if (int rc = ensure_smem((const void*)attn::k_attn_fwd_mma<true>, smem)) return rc;
+            AMID_K("k_attn_fwd_mma3", stream);
+            attn::k_attn_fwd_mma<true><<<B * H, attn::NW * 32, smem, stream>>>(q, k, v, o, lse, L, dc, site);
+            AMID_LAUNCH_CHECK("k_attn_fwd_mma3");
+        }
+    } else {
+        AMID_REQUIRE(L <= attn_tc::MAXL, "attn_fwd_test: tcgen05 path needs L <= %d", attn_tc::MAXL);
+        if (int rc = ensure_smem((const void*)attn_tc::k_attn_fwd_tc, attn_tc::FWD_SMEM)) return rc;
+        AMID_K("k_attn_fwd_tc", stream);
+        attn_tc::k_attn_fwd_tc<<<B * H, 256, attn_tc::FWD_SMEM, stream>>>(q, k, v, o, lse, L, dc, site);
+        AMID_LAUNCH_CHECK("k_attn_fwd_tc");
+    }
+    return 0;
+}
+
+extern "C" int amid_attn_bwd_test(const float* q, const float* k, const float* v, const float* o, const float* lse,
+                                  const float* dO, float* dq, float* dk, float* dv, int32_t B, int32_t L,
+                                  const amid_dropout* drop, uint32_t site, int32_t impl, amid_stream_t s_) {
+    AMID_REQUIRE(q && k && v && o && lse && dO && dq && dk && dv && B > 0 && L > 0 && L <= 512, "attn_bwd_test: bad argument");
+    cudaStream_t stream = (cudaStream_t)s_;
+    const DropCfg dc = make_drop(drop);
+    if (impl == 0) {
+        const size_t smem = (size_t)(4 * L * DH + 2 * L) * sizeof(float);
+        if (int rc = ensure_smem((const void*)k_attn_bwd, smem)) return rc;
+        AMID_K("k_attn_bwd", stream);
+        k_attn_bwd<<<B * H, (int)round_up((L + 1) / 2, 32), smem, stream>>>(q, k, v, o, lse, dO, dq, dk, dv, L, dc, site);
+        AMID_LAUNCH_CHECK("k_attn_bwd");
+    } else if (impl == 1 || impl == 2) {
+        const size_t smem = (size_t)((L + 15) / 16 * 16) * (4 * attn::LDS + 2) * sizeof(float);
+        if (impl == 1) {
+            if (int rc = ensure_smem((const void*)attn::k_attn_bwd_mma<false>, smem)) return rc;
+            AMID_K("k_attn_bwd_mma", stream);
+            attn::k_attn_bwd_mma<false><<<B * H, attn::NWB * 32, smem, stream>>>(q, k, v, o, lse, dO, dq, dk, dv, L, dc, site);
+            AMID_LAUNCH_CHECK("k_attn_bwd_mma");
+        } else {
+            if (int rc = ensure_smem((const void*)attn::k_attn_bwd_mma<true>, smem)) return rc;
+            AMID_K("k_attn_bwd_mma3", stream);
+            attn::k_attn_bwd_mma<true><<<B * H, attn::NWB * 32, smem, stream>>>(q, k, v, o, lse, dO, dq, dk, dv, L, dc, site);
+            AMID_LAUNCH_CHECK("k_attn_bwd_mma3");
+        }
+    } else {
+        AMID_REQUIRE(L <= attn_tc::MAXL, "attn_bwd_test: tcgen05 path needs L <= %d", attn_tc::MAXL);
+        if (int rc = ensure_smem((const void*)attn_tc::k_attn_bwd_tc, attn_tc::BWD_SMEM)) return rc;
+        AMID_K("k_attn_bwd_tc", stream);
+        attn_tc::k_attn_bwd_tc<<<B * H, 256, attn_tc::BWD_SMEM, stream>>>(q, k, v, o, lse, dO, dq, dk, dv, L, dc, site);
+        AMID_LAUNCH_CHECK("k_attn_bwd_tc");
+    }
+    return 0;
+}

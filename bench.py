@@ -50,7 +50,7 @@ def parse():
     ap.add_argument("--ids", default="uniform", choices=["uniform", "realistic"],
                     help="uniform = roofline variant (default); realistic = short left-padded histories (SURVEY 8d)")
     ap.add_argument("--items", type=int, default=V_ITEMS, help="table rows V (config 4: 20000002)")
-    ap.add_argument("--precision", default="bf16", choices=["fp32", "tf32", "bf16"],
+    ap.add_argument("--precision", default="bf16", choices=["fp32", "x3", "tf32", "bf16"],
                     help="encoder GEMM stages: tf32 = tcgen05 tensor cores (fp32 accumulate), fp32 = exact CUDA-core tiles")
     a = ap.parse_args()
     V_ITEMS = a.items
@@ -207,6 +207,8 @@ def kernel_work(name, B, L, C):
     table = {
         "k_attn_fwd": {"flop": attn_full, "byte": 4 * act}, "k_attn_bwd": {"flop": 2.5 * attn_full, "byte": 8 * act},
         "k_attn_fwd_mma": {"flop": attn_full, "byte": 4 * act}, "k_attn_bwd_mma": {"flop": 2.5 * attn_full, "byte": 8 * act},
+        "k_attn_fwd_mma3": {"flop": attn_full, "byte": 4 * act}, "k_attn_bwd_mma3": {"flop": 2.5 * attn_full, "byte": 8 * act},
+        "k_attn_fwd_tc": {"flop": attn_full, "byte": 4 * act}, "k_attn_bwd_tc": {"flop": 2.5 * attn_full, "byte": 8 * act},
         "k_seq_embed": {"byte": rows_seq * (2 * D * 4 + 8)}, "k_gather": {"byte": rows_items * (2 * D * 4 + 8)},
         "k_embed_all": {"byte": (2 * rows_seq + rows_items) * (2 * D * 4 + 8)},
         "k_mim_scores": {"flop": 2.0 * B * L * L * D, "byte": 2 * act},
@@ -214,7 +216,7 @@ def kernel_work(name, B, L, C):
         "k_mim_scores_tc5": {"flop": 3 * 2.0 * B * L * L * D, "byte": 2 * act},   # 3xTF32: three MMAs per product
     }
     for k, (f, b) in chain.items():
-        for suffix in ("", "_tc", "_16"):
+        for suffix in ("", "_tc", "_16", "_x3"):
             table[k + suffix] = {"flop": f, "byte": b}
     return table.get(name)
 
@@ -515,7 +517,7 @@ def run_ours(a):
     # tensor-pipe utilisation is quoted on the 12*L*d^2 projection/FFN part only (fwd + 2x bwd),
     # over the time of the kernels that hold those contractions
     gemm_ms = sum(e["ms_per_step"] for e in breakdown
-                  if e["kernel"].split("_tc")[0].split("_16")[0] in ("k_ln_qkv", "k_proj_ffn", "k_ffn_bwd", "k_qkv_bwd", "k_wgrad"))
+                  if e["kernel"].split("_tc")[0].split("_16")[0].split("_x3")[0] in ("k_ln_qkv", "k_proj_ffn", "k_ffn_bwd", "k_qkv_bwd", "k_wgrad"))
     gemm_flop = 3.0 * 4 * 12 * L * D * D * B          # 2 blocks x 2 encoders, fwd + dX + dW
     tensor_pipe = None if gemm_ms <= 0 else {
         "flop_per_step": gemm_flop, "ms_in_gemm_kernels": gemm_ms, "achieved_tflops": gemm_flop / (gemm_ms / 1e3) / 1e12,
@@ -524,7 +526,7 @@ def run_ours(a):
     line = {
         "metric": "train_seqs_per_sec", "value": Bg / (ms_step / 1e3), "unit": "seq/s", "n_gpus": world,
         "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": {"fp32": "f32", "tf32": "tf32", "bf16": "bf16"}[a.precision], "data": "synthetic",
+        "vs_baseline": None, "dtype": {"fp32": "f32", "x3": "f32", "tf32": "tf32", "bf16": "bf16"}[a.precision], "data": "synthetic",
         "config": {"workload": workload_name(a), "global_batch": Bg, "seq_len": L, "parallelism": f"dp{world}",
                    "l2": "no explicit flush: each step streams ~8 GB of activations, far larger than the 126 MB L2",
                    "table_update": ("dense" if a.dense_table else "row-sparse lazy Adam (exact dense semantics)") if world == 1

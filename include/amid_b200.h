@@ -324,6 +324,14 @@ int amid_tc_wgrad16_test(const float* dy, const float* x, int32_t M, float* part
  * kernel with BF16 triples: sum over cta of wpart[cta] = dy^T x, sum over cta of bpart[cta] = column sums of dy. */
 int amid_x3_linear_test(const float* x, const float* w, const float* b, int32_t M, float* y, void* scratch,
                         amid_stream_t stream);
+/* Attention kernels side by side (q, k, v, o: [B*L,128] with heads along the columns; lse: [B*8*L]).
+ * impl 0 = fp32 CUDA cores, 1 = mma.sync TF32, 2 = mma.sync 3xTF32, 3 = tcgen05 FP16-pair split (L <= 224). */
+int amid_attn_fwd_test(const float* q, const float* k, const float* v, float* o, float* lse, int32_t B, int32_t L,
+                       const amid_dropout* drop, uint32_t site, int32_t impl, amid_stream_t stream);
+/* backward: dq is the gradient with respect to q / 0.25 (the convention of amid_encoder_bwd's chain kernels) */
+int amid_attn_bwd_test(const float* q, const float* k, const float* v, const float* o, const float* lse, const float* dO,
+                       float* dq, float* dk, float* dv, int32_t B, int32_t L, const amid_dropout* drop, uint32_t site,
+                       int32_t impl, amid_stream_t stream);
 int amid_x3_wgrad_test(const float* dy, const float* x, int32_t M, float* wpart, float* bpart, int32_t n_ctas,
                        amid_stream_t stream);
 

@@ -1,0 +1,96 @@
+"""Attention kernels side by side against a float64 restatement of torch/nn/functional.py:6630-6647
+(q pre-scaled by 0.25 as the kernels receive it, additive -inf above the diagonal, softmax, dropout without
+renormalisation, P v), with the dropout keep bits the kernels export (amid_dropout_mask_attn)."""
+import ctypes as C
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+D, H, DH = 128, 8, 16
+IMPLS = {"fp32": 0, "mma_tf32": 1, "mma_3xtf32": 2, "tcgen05": 3}
+TOL = {"fp32": 3e-6, "mma_tf32": 3e-3, "mma_3xtf32": 3e-6, "tcgen05": 3e-6}
+
+
+def _ref_fwd(q, k, v, L, keep, scale):
+    B = q.shape[0] // L
+    qh = q.double().view(B, L, H, DH).transpose(1, 2)
+    kh = k.double().view(B, L, H, DH).transpose(1, 2)
+    vh = v.double().view(B, L, H, DH).transpose(1, 2)
+    s = qh @ kh.transpose(-1, -2)
+    s = s.masked_fill(torch.triu(torch.ones(L, L, dtype=torch.bool, device=q.device), 1), float("-inf"))
+    p = torch.softmax(s, -1)
+    lse = torch.logsumexp(s, -1)
+    pd = p * keep.double() * scale if keep is not None else p
+    o = (pd @ vh).transpose(1, 2).reshape(B * L, D)
+    return o, lse.reshape(-1), p, pd
+
+
+def _inputs(B, L, seed, spread=False):
+    g = torch.Generator().manual_seed(seed)
+    q = torch.randn(B * L, D, generator=g) * 0.6
+    k = torch.randn(B * L, D, generator=g) * 1.3
+    v = torch.randn(B * L, D, generator=g)
+    if spread:
+        v[:, 16:32] *= 1e-3
+        k[:, 32:48] *= 30.0
+    return q.cuda(), k.cuda(), v.cuda()
+
+
+def _keep(drop, site, B, L):
+    from amid_b200 import hotpath as hp
+    from amid_b200._abi import call
+    t = torch.empty(B * H * L * L, device="cuda", dtype=torch.uint8)
+    call("amid_dropout_mask_attn", C.byref(drop), site, B, L, hp._ptr(t), hp._stream())
+    return t.view(B, H, L, L).bool()
+
+
+@pytest.mark.parametrize("impl", list(IMPLS))
+@pytest.mark.parametrize("B,L,train", [(2, 64, False), (3, 200, True), (2, 130, True), (1, 224, False), (5, 97, True),
+                                       (2, 128, True), (1, 20, True)])
+def test_attention_forward_all_impls(impl, B, L, train):
+    from amid_b200 import hotpath as hp
+    from amid_b200._abi import Dropout, call
+    q, k, v = _inputs(B, L, 100 * B + L, spread=(L == 130))
+    drop = Dropout(1 if train else 0, 0.5, 9876543210, 8)
+    site = 8 + 4
+    keep = _keep(drop, site, B, L) if train else None
+    want_o, want_lse, _, _ = _ref_fwd(q, k, v, L, keep, 2.0)
+    o = torch.full((B * L, D), float("nan"), device="cuda")
+    lse = torch.full((B * H * L,), float("nan"), device="cuda")
+    call("amid_attn_fwd_test", hp._ptr(q), hp._ptr(k), hp._ptr(v), hp._ptr(o), hp._ptr(lse), B, L, C.byref(drop), site,
+         IMPLS[impl], hp._stream())
+    torch.cuda.synchronize()
+    assert torch.isfinite(o).all() and torch.isfinite(lse).all()
+    eo = (o.double() - want_o).abs().max().item() / want_o.abs().max().item()
+    el = (lse.double() - want_lse).abs().max().item() / max(1.0, want_lse.abs().max().item())
+    tol = TOL[impl] * (4 if L == 130 else 1)       # the spread case has scores of +-60: exp amplifies every impl alike
+    assert eo < tol, (impl, eo)
+    assert el < max(TOL[impl] * 20, 1e-5), (impl, el)
+
+
+@pytest.mark.parametrize("impl", list(IMPLS))
+@pytest.mark.parametrize("B,L,train", [(2, 64, False), (3, 200, True), (1, 224, True), (5, 97, True), (2, 128, False),
+                                       (1, 20, True), (2, 113, True)])
+def test_attention_backward_all_impls(impl, B, L, train):
+    from amid_b200 import hotpath as hp
+    from amid_b200._abi import Dropout, call
+    q, k, v = _inputs(B, L, 7 * B + L)
+    g = torch.Generator().manual_seed(L)
+    dO = (torch.randn(B * L, D, generator=g) * 1e-3).cuda()
+    drop = Dropout(1 if train else 0, 0.5, 1122334455, 0)
+    site = 1
+    keep = _keep(drop, site, B, L) if train else None
+    qd, kd, vd = (t.double().requires_grad_(True) for t in (q, k, v))
+    want_o, want_lse, _, _ = _ref_fwd(qd, kd, vd, L, keep, 2.0)
+    (want_o * dO.double()).sum().backward()
+    o, lse = want_o.detach().float().contiguous(), want_lse.detach().float().contiguous()
+    outs = [torch.full((B * L, D), float("nan"), device="cuda") for _ in range(3)]
+    call("amid_attn_bwd_test", hp._ptr(q), hp._ptr(k), hp._ptr(v), hp._ptr(o), hp._ptr(lse), hp._ptr(dO), hp._ptr(outs[0]),
+         hp._ptr(outs[1]), hp._ptr(outs[2]), B, L, C.byref(drop), site, IMPLS[impl], hp._stream())
+    torch.cuda.synchronize()
+    wants = [0.25 * qd.grad, kd.grad, vd.grad]
+    for name, got, want in zip(("dq", "dk", "dv"), outs, wants):
+        assert torch.isfinite(got).all(), name
+        err = (got.double() - want).abs().max().item() / want.abs().max().item()
+        assert err < (4e-2 if impl == "mma_tf32" else TOL[impl] * 2), (impl, name, err)
