@@ -287,7 +287,7 @@ def test_dropin_unchanged_driver_loop_with_torch_adam(prec):
     named = dict(model.named_parameters())
     for k in z:
         if k.startswith("after3/"):
-            assert_close(named[k[7:]], z[k], 0, 3e-5, k)
+            _assert_trajectory(named[k[7:]], z[k], prec, 5e-4, 3, k)
     sd = model.state_dict()
     assert sd["item_emb_layer.emb_item.weight"].shape == (V, D)
 
