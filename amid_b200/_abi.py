@@ -20,7 +20,7 @@ class AmidError(RuntimeError):
 
 
 class Dropout(C.Structure):
-    _fields_ = [("train", c_int32), ("p", c_float), ("seed", c_uint64), ("site_base", c_uint32)]
+    _fields_ = [("train", c_int32), ("p", c_float), ("seed", c_uint64), ("site_base", c_uint32), ("batch_offset", c_int32)]
 
 
 class EncoderTensors(C.Structure):

@@ -211,8 +211,8 @@ k_attn_fwd_mma(const float* __restrict__ q, const float* __restrict__ k, const f
         float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
         const int row_a = r0 + g, row_b = r0 + g + 8;
         RowKeep rk;
-        rk.rb4_a = ((uint32_t)bhL + (uint32_t)min(row_a, L - 1)) * (uint32_t)(Lp >> 2);
-        rk.rb4_b = ((uint32_t)bhL + (uint32_t)min(row_b, L - 1)) * (uint32_t)(Lp >> 2);
+        rk.rb4_a = ((uint32_t)bhL + dc.bh_off * (uint32_t)L + (uint32_t)min(row_a, L - 1)) * (uint32_t)(Lp >> 2);
+        rk.rb4_b = ((uint32_t)bhL + dc.bh_off * (uint32_t)L + (uint32_t)min(row_b, L - 1)) * (uint32_t)(Lp >> 2);
         const int kend = min(r0 + 16, L);         // keys [0, kend) can be visible to this tile
         for (int kb = 0; kb < kend; kb += 32) {
             float s[4][4];
@@ -334,8 +334,8 @@ k_attn_bwd_mma(const float* __restrict__ q, const float* __restrict__ k, const f
             const int row_a = r0 + g, row_b = r0 + g + 8;
             const float la = ls[row_a], lb = ls[row_b], Da = Dv[row_a], Db = Dv[row_b];
             RowKeep rk;
-            rk.rb4_a = ((uint32_t)bhL + (uint32_t)min(row_a, L - 1)) * (uint32_t)(Lp >> 2);
-            rk.rb4_b = ((uint32_t)bhL + (uint32_t)min(row_b, L - 1)) * (uint32_t)(Lp >> 2);
+            rk.rb4_a = ((uint32_t)bhL + dc.bh_off * (uint32_t)L + (uint32_t)min(row_a, L - 1)) * (uint32_t)(Lp >> 2);
+            rk.rb4_b = ((uint32_t)bhL + dc.bh_off * (uint32_t)L + (uint32_t)min(row_b, L - 1)) * (uint32_t)(Lp >> 2);
             float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
             const int kend = min(r0 + 16, L);
             for (int n0 = 0; n0 < kend; n0 += 8) {
@@ -396,7 +396,7 @@ k_attn_bwd_mma(const float* __restrict__ q, const float* __restrict__ k, const f
                 float pd[4] = {p[0], p[1], p[2], p[3]};
                 if (dc.train) {
                     const int qsel = min((hsel & 1) ? qb : qa, L - 1);
-                    const uint32_t idx4 = ((uint32_t)bhL + (uint32_t)qsel) * (uint32_t)(Lp >> 2) + ((hsel & 2) ? grp_b : grp_a);
+                    const uint32_t idx4 = ((uint32_t)bhL + dc.bh_off * (uint32_t)L + (uint32_t)qsel) * (uint32_t)(Lp >> 2) + ((hsel & 2) ? grp_b : grp_a);
                     const uint32_t mine = rng4(dc.seed, site, (uint64_t)idx4);
                     uint32_t r[4];
 #pragma unroll

@@ -227,7 +227,7 @@ k_attn_fwd_tc(const float* __restrict__ q, const float* __restrict__ k, const fl
         // ---- P = 2^(S f - m), row sum, dropout, FP16 pairs in place
         float l = 0.f;
         if (wvalid) {
-            const uint32_t rb4 = ((uint32_t)bh * (uint32_t)L + (uint32_t)min(i, L - 1)) * (uint32_t)Lp4;
+            const uint32_t rb4 = (((uint32_t)bh + dc.bh_off) * (uint32_t)L + (uint32_t)min(i, L - 1)) * (uint32_t)Lp4;
 #pragma unroll 1
             for (int c = half; c < nch; c += 2) {
                 uint32_t p0[16], p1[16];
@@ -419,7 +419,7 @@ k_attn_bwd_tc(const float* __restrict__ q, const float* __restrict__ k, const fl
         const bool wvalid = Rw < L;
         const int last_q = min(L, 128 * (t + 1)) - 1;
         const float li = sh.ls[i], Di = sh.dl[i];
-        const uint32_t rb4 = ((uint32_t)bh * (uint32_t)L + (uint32_t)min(i, L - 1)) * (uint32_t)Lp4;
+        const uint32_t rb4 = (((uint32_t)bh + dc.bh_off) * (uint32_t)L + (uint32_t)min(i, L - 1)) * (uint32_t)Lp4;
         bool first = true;
 #pragma unroll 1
         for (int kb = 0; kb < nblk; ++kb) {
@@ -542,7 +542,7 @@ k_attn_bwd_tc(const float* __restrict__ q, const float* __restrict__ k, const fl
 #pragma unroll
                         for (int u = 0; u < 4; ++u) {
                             const int qi = min(i0 + (lane & 3) + 4 * u, L - 1);
-                            hv[u] = rng4(dc.seed, site, (uint64_t)(((uint32_t)bh * (uint32_t)L + (uint32_t)qi) * (uint32_t)Lp4 + jg));
+                            hv[u] = rng4(dc.seed, site, (uint64_t)((((uint32_t)bh + dc.bh_off) * (uint32_t)L + (uint32_t)qi) * (uint32_t)Lp4 + jg));
                         }
                     }
 #pragma unroll

@@ -72,9 +72,12 @@ struct DropCfg {
     float scale;
     uint32_t seed;       // 32-bit digest of the 64-bit step seed
     uint32_t site_base;
+    uint32_t b_off;      // first sample of this call in the global batch (data parallelism)
+    uint32_t tok_off;    // = b_off * L   (set by the launcher once L is known: see with_offsets)
+    uint32_t bh_off;     // = b_off * H
 };
 inline DropCfg make_drop(const amid_dropout* d) {
-    DropCfg c{0, 0u, 1.0f, 0u, 0u};
+    DropCfg c{0, 0u, 1.0f, 0u, 0u, 0u, 0u, 0u};
     if (d && d->train && d->p > 0.f) {
         c.train = 1;
         double t = (double)d->p * 256.0 + 0.5;
@@ -86,7 +89,12 @@ inline DropCfg make_drop(const amid_dropout* d) {
         z ^= z >> 31;
         c.seed = (uint32_t)(z ^ (z >> 32));
     }
-    if (d) c.site_base = d->site_base;
+    if (d) { c.site_base = d->site_base; c.b_off = d->batch_offset > 0 ? (uint32_t)d->batch_offset : 0u; }
+    return c;
+}
+inline DropCfg with_offsets(DropCfg c, int L) {
+    c.tok_off = c.b_off * (uint32_t)L;
+    c.bh_off = c.b_off * (uint32_t)H;
     return c;
 }
 

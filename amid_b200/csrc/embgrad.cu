@@ -17,11 +17,17 @@ constexpr int LONG_SEG = 512;
 constexpr int LONG_CHUNKS = 128;
 constexpr int MAX_LONG = 64;     // long segments reduced by the parallel path (others: same order, one warp)
 
-__global__ void k_make_keys(const int64_t* __restrict__ ids, int64_t n, uint32_t* __restrict__ keys,
-                            uint32_t* __restrict__ vals) {
+// ids outside [0, V) (the reference would raise an index error) get the key V: they sort behind every valid row, come out
+// of the reduction with the id -1, which the scatter / Adam kernels skip, and raise the device error flag that the host
+// polls (amid_gather_error_host_sync)
+__global__ void k_make_keys(const int64_t* __restrict__ ids, int64_t n, int64_t V, uint32_t* __restrict__ keys,
+                            uint32_t* __restrict__ vals, int* __restrict__ err) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    keys[i] = (uint32_t)ids[i];
+    const int64_t id = ids[i];
+    const bool ok = id >= 0 && id < V;
+    if (!ok) atomicOr(err, 2);
+    keys[i] = ok ? (uint32_t)id : (uint32_t)V;
     vals[i] = (uint32_t)i;
 }
 
@@ -60,7 +66,7 @@ __global__ void __launch_bounds__(256)
 k_segreduce(const float* __restrict__ grads, const uint32_t* __restrict__ vals, const uint32_t* __restrict__ ukeys,
             const int* __restrict__ counts, const int* __restrict__ offsets, const int* __restrict__ n_uniq,
             int64_t* __restrict__ uniq_ids, float* __restrict__ uniq_grads, int* __restrict__ long_list,
-            int* __restrict__ n_long) {
+            int* __restrict__ n_long, uint32_t V) {
     const int lane = threadIdx.x & 31;
     const int u0 = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * SEG_PER_WARP;
     const int nu = n_uniq[0];
@@ -70,7 +76,7 @@ k_segreduce(const float* __restrict__ grads, const uint32_t* __restrict__ vals, 
     if (lane < SEG_PER_WARP && u0 + lane < nu) {
         off = offsets[u0 + lane];
         cnt = counts[u0 + lane];
-        uniq_ids[u0 + lane] = (int64_t)ukeys[u0 + lane];
+        uniq_ids[u0 + lane] = ukeys[u0 + lane] < V ? (int64_t)ukeys[u0 + lane] : (int64_t)-1;
         first = vals[off];
     }
     float4 s[SEG_PER_WARP];
@@ -248,6 +254,7 @@ k_adam_rows_lazy(float* __restrict__ table, float* __restrict__ m, float* __rest
     const int u = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
     if (u >= n_uniq[0]) return;
     const int64_t id = uniq_ids[u];
+    if (id < 0) return;                              // out-of-range ids of the step (flagged by k_make_keys)
     float4* Pp = reinterpret_cast<float4*>(table + id * D) + lane;
     float4* Mp = reinterpret_cast<float4*>(m + id * D) + lane;
     float4* Vp = reinterpret_cast<float4*>(v + id * D) + lane;
@@ -336,16 +343,18 @@ extern "C" int amid_embgrad_segreduce(const int64_t* ids, const float* grad_rows
     cudaStream_t s = (cudaStream_t)s_;
     AMID_REQUIRE(ids && grad_rows && uniq_ids && uniq_grads && n_uniq && workspace, "embgrad_segreduce: null argument");
     AMID_REQUIRE(n > 0 && n < (1ll << 31), "embgrad_segreduce: n_rows=%lld", (long long)n);
-    AMID_REQUIRE(V > 0 && V <= 0xFFFFFFFFll, "embgrad_segreduce: V=%lld does not fit 32-bit keys", (long long)V);
+    AMID_REQUIRE(V > 0 && V < 0xFFFFFFFFll, "embgrad_segreduce: V=%lld does not fit 32-bit keys", (long long)V);
+    int* err = err_flag();
+    AMID_REQUIRE(err, "embgrad_segreduce: cannot allocate error flag");
     AMID_REQUIRE(aligned16(grad_rows) && aligned16(uniq_grads) && ((uintptr_t)workspace & 255) == 0, "embgrad_segreduce: misaligned buffer");
     SegWs w = carve(workspace, n);
     AMID_REQUIRE((int64_t)w.total <= workspace_bytes, "embgrad_segreduce: workspace too small (%lld < %zu)",
                  (long long)workspace_bytes, w.total);
     AMID_K("k_make_keys", s);
-    k_make_keys<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(ids, n, w.keys_in, w.vals_in);
+    k_make_keys<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(ids, n, V, w.keys_in, w.vals_in, err);
     AMID_LAUNCH_CHECK("k_make_keys");
     int end_bit = 1;
-    while (end_bit < 32 && (1ull << end_bit) < (unsigned long long)V) ++end_bit;
+    while (end_bit < 32 && (1ull << end_bit) < (unsigned long long)V + 1) ++end_bit;     // keys 0..V (V = invalid id)
     size_t tb = w.cub_bytes;
     AMID_K("cub_radix_sort_pairs", s);
     cudaError_t e = cub::DeviceRadixSort::SortPairs(w.cub_tmp, tb, w.keys_in, w.keys_out, w.vals_in, w.vals_out, (int)n,
@@ -365,7 +374,7 @@ extern "C" int amid_embgrad_segreduce(const int64_t* ids, const float* grad_rows
     const unsigned blocks = (unsigned)(((n + SEG_PER_WARP - 1) / SEG_PER_WARP * 32 + 255) / 256);
     AMID_K("k_segreduce", s);
     k_segreduce<<<blocks, 256, 0, s>>>(grad_rows, w.vals_out, w.ukeys, w.counts, w.offsets, n_uniq, uniq_ids, uniq_grads,
-                                       w.long_list, w.n_long);
+                                       w.long_list, w.n_long, (uint32_t)V);
     AMID_LAUNCH_CHECK("k_segreduce");
     AMID_K("k_long_partial", s);
     k_long_partial<<<dim3(LONG_CHUNKS, MAX_LONG), 32, 0, s>>>(grad_rows, w.vals_out, w.counts, w.offsets, w.long_list,

@@ -129,8 +129,8 @@ k_proj_ffn(const float* __restrict__ o, const float* __restrict__ qn, int M,
             float4 v0 = add4(f4(acc[i], 0), c0);
             float4 v1 = add4(f4(acc[i], 1), c1);
             if (dc.train) {
-                v0 = drop4(v0, dc, site1, (uint64_t)gr * D + f.c0());
-                v1 = drop4(v1, dc, site1, (uint64_t)gr * D + f.c1());
+                v0 = drop4(v0, dc, site1, (uint64_t)(gr + dc.tok_off) * D + f.c0());
+                v1 = drop4(v1, dc, site1, (uint64_t)(gr + dc.tok_off) * D + f.c1());
             }
             v0 = make_float4(fmaxf(v0.x, 0.f), fmaxf(v0.y, 0.f), fmaxf(v0.z, 0.f), fmaxf(v0.w, 0.f));
             v1 = make_float4(fmaxf(v1.x, 0.f), fmaxf(v1.y, 0.f), fmaxf(v1.z, 0.f), fmaxf(v1.w, 0.f));
@@ -153,8 +153,8 @@ k_proj_ffn(const float* __restrict__ o, const float* __restrict__ qn, int M,
             float4 v0 = add4(f4(acc[i], 0), c0);
             float4 v1 = add4(f4(acc[i], 1), c1);
             if (dc.train) {
-                v0 = drop4(v0, dc, site2, (uint64_t)gr * D + f.c0());
-                v1 = drop4(v1, dc, site2, (uint64_t)gr * D + f.c1());
+                v0 = drop4(v0, dc, site2, (uint64_t)(gr + dc.tok_off) * D + f.c0());
+                v1 = drop4(v1, dc, site2, (uint64_t)(gr + dc.tok_off) * D + f.c1());
             }
             v0 = add4(v0, ld4(T1 + r * LDA + f.c0()));
             v1 = add4(v1, ld4(T1 + r * LDA + f.c1()));
@@ -256,7 +256,7 @@ __global__ void k_attn_fwd(const float* __restrict__ q, const float* __restrict_
 #pragma unroll
             for (int c = 0; c < 16; ++c) acc[c] *= corr;
             uint32_t r = 0;
-            if (dc.train) r = rng4(dc.seed, site, (((uint64_t)bh * L + i) * Lp + j0) >> 2);
+            if (dc.train) r = rng4(dc.seed, site, (((uint64_t)(bh + dc.bh_off) * L + i) * Lp + j0) >> 2);
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 int j = j0 + u;
@@ -325,7 +325,7 @@ __global__ void k_attn_bwd(const float* __restrict__ q, const float* __restrict_
         for (int j0 = 0; j0 <= imax; j0 += 4) {
             if (j0 > i) continue;
             uint32_t r = 0;
-            if (dc.train) r = rng4(dc.seed, site, (((uint64_t)bh * L + i) * Lp + j0) >> 2);
+            if (dc.train) r = rng4(dc.seed, site, (((uint64_t)(bh + dc.bh_off) * L + i) * Lp + j0) >> 2);
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 int j = j0 + u;
@@ -360,7 +360,7 @@ __global__ void k_attn_bwd(const float* __restrict__ q, const float* __restrict_
             float dp = dot16(vr, ds + i * DH);
             float pd = p;
             if (dc.train) {
-                const uint32_t r = rng4(dc.seed, site, (((uint64_t)bh * L + i) * Lp + j) >> 2);
+                const uint32_t r = rng4(dc.seed, site, (((uint64_t)(bh + dc.bh_off) * L + i) * Lp + j) >> 2);
                 const bool kp = rng_keep(r, j & 3, dc.thr16);
                 dp = kp ? dp * dc.scale : 0.f;
                 pd = kp ? p * dc.scale : 0.f;
@@ -437,7 +437,7 @@ k_ffn_bwd(const float* __restrict__ dxo, const float* __restrict__ h, const floa
         if (gr < M) {
             g = __ldg(reinterpret_cast<const float4*>(dxo + (size_t)gr * D) + c4);
             g = apply_tmask(g, __ldg(reinterpret_cast<const uint4*>(tmask) + gr), c4);
-            if (dc.train) g = drop4(g, dc, site2, (uint64_t)gr * D + c4 * 4);
+            if (dc.train) g = drop4(g, dc, site2, (uint64_t)(gr + dc.tok_off) * D + c4 * 4);
             st4(do2 + (size_t)gr * D + c4 * 4, g);
         }
         st4(T0 + r * LDA + c4 * 4, g);
@@ -732,12 +732,13 @@ static int ensure_smem(const void* fn, size_t bytes) {
     return 0;
 }
 
-static int check_encoder_args(int B, int L) {
+static int check_encoder_args(int B, int L, int b_off = 0) {
     AMID_REQUIRE(B > 0 && L > 0, "encoder: B=%d L=%d must be positive", B, L);
     AMID_REQUIRE(L <= 512, "encoder: L=%d > 512 unsupported (per-CTA shared-memory attention)", L);
     AMID_REQUIRE((int64_t)B * L < (1ll << 31) / D, "encoder: B*L too large");
     // the tensor-core attention kernels index the dropout stream of a site with 32 bits
-    AMID_REQUIRE((int64_t)B * 8 * L * ((L + 3) / 4) < (1ll << 32), "encoder: B*8*L*ceil(L/4) must be below 2^32");
+    AMID_REQUIRE((int64_t)(B + b_off) * 8 * L * ((L + 3) / 4) < (1ll << 32),
+                 "encoder: (batch_offset+B)*8*L*ceil(L/4) must be below 2^32");
     return 0;
 }
 
@@ -761,13 +762,13 @@ static int encoder_fwd_impl(const amid_encoder_tensors* P, const float* x0, cons
                             void* workspace, int64_t workspace_bytes, amid_stream_t stream_, int mode) {
     const bool use_tc = mode != 0;
     cudaStream_t stream = (cudaStream_t)stream_;
-    if (int rc = check_encoder_args(B, L)) return rc;
+    if (int rc = check_encoder_args(B, L, drop ? drop->batch_offset : 0)) return rc;
     AMID_REQUIRE(P && S && x0 && tmask && enc_out && workspace, "encoder_fwd: null argument");
     AMID_REQUIRE(workspace_bytes >= amid_encoder_fwd_workspace_bytes(B, L), "encoder_fwd: workspace too small");
     AMID_REQUIRE(aligned16(x0) && aligned16(enc_out) && aligned16(workspace) && aligned16(tmask), "encoder_fwd: misaligned buffer");
     const int M = B * L;
     const int tiles = (M + TM - 1) / TM;
-    const DropCfg dc = make_drop(drop);
+    const DropCfg dc = with_offsets(make_drop(drop), L);
     const size_t attn_smem = (size_t)2 * L * DH * sizeof(float);
     if (int rc = ensure_smem((const void*)k_attn_fwd, attn_smem)) return rc;
     const int attn_threads = (int)round_up((L + 1) / 2, 32);
@@ -976,13 +977,13 @@ static int encoder_bwd_impl(const amid_encoder_tensors* P, const float* x0, cons
     const bool use_tc = mode != 0;
     (void)enc_out;
     cudaStream_t stream = (cudaStream_t)stream_;
-    if (int rc = check_encoder_args(B, L)) return rc;
+    if (int rc = check_encoder_args(B, L, drop ? drop->batch_offset : 0)) return rc;
     AMID_REQUIRE(P && S && G && x0 && tmask && d_enc && dx0 && workspace, "encoder_bwd: null argument");
     AMID_REQUIRE(workspace_bytes >= amid_encoder_bwd_workspace_bytes(B, L), "encoder_bwd: workspace too small");
     AMID_REQUIRE(aligned16(d_enc) && aligned16(dx0) && aligned16(workspace), "encoder_bwd: misaligned buffer");
     const int M = B * L;
     const int tiles = (M + TM - 1) / TM;
-    const DropCfg dc = make_drop(drop);
+    const DropCfg dc = with_offsets(make_drop(drop), L);
     int rp;
     int SW = wgrad_chunks(M, &rp);
     const int SWmax = SW < 2 * WG_TC_S ? 2 * WG_TC_S : SW;

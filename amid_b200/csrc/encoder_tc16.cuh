@@ -239,7 +239,7 @@ k_proj_ffn_16(const float* __restrict__ o, const float* __restrict__ qn, int M, 
             for (int i = 0; i < 32; i += 4) {
                 const float4 b4 = __ldg(reinterpret_cast<const float4*>(b1 + c0 + i));
                 float4 t = make_float4(a[i] + b4.x, a[i + 1] + b4.y, a[i + 2] + b4.z, a[i + 3] + b4.w);
-                if (dc.train) t = drop4(t, dc, site1, (uint64_t)gr * D + c0 + i);
+                if (dc.train) t = drop4(t, dc, site1, (uint64_t)(gr + dc.tok_off) * D + c0 + i);
                 a[i] = fmaxf(t.x, 0.f); a[i + 1] = fmaxf(t.y, 0.f); a[i + 2] = fmaxf(t.z, 0.f); a[i + 3] = fmaxf(t.w, 0.f);
             }
             tile16_store32(sm.A, e.row, c0, a);
@@ -263,7 +263,7 @@ k_proj_ffn_16(const float* __restrict__ o, const float* __restrict__ qn, int M, 
             for (int i = 0; i < 32; i += 4) {
                 const float4 b4 = __ldg(reinterpret_cast<const float4*>(b2 + c0 + i));
                 float4 t = make_float4(a[i] + b4.x, a[i + 1] + b4.y, a[i + 2] + b4.z, a[i + 3] + b4.w);
-                if (dc.train) t = drop4(t, dc, site2, (uint64_t)gr * D + c0 + i);
+                if (dc.train) t = drop4(t, dc, site2, (uint64_t)(gr + dc.tok_off) * D + c0 + i);
                 t = make_float4(t.x + yy[i], t.y + yy[i + 1], t.z + yy[i + 2], t.w + yy[i + 3]);
                 t = apply_tmask(t, tw, (c0 + i) >> 2);
                 a[i] = t.x; a[i + 1] = t.y; a[i + 2] = t.z; a[i + 3] = t.w;
@@ -361,7 +361,7 @@ k_ffn_bwd_16(const float* __restrict__ dxo, const float* __restrict__ h, const f
             tw.z = __shfl_sync(0xffffffffu, twl.z, it); tw.w = __shfl_sync(0xffffffffu, twl.w, it);
             float4 gg = apply_tmask(g[it], tw, c4);
             if (grr < M) {
-                if (dc.train) gg = drop4(gg, dc, site2, (uint64_t)grr * D + c4 * 4);
+                if (dc.train) gg = drop4(gg, dc, site2, (uint64_t)(grr + dc.tok_off) * D + c4 * 4);
                 *(reinterpret_cast<float4*>(do2 + (size_t)grr * D) + c4) = gg;
             }
             *reinterpret_cast<uint2*>(sm.A + tile16_off8(r, c4 >> 1) + (c4 & 1) * 8) = make_uint2(pack_bf16(gg.x, gg.y), pack_bf16(gg.z, gg.w));

@@ -80,7 +80,7 @@ k_seq_embed(const float* __restrict__ table, const int64_t* __restrict__ ids, co
         const uint32_t w2 = __ballot_sync(0xffffffffu, x.z == 0.f);
         const uint32_t w3 = __ballot_sync(0xffffffffu, x.w == 0.f);
         if (lane == 0) *reinterpret_cast<uint4*>(tmask + r * 4) = make_uint4(w0, w1, w2, w3);
-        if (dc.train) x = drop4(x, dc, dc.site_base + SITE_EMB, (uint64_t)r * D + lane * 4);   // :363
+        if (dc.train) x = drop4(x, dc, dc.site_base + SITE_EMB, (uint64_t)(r + dc.tok_off) * D + lane * 4);   // :363
         // `seqs *= ~timeline_mask` (:366) is a value no-op: masked elements are already 0
         stg_stream(reinterpret_cast<float4*>(x0 + r * D) + lane, x);
     }
@@ -147,7 +147,7 @@ k_embed_all(const float* __restrict__ table, int64_t V, EmbedAll ea, uint32_t L,
                 bits.w = __ballot_sync(0xffffffffu, x.w == 0.f);
             }
             if (lane == 0) *reinterpret_cast<uint4*>(tmk + (size_t)r * 4) = bits;
-            if (dc.train) x = drop4(x, dc, site, (uint64_t)r * D + lane * 4);                  // :363
+            if (dc.train) x = drop4(x, dc, site, (uint64_t)(r + dc.tok_off) * D + lane * 4);                  // :363
             if (++l == L) l = 0;
         }
         stg_stream(reinterpret_cast<float4*>(out + (size_t)r * D) + lane, x);
@@ -174,7 +174,7 @@ k_seq_embed_bwd(float* __restrict__ dx0, const uint32_t* __restrict__ tmask, int
         if ((tw.y >> lane) & 1u) g.y = 0.f;
         if ((tw.z >> lane) & 1u) g.z = 0.f;
         if ((tw.w >> lane) & 1u) g.w = 0.f;
-        if (dc.train) g = drop4(g, dc, dc.site_base + SITE_EMB, (uint64_t)r * D + lane * 4);
+        if (dc.train) g = drop4(g, dc, dc.site_base + SITE_EMB, (uint64_t)(r + dc.tok_off) * D + lane * 4);
         *(reinterpret_cast<float4*>(dx0 + r * D) + lane) = g;
         acc.x += g.x; acc.y += g.y; acc.z += g.z; acc.w += g.w;
     }
@@ -201,7 +201,7 @@ __global__ void k_mask_attn(DropCfg dc, uint32_t site, int64_t BH, int L, uint8_
     const int j = (int)(e % L);
     const int64_t bi = e / L;   // bh*L + i
     const int Lp = (L + 3) & ~3;
-    const uint32_t r = rng4(dc.seed, site, ((uint64_t)bi * Lp + j) >> 2);
+    const uint32_t r = rng4(dc.seed, site, ((uint64_t)(bi + (int64_t)dc.bh_off * L) * Lp + j) >> 2);
     out[e] = dc.train ? (rng_keep(r, j & 3, dc.thr16) ? 1 : 0) : 1;
 }
 
@@ -260,7 +260,7 @@ extern "C" int amid_seq_embed_fwd(const float* table, int64_t V, const int64_t* 
     const int64_t n_rows = (int64_t)B * L;
     const int64_t warps = (n_rows + ROWS_PER_WARP - 1) / ROWS_PER_WARP;
     const unsigned blocks = (unsigned)((warps + 7) / 8);
-    const DropCfg dc = make_drop(drop);
+    const DropCfg dc = with_offsets(make_drop(drop), L);
     if (ids) {
         AMID_K("k_seq_embed", stream);
         k_seq_embed<true><<<blocks, 256, 0, stream>>>(table, ids, nullptr, pos, n_rows, L, V, x0, tmask, dc, err);
@@ -292,7 +292,7 @@ extern "C" int amid_embed_all_fwd(const float* table, int64_t V, const int64_t* 
     ea.tm1 = tmask_d1; ea.tm2 = tmask_d2;
     ea.n0 = (uint32_t)n_items; ea.n1 = (uint32_t)((int64_t)B * L); ea.n2 = ea.n1;
     const int64_t ctas = (int64_t)embed_all_ctas(ea.n0) + embed_all_ctas(ea.n1) + embed_all_ctas(ea.n2);
-    const DropCfg dc = make_drop(drop);
+    const DropCfg dc = with_offsets(make_drop(drop), L);
     AMID_K("k_embed_all", stream);
     k_embed_all<<<(unsigned)ctas, 256, 0, stream>>>(table, V, ea, (uint32_t)L, dc, err);
     AMID_LAUNCH_CHECK("k_embed_all");
@@ -304,7 +304,7 @@ extern "C" int amid_seq_embed_bwd(float* dx0, const uint32_t* tmask, int32_t B, 
     cudaStream_t stream = (cudaStream_t)stream_;
     AMID_REQUIRE(dx0 && tmask && dpos, "seq_embed_bwd: null argument");
     AMID_REQUIRE(B > 0 && L > 0, "seq_embed_bwd: B=%d L=%d", B, L);
-    const DropCfg dc = make_drop(drop);
+    const DropCfg dc = with_offsets(make_drop(drop), L);
     AMID_K("k_seq_embed_bwd", stream);
     k_seq_embed_bwd<<<L, SEB_WARPS * 32, 0, stream>>>(dx0, tmask, B, L, dpos, dc);
     AMID_LAUNCH_CHECK("k_seq_embed_bwd");
@@ -313,7 +313,7 @@ extern "C" int amid_seq_embed_bwd(float* dx0, const uint32_t* tmask, int32_t B, 
 
 extern "C" int amid_dropout_mask_feature(const amid_dropout* drop, uint32_t site, int64_t rows, uint8_t* out,
                                          amid_stream_t stream_) {
-    const DropCfg dc = make_drop(drop);
+    const DropCfg dc = make_drop(drop);            // rows are indexed from 0: pass the rows of the global batch and slice
     const int64_t n = rows * D;
     AMID_K("k_mask_feature", (cudaStream_t)stream_);
     k_mask_feature<<<(unsigned)((n / 4 + 255) / 256 + 1), 256, 0, (cudaStream_t)stream_>>>(dc, site, n, out);
@@ -322,7 +322,7 @@ extern "C" int amid_dropout_mask_feature(const amid_dropout* drop, uint32_t site
 }
 extern "C" int amid_dropout_mask_attn(const amid_dropout* drop, uint32_t site, int32_t B, int32_t L, uint8_t* out,
                                       amid_stream_t stream_) {
-    const DropCfg dc = make_drop(drop);
+    const DropCfg dc = with_offsets(make_drop(drop), L);
     const int64_t n = (int64_t)B * H * L * L;
     AMID_K("k_mask_attn", (cudaStream_t)stream_);
     k_mask_attn<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream_>>>(dc, site, (int64_t)B * H, L, out);

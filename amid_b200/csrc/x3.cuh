@@ -459,7 +459,7 @@ k_proj_ffn_x3(const float* __restrict__ o, const float* __restrict__ qn, int M, 
             for (int i = 0; i < 32; i += 4) {
                 const float4 b4 = __ldg(reinterpret_cast<const float4*>(b1 + c0 + i));
                 float4 t = make_float4(fmaf(a[i], f, b4.x), fmaf(a[i + 1], f, b4.y), fmaf(a[i + 2], f, b4.z), fmaf(a[i + 3], f, b4.w));
-                if (dc.train) t = drop4(t, dc, site1, (uint64_t)gr * D + c0 + i);
+                if (dc.train) t = drop4(t, dc, site1, (uint64_t)(gr + dc.tok_off) * D + c0 + i);
                 a[i] = fmaxf(t.x, 0.f); a[i + 1] = fmaxf(t.y, 0.f); a[i + 2] = fmaxf(t.z, 0.f); a[i + 3] = fmaxf(t.w, 0.f);
             }
             am = absmax32(a, am);
@@ -487,7 +487,7 @@ k_proj_ffn_x3(const float* __restrict__ o, const float* __restrict__ qn, int M, 
             for (int i = 0; i < 32; i += 4) {
                 const float4 b4 = __ldg(reinterpret_cast<const float4*>(b2 + c0 + i));
                 float4 t = make_float4(fmaf(a[i], f, b4.x), fmaf(a[i + 1], f, b4.y), fmaf(a[i + 2], f, b4.z), fmaf(a[i + 3], f, b4.w));
-                if (dc.train) t = drop4(t, dc, site2, (uint64_t)gr * D + c0 + i);
+                if (dc.train) t = drop4(t, dc, site2, (uint64_t)(gr + dc.tok_off) * D + c0 + i);
                 t = make_float4(t.x + yy[i], t.y + yy[i + 1], t.z + yy[i + 2], t.w + yy[i + 3]);
                 t = apply_tmask(t, tw, (c0 + i) >> 2);
                 a[i] = t.x; a[i + 1] = t.y; a[i + 2] = t.z; a[i + 3] = t.w;
@@ -594,7 +594,7 @@ k_ffn_bwd_x3(const float* __restrict__ dxo, const float* __restrict__ h, const f
 #pragma unroll
             for (int i = 0; i < 32; i += 4) {
                 float4 t = apply_tmask(make_float4(g[half][i], g[half][i + 1], g[half][i + 2], g[half][i + 3]), tw, (c0 + i) >> 2);
-                if (dc.train) t = drop4(t, dc, site2, (uint64_t)gr * D + c0 + i);
+                if (dc.train) t = drop4(t, dc, site2, (uint64_t)(gr + dc.tok_off) * D + c0 + i);
                 g[half][i] = t.x; g[half][i + 1] = t.y; g[half][i + 2] = t.z; g[half][i + 3] = t.w;
             }
             am = absmax32(g[half], am);

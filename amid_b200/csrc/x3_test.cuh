@@ -88,7 +88,7 @@ extern "C" int amid_attn_fwd_test(const float* q, const float* k, const float* v
                                   const amid_dropout* drop, uint32_t site, int32_t impl, amid_stream_t s_) {
     AMID_REQUIRE(q && k && v && o && lse && B > 0 && L > 0 && L <= 512, "attn_fwd_test: bad argument");
     cudaStream_t stream = (cudaStream_t)s_;
-    const DropCfg dc = make_drop(drop);
+    const DropCfg dc = with_offsets(make_drop(drop), L);
     if (impl == 0) {
         const size_t smem = (size_t)2 * L * DH * sizeof(float);
         if (int rc = ensure_smem((const void*)k_attn_fwd, smem)) return rc;
@@ -123,7 +123,7 @@ extern "C" int amid_attn_bwd_test(const float* q, const float* k, const float* v
                                   const amid_dropout* drop, uint32_t site, int32_t impl, amid_stream_t s_) {
     AMID_REQUIRE(q && k && v && o && lse && dO && dq && dk && dv && B > 0 && L > 0 && L <= 512, "attn_bwd_test: bad argument");
     cudaStream_t stream = (cudaStream_t)s_;
-    const DropCfg dc = make_drop(drop);
+    const DropCfg dc = with_offsets(make_drop(drop), L);
     if (impl == 0) {
         const size_t smem = (size_t)(4 * L * DH + 2 * L) * sizeof(float);
         if (int rc = ensure_smem((const void*)k_attn_bwd, smem)) return rc;

@@ -117,14 +117,34 @@ class Trainer:
         self.active_opt = 0
         self.last_losses = None
         self._seed = 0
+        if self.world > 1:
+            # replicas must start from rank 0's weights and share the dropout seed stream (the keep bits are indexed by
+            # global sample, so every rank must hash with the same seed)
+            tdist = dist.dist
+            tdist.broadcast(self.flat_p, 0, group=dist.group)
+            if self.table_sync != "sharded":
+                tdist.broadcast(self.table_padded if self.table_sync == "dense" else self.table.data, 0, group=dist.group)
+            sb = torch.tensor([model._seed_base], device=dev, dtype=torch.int64)
+            tdist.broadcast(sb, 0, group=dist.group)
+            model._seed_base = int(sb.item())
 
     # ------------------------------------------------------------------ helpers
     def _table_adam(self, st: _AdamState, uid, ug, nu, lr):
         call("amid_adam_rows_lazy", _ptr(self.table.data), _ptr(st.tm), _ptr(st.tv), _ptr(st.last), _ptr(uid), _ptr(ug),
              _ptr(nu), uid.numel(), st.step, lr, self.betas[0], self.betas[1], self.eps, _stream())
 
+    def check_ids(self):
+        """Raise IndexError if any kernel since the last check met an item id outside [0, V) (the reference raises
+        at the embedding lookup; here the kernels skip the row, set a device flag, and the host polls it at flush /
+        checkpoint / end of epoch -- one 4-byte read, no per-step synchronisation)."""
+        code = _abi.lib().amid_gather_error_host_sync()
+        if code:
+            raise IndexError("amid_b200: an item id outside [0, item_length) reached the table kernels "
+                             f"(device flag {code}); the offending rows were skipped")
+
     def flush(self):
         """Apply the pending zero-gradient Adam steps to every table row (exact dense semantics)."""
+        self.check_ids()
         for i, st in enumerate(self.opt):
             if st.step > 0 and self.sparse_table:
                 lr = self.lr if i == 0 else self.lr2
@@ -289,7 +309,8 @@ class Trainer:
               "params": {n: p.detach().clone() for n, p in self.P.items()},
               "opt": [{"m": st.m.clone(), "v": st.v.clone(), "tm": st.tm.clone(), "tv": st.tv.clone(),
                        "last": st.last.clone(), "step": st.step} for st in self.opt],
-              "active_opt": self.active_opt, "seed": self._seed, "seed_base": self.model._seed_base}
+              "active_opt": self.active_opt, "seed": self._seed, "seed_base": self.model._seed_base,
+              "model_step": self.model._step}
         return ck
 
     def load_checkpoint(self, ck: Dict[str, object]) -> None:
@@ -298,6 +319,10 @@ class Trainer:
         if ck["table_sync"] != self.table_sync or ck["world"] != self.world:
             raise _abi.AmidError(f"checkpoint was written with table_sync={ck['table_sync']} on {ck['world']} rank(s); "
                                  f"this trainer runs table_sync={self.table_sync} on {self.world}")
+        my_rank = self.dist.rank if self.dist is not None else 0
+        if self.table_sync in ("sharded", "dense") and int(ck.get("rank", 0)) != my_rank:
+            raise _abi.AmidError(f"checkpoint was written by rank {ck.get('rank')}: with table_sync={self.table_sync} the table "
+                                 f"shard / Adam moments are per rank (one file per rank); this is rank {my_rank}")
         if len(ck["opt"]) != len(self.opt):
             raise _abi.AmidError("checkpoint and model disagree on isDR (number of optimizers)")
         for n, p in self.P.items():
@@ -311,6 +336,7 @@ class Trainer:
         self.active_opt = int(ck["active_opt"])
         self._seed = int(ck["seed"])
         self.model._seed_base = int(ck["seed_base"])
+        self.model._step = int(ck.get("model_step", self.model._step))
 
     # ------------------------------------------------------------------ opt-in fast epoch loop
     def train_epoch(self, loader, phase: int = 1, log_every: int = 0, log=print) -> float:
@@ -336,4 +362,5 @@ class Trainer:
                 log(f"train total loss:{float(acc) / n}")
         if n == 0:
             raise ValueError("train_epoch(): empty loader")
+        self.check_ids()
         return float(acc) / n

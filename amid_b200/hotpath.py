@@ -188,8 +188,11 @@ class _Mim:
     __slots__ = ("name", "p", "gate", "coef", "active", "n_active", "scal", "Ssum", "E", "esum", "other", "n")
 
 
-def _dropout(cfg: Config, train: bool, seed: int, site_base: int) -> Dropout:
-    return Dropout(1 if (train and cfg.drop_p > 0) else 0, float(cfg.drop_p), int(seed) & (2**64 - 1), site_base)
+def _dropout(cfg: Config, train: bool, seed: int, site_base: int, batch_offset: int = 0) -> Dropout:
+    """batch_offset = position of this rank's first sample in the global batch: the keep bits are indexed by global
+    sample, so data-parallel training with dropout equals single-GPU training on the global batch."""
+    return Dropout(1 if (train and cfg.drop_p > 0) else 0, float(cfg.drop_p), int(seed) & (2**64 - 1), site_base,
+                   int(batch_offset))
 
 
 def _mim_forward(P, name: str, m_global: torch.Tensor, other: torch.Tensor, n: int, ts: float, j0: int,
@@ -306,14 +309,14 @@ def forward(P: Dict[str, torch.Tensor], cfg: Config, i_node, neg_samples, seq_d1
     if not cfg.isInC:
         pre_x0 = [f(B * Le, D), f(B * Le, D)]
         pre_tm = [torch.empty(B * Le * 4, device=dev, dtype=torch.int32) for _ in range(2)]
-        drop0 = _dropout(cfg, train, seed, 0)
+        drop0 = _dropout(cfg, train, seed, 0, j0)
         call("amid_embed_all_fwd", _ptr(table), V, _ptr(ids_items), B * Cn, _ptr(seqs[0]), _ptr(seqs[1]),
              _ptr(P["sac1.pos_emb.weight"]), _ptr(P["sac2.pos_emb.weight"]), B, L, _ptr(items), _ptr(pre_x0[0]),
              _ptr(pre_x0[1]), _ptr(pre_tm[0]), _ptr(pre_tm[1]), C.byref(drop0), s)
     else:
         call("amid_emb_gather_fwd", _ptr(table), V, _ptr(ids_items), B * Cn, _ptr(items), s)
     for k, sac in enumerate(("sac1.", "sac2.")):
-        drop = _dropout(cfg, train, seed, 8 * k)
+        drop = _dropout(cfg, train, seed, 8 * k, j0)
         if cfg.isInC:
             x0 = f(B * Le, D)
             tm = torch.empty(B * Le * 4, device=dev, dtype=torch.int32)
@@ -339,7 +342,7 @@ def forward(P: Dict[str, torch.Tensor], cfg: Config, i_node, neg_samples, seq_d1
     with _Fork(dev, cfg.overlap_encoders) as fork:
         for k, sac in enumerate(("sac1.", "sac2.")):
             with fork.branch(k):
-                drop = _dropout(cfg, train, seed, 8 * k)
+                drop = _dropout(cfg, train, seed, 8 * k, j0)
                 es = encoder_struct(P, sac)
                 call(_ENC_FWD[cfg.precision], C.byref(es), _ptr(x0s[k]), _ptr(tms[k]), B, Le, C.byref(drop),
                      C.byref(saveds[k].struct), _ptr(encs[k]), _ptr(wss[k]), ws_bytes, _stream())
@@ -436,7 +439,7 @@ def backward(P: Dict[str, torch.Tensor], cfg: Config, ctx: Ctx, dprobs: torch.Te
     with _Fork(dev, cfg.overlap_encoders and not cfg.isInC) as fork:
         for k, sac in enumerate(("sac1.", "sac2.")):
             with fork.branch(k):
-                drop = _dropout(cfg, ctx.train, ctx.seed, 8 * k)
+                drop = _dropout(cfg, ctx.train, ctx.seed, 8 * k, ctx.j0)
                 es = encoder_struct(P, sac)
                 gstruct = encoder_struct(G, sac)
                 dx0 = dx0s[k]

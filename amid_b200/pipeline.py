@@ -10,9 +10,13 @@ is produced by one kernel launch (csrc/pipeline.cu) directly as int64 device ten
 Two modes:
   * ``batch(rows, negatives=...)``: "replay" -- negatives drawn elsewhere (e.g. by the reference sampler) are
     used as given; every field is then bit-identical to the reference's collated batch (tests/test_gpu_pipeline.py).
+    Evaluation PARITY with the reference protocol requires this mode.
   * ``batch(rows, k=..., seed=...)``: negatives are drawn on the device: k distinct items of the target domain's
-    pool outside the user's full own-domain sequence, reproducible in (seed, row).  The stream differs from
-    Python's random.sample (which is not reproducible across Python versions either); the constraints are the same.
+    pool outside the user's full own-domain sequence, reproducible in (seed, row).  The draw is an affine walk
+    (random start, random coprime stride) over the id-sorted pool, NOT random.sample's uniform k-subset: a user's
+    negatives form an arithmetic progression in pool order, so sampled HR/NDCG can differ systematically from the
+    reference protocol when item ids correlate with popularity.  Use it for training throughput; use replay mode
+    when the metric has to match the reference.
 """
 from __future__ import annotations
 
@@ -124,7 +128,7 @@ class DeviceDataset:
             K, sample = neg.shape[1], 0
         else:
             K, sample = int(k), int(k)
-            neg = i64(B, K)
+            neg = torch.zeros(B, K, device=self.dev, dtype=torch.int64)   # a row whose pool is exhausted keeps id 0 + error flag
         o = BatchOut(*[out[n].data_ptr() for n in ("seq_d1", "seq_d2", "i_node", "user_node", "domain_id", "overlap_label",
                                                    "long_tail_mask_d1", "long_tail_mask_d2")], neg.data_ptr() if sample else None)
         call("amid_batch_build", C.byref(self.src), _ptr(rows), B, L, sample, self.long_length, self.pad_id,
@@ -139,11 +143,29 @@ class DeviceDataset:
         out["label"] = torch.cat((torch.ones(B, 1, device=self.dev), torch.zeros(B, K, device=self.dev)), 1)
         return out
 
-    def epoch(self, batch_size: int, k: int = 1, seed: int = 0, shuffle: bool = True, drop_last: bool = True) -> Iterable[Dict]:
-        """Batches of one epoch (DataLoader(shuffle=True, drop_last=True) of train_sr.py:452-455), built on the device."""
+    def epoch(self, batch_size: int, k: int = 1, seed: int = 0, shuffle: bool = True, drop_last: bool = True,
+              rank: int = 0, world: int = 1) -> Iterable[Dict]:
+        """Batches of one epoch (DataLoader(shuffle=True, drop_last=True) of train_sr.py:452-455), built on the device.
+        ``batch_size`` is the GLOBAL batch; under data parallelism rank r gets rows [r*B/world, (r+1)*B/world) of every
+        global batch (the slice DistCtx assigns it).  The sampler seed of a batch is a 64-bit mix of (seed, batch index),
+        so epochs never share a negative stream; the first batch of an epoch is range-checked on the host."""
+        if batch_size % world:
+            raise ValueError(f"global batch {batch_size} is not divisible by the world size {world}")
         g = torch.Generator(device="cpu").manual_seed(int(seed))
         order = torch.randperm(self.n_rows, generator=g) if shuffle else torch.arange(self.n_rows)
         order = order.to(self.dev)
         stop = self.n_rows - (self.n_rows % batch_size if drop_last else 0)
-        for i in range(0, stop, batch_size):
-            yield self.batch(order[i:i + batch_size], k=k, seed=(int(seed) << 20) + i)
+        bl = batch_size // world
+        for bi, i in enumerate(range(0, stop, batch_size)):
+            rows = order[i:i + batch_size]
+            if world > 1:
+                rows = rows[rank * bl:(rank + 1) * bl]
+            yield self.batch(rows, k=k, seed=_mix64(int(seed), bi), check=(bi == 0))
+
+
+def _mix64(seed: int, index: int) -> int:
+    """splitmix64 of the pair: distinct (seed, batch index) pairs give unrelated sampler seeds."""
+    z = ((seed & (2**64 - 1)) * 0x9E3779B97F4A7C15 + (index + 1) * 0xD1B54A32D192ED03) & (2**64 - 1)
+    z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & (2**64 - 1)
+    z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & (2**64 - 1)
+    return z ^ (z >> 31)

@@ -1,14 +1,22 @@
 """bench.py -- training throughput of the AMID SASRec hot path on B200 (BASELINE.json metric
-"train seqs/sec at 1/2/4/8 B200").
+"train seqs/sec at 1/2/4/8 B200; emb-gather HBM GB/s; eval users/sec").
 
     python bench.py --gpus N --steps K --warmup W            # this repo (one process per GPU under torchrun)
-    python bench.py --impl reference --steps K --warmup W    # the reference path's CPU port on the host cores
+    python bench.py --impl reference --steps K --warmup W    # the reference's own code on the host cores
 
-A "step" is one full training step of train_sr.py:201-215 on one synthetic batch of the C3
-shape: forward, domain-masked BCE, backward, embedding-gradient
-reduction and Adam on every parameter.  `value` = global sequences / second with the batch
-already resident in HBM; `e2e` = the same through the public `Trainer` API with the batch in
-pinned HOST memory (H2D every step, loss read back every step).  Prints ONE JSON line.
+A "step" is one full training step of train_sr.py:201-215 on one synthetic batch of the C3 shape (SURVEY.md
+section 8): forward, domain-masked BCE, backward, embedding-gradient reduction and Adam on every parameter.
+`value` = global sequences / second with the batch already resident in HBM; `e2e` = the same through the
+public `Trainer` API with the batch in pinned HOST memory (H2D every step, loss read back every step).
+The timed mode is the parity-grade one (`--precision x3`: tcgen05 tensor cores at fp32-level accuracy, the same
+test tolerances as the exact fp32 path); `precisions` carries the other modes measured in the same run.
+Prints ONE JSON line.
+
+The reference arm drives the UNMODIFIED `model_seq.SASRec` of WujiangXu/AMID (vendored byte-for-byte into
+oracle/_ref by oracle/build_ref.py, imported with the two SURVEY 8c shims) through the train_sr.py loop body with
+torch.optim.Adam on the box's host cores.  At the C3 shape the literal InterComp needs 275 GB, so its forward is
+swapped for the exact closed form (oracle/ref_loader.closed_form_itc; `kind` says so); each step runs a bounded
+sample of the per-step batch so that the arm ends within minutes.
 """
 from __future__ import annotations
 
@@ -29,6 +37,14 @@ import torch  # noqa: E402
 
 V_ITEMS = 894820          # train_sr.py:450,456  item_length * 2
 D, HID = 128, 32
+REALISTIC = False
+PRECISIONS = ("x3", "fp32", "tf32", "bf16")
+PREC_NOTE = {
+    "x3": "tcgen05 split-operand GEMMs + tcgen05 attention at fp32-level accuracy (parity-grade: the fp32 tolerances)",
+    "fp32": "exact fp32 CUDA-core tiles (parity-grade anchor)",
+    "tf32": "single-pass tcgen05 TF32 (reduced precision: 5e-3 tolerances)",
+    "bf16": "single-pass tcgen05 BF16 operands (reduced precision: 2e-2 tolerances)",
+}
 
 
 def parse():
@@ -43,15 +59,18 @@ def parse():
     ap.add_argument("--neg", type=int, default=1, help="negatives per row in training (dataset_seq.py:197-199)")
     ap.add_argument("--dr", action="store_true", help="isDR=True, phase-1 loss (train_sr_dr.py config)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-sample", type=int, default=32, help="sequences per CPU-baseline step (bounded sample)")
+    ap.add_argument("--no-extras", action="store_true", help="skip the precisions / eval / c1 / dp_check sub-records")
+    ap.add_argument("--cpu-sample", type=int, default=128, help="sequences per reference-arm step (bounded sample)")
+    ap.add_argument("--cpu-budget", type=float, default=150.0, help="seconds the reference arm may spend on timed steps")
     ap.add_argument("--dense-table", action="store_true", help="dense Adam over the whole table (reference-style)")
     ap.add_argument("--table-sync", default="auto", choices=["auto", "sparse", "dense", "sharded"],
                     help="multi-GPU table strategy (engine.Trainer); 'sharded' = row-sharded table + all-to-all (config 4)")
     ap.add_argument("--ids", default="uniform", choices=["uniform", "realistic"],
                     help="uniform = roofline variant (default); realistic = short left-padded histories (SURVEY 8d)")
     ap.add_argument("--items", type=int, default=V_ITEMS, help="table rows V (config 4: 20000002)")
-    ap.add_argument("--precision", default="bf16", choices=["fp32", "x3", "tf32", "bf16"],
-                    help="encoder GEMM stages: tf32 = tcgen05 tensor cores (fp32 accumulate), fp32 = exact CUDA-core tiles")
+    ap.add_argument("--precision", default="x3", choices=list(PRECISIONS),
+                    help="encoder arithmetic: x3 = tcgen05 at fp32-level accuracy (default, parity-grade), fp32 = exact "
+                         "CUDA-core tiles, tf32 / bf16 = single-pass tcgen05 (reduced precision)")
     a = ap.parse_args()
     V_ITEMS = a.items
     REALISTIC = a.ids == "realistic"
@@ -60,11 +79,8 @@ def parse():
 
 def workload_name(a):
     return (f"C3 synthetic train step: per-GPU batch {a.batch}, L={a.seq_len}, d={D}, hid={HID}, C={1 + a.neg}, "
-            f"V={V_ITEMS}, SASRec+ItC(ts2=0.4){'+DR' if a.dr else ''}, dropout 0.5, {'uniform ids (roofline variant)' if a.ids == 'uniform' else 'realistic ids (median-5 histories, left-padded)'}, "
-            f"{'exact-fp32 path' if a.precision == 'fp32' else 'tcgen05 ' + a.precision.upper() + ' GEMM stages, fp32 accumulate/storage'}")
-
-
-REALISTIC = False
+            f"V={V_ITEMS}, SASRec+ItC(ts2=0.4){'+DR' if a.dr else ''}, dropout 0.5, "
+            f"{'uniform ids (roofline variant)' if a.ids == 'uniform' else 'realistic ids (median-5 histories, left-padded)'}")
 
 
 def synth_batch(rng, B, L, C, V):
@@ -87,52 +103,240 @@ def synth_batch(rng, B, L, C, V):
     }
 
 
-def cpu_reference_steps(a, steps, warmup, sample):
-    """Times `steps` CPU train steps on `sample` sequences of the workload; returns seq/s."""
-    from common import make_keep_masks, make_params
-    from oracle import amid_oracle as O
+# ------------------------------------------------------------------------------------------------
+# the reference on the host cores
+# ------------------------------------------------------------------------------------------------
+def _ref():
+    from oracle import ref_loader
+    return ref_loader if ref_loader.available() else None
+
+
+def ref_train_step(model, opt, crit, b, dr=False, dr_e_w=0.01):
+    """Loop body of train_sr.py:191-215 (train_sr_dr.py:205-225 with --dr), device calls removed by the CPU shim."""
+    outs = model(b["i_node"], b["i_node"], b["neg_samples"], b["seq_d1"], b["seq_d2"], b["i_node"], b["i_node"])
+    dom = b["domain_id"]
+    m1, m2 = (torch.ones_like(dom) - dom).unsqueeze(1), dom.unsqueeze(1)
+    loss = torch.mean(crit(outs[0], b["label"]) * m1 + crit(outs[1], b["label"]) * m2)
+    if dr:
+        e1 = (crit(outs[0], b["label"]) - outs[4]) ** 2 / outs[2]
+        e2 = (crit(outs[1], b["label"]) - outs[5]) ** 2 / outs[3]
+        loss = loss + dr_e_w * torch.mean(e1 * m1 + e2 * m2)
+    opt.zero_grad()
+    loss.backward()
+    opt.step()
+    return float(loss.item())
+
+
+def cpu_train_baseline(a, steps, warmup, sample, variant="closed_form_itc", budget=None):
+    """Times train steps of the reference on `sample` sequences of the workload.  variant: 'closed_form_itc' (the
+    configured SASRec+ItC with InterComp.forward swapped for its exact closed form) or 'no_itc' (isItC=False, the
+    unpatched reference).  Falls back to the oracle port when oracle/_ref is absent.  Returns a cpu_baseline dict."""
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     L, C = a.seq_len, 1 + a.neg
     rng = np.random.default_rng(1234)
-    P = {k: v.requires_grad_(True) for k, v in make_params(7, V_ITEMS, D, L, HID, sample, isDR=a.dr).items()}
-    opt = torch.optim.Adam(list(P.values()), lr=5e-4)              # train_sr.py:480
+    rl = _ref()
     times = []
-    for it in range(warmup + steps):
-        b = synth_batch(rng, sample, L, C, V_ITEMS)
-        t0 = time.perf_counter()
-        masks = make_keep_masks(it, sample, L, D)                   # F.dropout's Bernoulli draws
-        outs = O.sasrec_forward(P, b["i_node"], b["neg_samples"], b["seq_d1"], b["seq_d2"], isInC=False, isItC=True,
-                                ts1=0.5, ts2=0.4, isDR=a.dr, masks=masks, closed_form=True)
-        loss = O.loss_cls(outs[0], outs[1], b["label"], b["domain_id"])
-        if a.dr:
-            loss = loss + 0.01 * O.loss_dr_e(*outs, b["label"], b["domain_id"])
-        opt.zero_grad()
-        loss.backward()
-        opt.step()                                                   # dense Adam over the [V,128] table too
-        dt = time.perf_counter() - t0
-        if it >= warmup:
-            times.append(dt)
-    ms = 1e3 * float(np.mean(times))
-    return sample / (ms / 1e3), ms, cores
+    if rl is not None:
+        ref = rl.load("cpu")
+        ms = ref.model_seq
+        literal = ms.InterComp.forward
+        if variant == "closed_form_itc":
+            rl.closed_form_itc(ms)
+        try:
+          with ref.on_cpu():
+            torch.manual_seed(7)
+            model = ms.SASRec(0, D, V_ITEMS, D, L, HID, sample, False, variant != "no_itc", 0.5, 0.4, isDR=a.dr).train()
+            opt = torch.optim.Adam(model.parameters(), lr=5e-4)          # train_sr.py:480
+            crit = torch.nn.BCELoss(reduction="none")                    # train_sr.py:184
+            t_start = time.perf_counter()
+            for it in range(warmup + steps):
+                b = synth_batch(rng, sample, L, C, V_ITEMS)
+                t0 = time.perf_counter()
+                ref_train_step(model, opt, crit, b, a.dr)
+                dt = time.perf_counter() - t0
+                if it >= warmup:
+                    times.append(dt)
+                    if budget is not None and len(times) >= 2 and time.perf_counter() - t_start + dt > budget:
+                        break
+        finally:
+            ms.InterComp.forward = literal
+        kind = "reference"
+        what = ("the reference's model_seq.SASRec + train_sr.py loop body + torch.optim.Adam (dense 458 MB table), "
+                + ("InterComp.forward swapped for its exact closed form (the literal [bs,bs,n,n] code needs 275 GB at this shape)"
+                   if variant == "closed_form_itc" else "isItC=False (unpatched reference code)"))
+    else:
+        from common import make_keep_masks, make_params
+        from oracle import amid_oracle as O
+        P = {k: v.requires_grad_(True) for k, v in make_params(7, V_ITEMS, D, L, HID, sample, isDR=a.dr).items()}
+        opt = torch.optim.Adam(list(P.values()), lr=5e-4)
+        for it in range(warmup + steps):
+            b = synth_batch(rng, sample, L, C, V_ITEMS)
+            t0 = time.perf_counter()
+            masks = make_keep_masks(it, sample, L, D)
+            outs = O.sasrec_forward(P, b["i_node"], b["neg_samples"], b["seq_d1"], b["seq_d2"], isInC=False,
+                                    isItC=variant != "no_itc", ts1=0.5, ts2=0.4, isDR=a.dr, masks=masks, closed_form=True)
+            loss = O.loss_cls(outs[0], outs[1], b["label"], b["domain_id"])
+            opt.zero_grad(); loss.backward(); opt.step()
+            if it >= warmup:
+                times.append(time.perf_counter() - t0)
+        kind = "port"
+        what = "oracle port of the reference path + torch.optim.Adam (oracle/_ref not built on this machine)"
+    ms_step = 1e3 * float(np.mean(times))
+    return {"value": sample / (ms_step / 1e3), "unit": "seq/s", "cores": cores, "kind": kind, "variant": variant,
+            "ms_per_step": ms_step, "steps_timed": len(times),
+            "sample": f"{sample} of the {a.batch} sequences of a per-GPU step (L={a.seq_len}), {warmup} warm-up + {len(times)} "
+                      f"timed steps; {what}"}
 
 
 def run_reference(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    value, ms, cores = cpu_reference_steps(a, a.steps, a.warmup, a.cpu_sample)
-    sample = (f"{a.cpu_sample} sequences per step of the same workload (L={a.seq_len}); oracle port of the reference "
-              f"path + torch.optim.Adam (dense table), closed-form ItC (the literal [bs,bs,n,n] ItC needs 275 GB here)")
+    cb = cpu_train_baseline(a, a.steps, min(a.warmup, 2), a.cpu_sample, "closed_form_itc", budget=a.cpu_budget)
     line = {
-        "impl": "reference", "metric": "train_seqs_per_sec", "value": value, "unit": "seq/s", "n_gpus": a.gpus,
-        "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": {"workload": workload_name(a)},
-        "cpu_baseline": {"value": value, "unit": "seq/s", "cores": cores, "kind": "port", "sample": sample},
-        "e2e": {"value": value, "unit": "seq/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "impl": "reference", "metric": "train_seqs_per_sec", "value": cb["value"], "unit": "seq/s", "n_gpus": a.gpus,
+        "steps": cb["steps_timed"], "warmup": min(a.warmup, 2), "ms_per_step": cb["ms_per_step"], "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(a), "global_batch": a.batch * a.gpus, "seq_len": a.seq_len,
+                   "parallelism": "host cores (the reference has no multi-GPU path: one process whatever --gpus says)"},
+        "cpu_baseline": cb,
+        "e2e": {"value": cb["value"], "unit": "seq/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    try:
+        line["no_itc"] = cpu_train_baseline(a, 2, 1, a.cpu_sample, "no_itc")
+    except Exception as e:
+        line["no_itc"] = {"value": None, "error": repr(e)}
+    try:
+        line["c1"] = c1_reference_cpu()
+    except Exception as e:
+        line["c1"] = {"value": None, "error": repr(e)}
     print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# C1: real cloth_sport batches from the reference's own dataset + sampler + collate (BASELINE.md section 4)
+# ------------------------------------------------------------------------------------------------
+C1 = dict(bs=256, L=20, item_length=447410, neg_eval=999)
+
+
+def c1_batches(n_train=6, n_eval=3):
+    """Reference-collated batches (float32 tensors, train_sr.py:451-455 arguments) from the vendored CSVs, drawn ONCE
+    (seeded) and fed to both arms: the same batches and the same sampled negatives."""
+    import random
+    rl = _ref()
+    if rl is None:
+        return None
+    ref = rl.load("cpu")
+    ds = ref.dataset_seq
+    random.seed(1); np.random.seed(1); torch.manual_seed(1)
+    L, bs = C1["L"], C1["bs"]
+    pad_id = C1["item_length"] + 1                                       # train_sr.py:451
+    root = ref.data_root
+
+    def draw(csv, neg, n, is_train):
+        d = ds.DualDomainSeqDataset(seq_len=L, isTrain=is_train, neg_nums=neg, long_length=7, pad_id=pad_id,
+                                    csv_path=os.path.join(root, csv))
+        out = []
+        for k in range(n):
+            out.append(ds.collate_fn_enhance([d[i] for i in range(k * bs, (k + 1) * bs)]))
+        return out
+    import contextlib
+    import io
+    with contextlib.redirect_stdout(io.StringIO()):          # the reference's dataset prints its sizes on stdout
+        return {"train": draw("cloth_sport_train75.csv", C1["neg_eval"], n_train, True),
+                "eval": draw("cloth_sport_test.csv", C1["neg_eval"], n_eval, False)}
+
+
+def _c1_fields(b, long=True):
+    f = (lambda t: t.long()) if long else (lambda t: t)
+    return {"i_node": f(b["i_node"]), "neg_samples": f(b["neg_samples"]), "seq_d1": f(b["seq_d1"]), "seq_d2": f(b["seq_d2"]),
+            "domain_id": f(b["domain_id"]), "label": b["label"].float()}
+
+
+def c1_reference_cpu(batches=None):
+    """The reference itself (LITERAL InterComp: it fits at bs=256, L=20) on the C1 batches, host cores."""
+    rl = _ref()
+    if rl is None:
+        return {"value": None, "error": "oracle/_ref not built on this machine"}
+    batches = batches or c1_batches()
+    ref = rl.load("cpu")
+    ms, ut = ref.model_seq, ref.utils
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    with ref.on_cpu():
+        torch.manual_seed(5)
+        model = ms.SASRec(0, D, C1["item_length"] * 2, D, C1["L"], HID, C1["bs"], False, True, 0.5, 0.4).train()
+        opt = torch.optim.Adam(model.parameters(), lr=5e-4)
+        crit = torch.nn.BCELoss(reduction="none")
+        ts = []
+        for k, hb in enumerate(batches["train"][:3]):
+            b = _c1_fields(hb)
+            t0 = time.perf_counter()
+            ref_train_step(model, opt, crit, b)
+            if k:
+                ts.append(time.perf_counter() - t0)
+        model.eval()
+        te = []
+        with torch.no_grad():
+            for k, hb in enumerate(batches["eval"][:2]):
+                b = _c1_fields(hb)
+                t0 = time.perf_counter()
+                p1, p2 = model(b["i_node"], b["i_node"], b["neg_samples"], b["seq_d1"], b["seq_d2"], b["i_node"], b["i_node"])
+                pred = np.where((b["domain_id"] == 0).numpy()[:, None], p1.numpy(), p2.numpy())
+                ut.get_sample_scores(pred)                                    # utils.py:296-313
+                if k:
+                    te.append(time.perf_counter() - t0)
+    return {"kind": "reference", "cores": cores, "train_seqs_per_sec": C1["bs"] / float(np.mean(ts)),
+            "eval_users_per_sec": C1["bs"] / float(np.mean(te)),
+            "sample": f"cloth_sport_train75 / cloth_sport_test batches of {C1['bs']} rows, L={C1['L']}, eval C=1+{C1['neg_eval']}; "
+                      f"unpatched reference (literal InterComp), {len(ts)} timed train steps, {len(te)} timed eval batches"}
+
+
+def c1_ours(precision, graph_ok=True):
+    """The same reference-drawn C1 batches through the public Trainer API from HOST tensors (H2D in the timed loop)."""
+    from amid_b200 import evaluate
+    from amid_b200.engine import Trainer
+    from amid_b200.model_seq import SASRec
+    batches = c1_batches()
+    if batches is None:
+        return {"value": None, "error": "oracle/_ref not built on this machine (C1 needs the reference's CSVs and sampler)"}
+    torch.manual_seed(5)
+    m = SASRec(0, D, C1["item_length"] * 2, D, C1["L"], HID, C1["bs"], False, True, 0.5, 0.4).cuda().train()
+    m.cfg.precision = precision
+    tr = Trainer(m, lr=5e-4)
+    host = [{k: v.pin_memory() for k, v in _c1_fields(hb, long=False).items()} for hb in batches["train"]]
+    for i in range(3):
+        tr.step(tr.to_device(host[i % len(host)]))
+    torch.cuda.synchronize()
+    n = 60                                                                # one epoch of cloth_sport_train75 is 60 steps
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(n):
+        losses = tr.step(tr.to_device(host[i % len(host)]))
+    e1.record()
+    torch.cuda.synchronize()
+    train = n * C1["bs"] / (e0.elapsed_time(e1) / 1e3)
+    m.eval()
+    ev = [{k: v.pin_memory() for k, v in _c1_fields(hb, long=False).items()} for hb in batches["eval"]]
+
+    def one(i):
+        b = tr.to_device(ev[i % len(ev)])
+        probs = tr.scores(b)
+        return evaluate.evaluate_lists(probs[0, 0], probs[0, 1], b["domain_id"])
+    for i in range(2):
+        one(i)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for i in range(12):
+        one(i)
+    torch.cuda.synchronize()
+    users = 12 * C1["bs"] / (time.perf_counter() - t0)
+    return {"train_seqs_per_sec": train, "eval_users_per_sec": users, "precision": precision, "final_loss": float(losses[0].item()),
+            "config": f"cloth_sport_train75 / cloth_sport_test batches from the reference's dataset + sampler + collate "
+                      f"(float32 ids as collated), bs={C1['bs']}, L={C1['L']}, eval C=1+{C1['neg_eval']}, SASRec+ItC, 1 GPU, "
+                      f"host batches through Trainer.step / Trainer.scores"}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -149,8 +353,9 @@ class Clocks:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                          "--format=csv,noheader,nounits", "-lms", "25"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            time.sleep(0.3)                       # let the sampler reach its first sample before the timed region
         except Exception:
             self.proc = None
 
@@ -205,16 +410,15 @@ def kernel_work(name, B, L, C):
         "k_wgrad": (6 * gemm, 11 * act),        # r: 6 dY + 5 distinct X
     }
     table = {
-        "k_attn_fwd": {"flop": attn_full, "byte": 4 * act}, "k_attn_bwd": {"flop": 2.5 * attn_full, "byte": 8 * act},
-        "k_attn_fwd_mma": {"flop": attn_full, "byte": 4 * act}, "k_attn_bwd_mma": {"flop": 2.5 * attn_full, "byte": 8 * act},
-        "k_attn_fwd_mma3": {"flop": attn_full, "byte": 4 * act}, "k_attn_bwd_mma3": {"flop": 2.5 * attn_full, "byte": 8 * act},
-        "k_attn_fwd_tc": {"flop": attn_full, "byte": 4 * act}, "k_attn_bwd_tc": {"flop": 2.5 * attn_full, "byte": 8 * act},
         "k_seq_embed": {"byte": rows_seq * (2 * D * 4 + 8)}, "k_gather": {"byte": rows_items * (2 * D * 4 + 8)},
         "k_embed_all": {"byte": (2 * rows_seq + rows_items) * (2 * D * 4 + 8)},
         "k_mim_scores": {"flop": 2.0 * B * L * L * D, "byte": 2 * act},
         "k_mim_scores_mma": {"flop": 2.0 * B * L * L * D, "byte": 2 * act},
         "k_mim_scores_tc5": {"flop": 3 * 2.0 * B * L * L * D, "byte": 2 * act},   # 3xTF32: three MMAs per product
     }
+    for suffix in ("", "_mma", "_mma3", "_tc"):
+        table["k_attn_fwd" + suffix] = {"flop": attn_full, "byte": 4 * act}          # r: q k v     w: o
+        table["k_attn_bwd" + suffix] = {"flop": 2.5 * attn_full, "byte": 8 * act}    # r: q k v o dO   w: dq dk dv
     for k, (f, b) in chain.items():
         for suffix in ("", "_tc", "_16", "_x3"):
             table[k + suffix] = {"flop": f, "byte": b}
@@ -222,14 +426,17 @@ def kernel_work(name, B, L, C):
 
 
 def measured_traffic(name, a):
-    """dram__bytes_read.sum + dram__bytes_write.sum of one launch from the committed `ncu --set full` capture
-    (profiles/r01_traffic_c3.json); only meaningful for the default C3 shape it was captured on."""
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch from the committed `ncu --set full` captures
+    (profiles/r02_traffic_c3.json, else the round-1 file); only meaningful for the default C3 shape."""
     if (a.batch, a.seq_len, a.neg) != (1024, 200, 1):
         return None
-    path = os.path.join(ROOT, "profiles", "r01_traffic_c3.json")
-    if not os.path.exists(path):
-        return None
-    return json.load(open(path)).get("bytes_per_launch", {}).get(name)
+    for f in ("r02_traffic_c3.json", "r01_traffic_c3.json"):
+        path = os.path.join(ROOT, "profiles", f)
+        if os.path.exists(path):
+            v = json.load(open(path)).get("bytes_per_launch", {}).get(name)
+            if v is not None:
+                return v
+    return None
 
 
 def gather_gbs(model, a, iters=40):
@@ -274,7 +481,10 @@ def gather_gbs(model, a, iters=40):
     return nbytes / (us * 1e-6) / 1e9, us
 
 
-def eval_full_catalogue_users_per_sec(a, n_batches=12):
+# ------------------------------------------------------------------------------------------------
+# evaluation metrics (BASELINE metric 3 and config 5), each with its CPU baseline and roofline
+# ------------------------------------------------------------------------------------------------
+def eval_full_catalogue_users_per_sec(a, pk, n_batches=12):
     """BASELINE config 5 on one GPU: 256-user eval batches (L=20, the C1 eval shape), every user ranked against the
     whole item pool of its target domain (16,084 / 12,153 items: the cloth_sport_train75 pools) by
     csrc/catalogue.cu; includes the encoder forward, the D2H of the counts and the metric reduce."""
@@ -291,12 +501,13 @@ def eval_full_catalogue_users_per_sec(a, n_batches=12):
     perm = torch.from_numpy(rng.permutation(V_ITEMS)[:n1 + n2])
     pool1, pool2 = perm[:n1], perm[n1:]
     cat = tr.catalogue(pool1, pool2)
-    bs = []
+    bs, hosts = [], []
     for _ in range(4):
         b = synth_batch(rng, B, L, 2, V_ITEMS)
         dom = b["domain_id"]
         b["i_node"] = torch.where(dom == 0, pool1[torch.from_numpy(rng.integers(0, n1, B))], pool2[torch.from_numpy(rng.integers(0, n2, B))])
         b["overlap_label"] = torch.from_numpy(rng.integers(0, 2, B))
+        hosts.append(b)
         bs.append(tr.to_device(b))
     evaluate.evaluate_full_catalogue(tr.P, tr.cfg, cat, bs[:2])
     torch.cuda.synchronize()
@@ -329,13 +540,38 @@ def eval_full_catalogue_users_per_sec(a, n_batches=12):
     e1.record()
     torch.cuda.synchronize()
     kernel_pairs = 5.0 * nu * n1 / (e0.elapsed_time(e1) / 1e3)
-    return {"metric": "eval_users_per_sec_full_catalogue", "value": n_batches * B / dt, "unit": "users/s",
-            "ms_per_batch": 1e3 * dt / n_batches, "pairs_per_sec": pairs / dt,
-            "kernel_pairs_per_sec": kernel_pairs, "kernel_users_per_sec": kernel_pairs / n1,
-            "config": f"256 users per batch, L={L}, pools {n1} / {n2} items (every pool item scored, fp32 post-sigmoid), 1 GPU"}
+    # the U x I stage is FP32-ALU bound (ReLU couples user and item inside the nonlinearity): ~165 issued
+    # instructions per (user, item) pair against 148 SMs x 128 lanes at the measured SM clock
+    alu_peak = 148 * 128 * 1.965e9 / 165.0
+    out = {"metric": "eval_users_per_sec_full_catalogue", "value": n_batches * B / dt, "unit": "users/s",
+           "ms_per_batch": 1e3 * dt / n_batches, "pairs_per_sec": pairs / dt,
+           "kernel_pairs_per_sec": kernel_pairs, "kernel_users_per_sec": kernel_pairs / n1,
+           "roofline": {"kernel": "k_rank_full", "bound": "fp32-alu", "achieved": kernel_pairs / 1e9, "peak": alu_peak / 1e9,
+                        "unit": "Gpair/s", "frac": kernel_pairs / alu_peak, "traffic": None,
+                        "note": "peak = 148 SMs x 128 fp32 lanes x 1.965 GHz / 165 instructions per pair"},
+           "config": f"256 users per batch, L={L}, pools {n1} / {n2} items (every pool item scored, fp32 post-sigmoid), 1 GPU"}
+    if not a.no_cpu_baseline:
+        try:
+            from oracle import amid_oracle as O
+            Pc = {k: v.detach().cpu() for k, v in tr.P.items()}
+            hb = hosts[0]
+            cores = os.cpu_count() or 1
+            torch.set_num_threads(cores)
+            t0 = time.perf_counter()
+            with torch.no_grad():
+                O.full_catalogue_scores(Pc, hb["i_node"], hb["seq_d1"], hb["seq_d2"], hb["domain_id"], pool1, pool2,
+                                        isInC=False, isItC=True, ts1=0.5, ts2=0.4)
+            dtc = time.perf_counter() - t0
+            out["cpu_baseline"] = {"value": B / dtc, "unit": "users/s", "cores": cores, "kind": "port",
+                                   "sample": f"one 256-user batch against the whole pool of each user's domain: oracle forward + "
+                                             f"predictModule over the pool (the reference itself never scores a full catalogue, "
+                                             f"dataset_seq.py:201)"}
+        except Exception as e:
+            out["cpu_baseline"] = {"value": None, "kind": "port", "sample": f"failed: {e!r}"}
+    return out
 
 
-def eval_users_per_sec(a, n_batches=20):
+def eval_users_per_sec(a, pk, n_batches=20):
     """BASELINE metric 3 ("eval users/sec"): the C1 evaluation shape of run.sh -- 256 users per batch,
     1 + 999 candidates, L = 20 -- scored in eval mode and ranked on the device (test() of train_sr.py:31-128).
     One GPU (rank 0), batches resident in HBM, includes the D2H of the rank counts and the metric reduce."""
@@ -348,7 +584,8 @@ def eval_users_per_sec(a, n_batches=20):
     m.cfg.precision = a.precision
     tr = Trainer(m)
     rng = np.random.default_rng(7)
-    bs = [tr.to_device(synth_batch(rng, B, L, C, V_ITEMS)) for _ in range(4)]
+    hosts = [synth_batch(rng, B, L, C, V_ITEMS) for _ in range(4)]
+    bs = [tr.to_device(h) for h in hosts]
 
     def one(i):
         b = bs[i % 4]
@@ -363,10 +600,94 @@ def eval_users_per_sec(a, n_batches=20):
         one(i)
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
-    return {"metric": "eval_users_per_sec", "value": n_batches * B / dt, "unit": "users/s", "ms_per_batch": 1e3 * dt / n_batches,
-            "config": f"{B} users x {C} candidates per batch, L={L}, SASRec+ItC, device ranking + HR/NDCG/MRR, 1 GPU"}
+    users = n_batches * B / dt
+    bytes_user = (2 * L + C) * (2 * D * 4 + 8)                            # 1,073,280 B per user at C=1000
+    out = {"metric": "eval_users_per_sec", "value": users, "unit": "users/s", "ms_per_batch": 1e3 * dt / n_batches,
+           "roofline": {"kernel": "k_embed_all (candidate + history gather: the only O(C) HBM traffic of an eval batch)",
+                        "bound": "hbm", "achieved": users * bytes_user / 1e9, "peak": pk["hbm"], "unit": "GB/s",
+                        "frac": users * bytes_user / 1e9 / pk["hbm"], "traffic": None,
+                        "note": "end-to-end users/s x algorithmic gather bytes per user; the batch loop is launch- and "
+                                "host-sync-bound at B=256, see eval_graph in DESIGN.md"},
+           "config": f"{B} users x {C} candidates per batch, L={L}, SASRec+ItC, device ranking + HR/NDCG/MRR, 1 GPU"}
+    rl = _ref()
+    if not a.no_cpu_baseline and rl is not None:
+        try:
+            ref = rl.load("cpu")
+            ms, ut = ref.model_seq, ref.utils
+            cores = os.cpu_count() or 1
+            torch.set_num_threads(cores)
+            with ref.on_cpu():
+                torch.manual_seed(1)
+                rm = ms.SASRec(0, D, V_ITEMS, D, L, HID, B, False, True, 0.5, 0.4).eval()
+                ts = []
+                with torch.no_grad():
+                    for k in range(2):
+                        b = hosts[k]
+                        t0 = time.perf_counter()
+                        p1, p2 = rm(b["i_node"], b["i_node"], b["neg_samples"], b["seq_d1"], b["seq_d2"], b["i_node"], b["i_node"])
+                        pred = np.where((b["domain_id"] == 0).numpy()[:, None], p1.numpy(), p2.numpy())
+                        ut.get_sample_scores(pred)
+                        if k:
+                            ts.append(time.perf_counter() - t0)
+            out["cpu_baseline"] = {"value": B / float(np.mean(ts)), "unit": "users/s", "cores": cores, "kind": "reference",
+                                   "sample": "one timed 256-user x 1000-candidate batch (after one warm-up): unpatched reference "
+                                             "model_seq.SASRec (literal InterComp) + utils.get_sample_scores"}
+        except Exception as e:
+            out["cpu_baseline"] = {"value": None, "kind": "reference", "sample": f"failed: {e!r}"}
+    return out
 
 
+# ------------------------------------------------------------------------------------------------
+# data-parallel correctness record (rank 0 replays the global batch on one GPU)
+# ------------------------------------------------------------------------------------------------
+def dp_check(dctx, world, rank, precision):
+    """Small-shape DP step (dropout ON, per-rank masks) against a single-GPU replay of the same global batch on rank 0:
+    max relative differences of the loss, of the all-reduced dense gradients, and of the parameters after the step,
+    for the table strategies that apply.  Every rank takes part in the collectives; rank 0 returns the record."""
+    from common import make_params
+    from amid_b200.engine import Trainer
+    from amid_b200.model_seq import SASRec
+    Bl, L, C, V = 8, 24, 2, 512
+    Bg = Bl * world
+    P = make_params(9, V, D, L, HID, Bg)
+    rng = np.random.default_rng(3)
+    b = synth_batch(rng, Bg, L, C, V)
+
+    def build():
+        m = SASRec(10, D, V, D, L, HID, Bg, False, True, 0.5, 0.3)
+        m.load_state_dict(P)
+        m.cfg.precision = precision
+        return m.cuda().train()
+
+    out = {}
+    for mode in ("sparse", "dense", "sharded"):
+        tr = Trainer(build(), lr=1e-3, dist=dctx, table_sync=mode)
+        shard = {k: v[rank * Bl:(rank + 1) * Bl].cuda().contiguous() for k, v in b.items()}
+        loss = tr.step(shard).clone()
+        g = tr.flat_g.clone()
+        tr.flush()
+        table = tr.full_table().clone()
+        params = tr.flat_p.clone()
+        torch.cuda.synchronize()
+        if rank == 0:
+            ref = Trainer(build(), lr=1e-3)
+            ref.model._seed_base = tr.model._seed_base
+            l1 = ref.step({k: v.cuda().contiguous() for k, v in b.items()})
+            ref.flush()
+            rel = lambda x, y: float((x - y).norm() / y.norm().clamp_min(1e-30))
+            out[mode] = {"loss_rel": abs(float(loss[0]) - float(l1[0])) / max(abs(float(l1[0])), 1e-30),
+                         "dense_grad_rel": rel(g, ref.flat_g), "dense_param_rel": rel(params, ref.flat_p),
+                         "table_rel": rel(table[:V], ref.table.data[:V])}
+        del tr
+    if rank == 0:
+        worst = max(max(v.values()) for v in out.values())
+        out["ok"] = bool(worst < 1e-4)
+        out["config"] = (f"{world} ranks x {Bl} sequences, L={L}, V={V}, dropout 0.5 with row-indexed masks, one Adam step; "
+                         f"relative Frobenius differences against a single-GPU replay of the global batch on rank 0")
+    return out if rank == 0 else None
+
+
+# ------------------------------------------------------------------------------------------------
 def run_ours(a):
     from amid_b200 import _abi
     from amid_b200.engine import Trainer
@@ -447,11 +768,27 @@ def run_ours(a):
     l0 = _abi.kernel_launches()
     ms_total = timed(dev_step, a.steps)
     launches = _abi.kernel_launches() - l0
-    clk = clocks.stop() if rank == 0 else None
     for i in range(2):
         host_step(i)
     ms_e2e = timed(host_step, a.steps)
+    clk = clocks.stop() if rank == 0 else None
     h2d = sum(v.numel() * (4 if k == "label" else 8) for k, v in host[0].items())
+
+    # the other precision modes on the same trainer, same batches (all ranks take part: the steps contain collectives)
+    precisions = {}
+    if not a.no_extras:
+        for mode in PRECISIONS:
+            if mode == a.precision:
+                precisions[mode] = {"seqs_per_sec": Bg / (ms_total / a.steps / 1e3), "ms_per_step": ms_total / a.steps,
+                                    "steps": a.steps, "note": PREC_NOTE[mode] + " -- the timed mode of this line"}
+                continue
+            model.cfg.precision = mode
+            n = 6 if mode == "fp32" else 10
+            for i in range(2):
+                dev_step(i)
+            ms = timed(dev_step, n)
+            precisions[mode] = {"seqs_per_sec": Bg / (ms / n / 1e3), "ms_per_step": ms / n, "steps": n, "note": PREC_NOTE[mode]}
+        model.cfg.precision = a.precision
 
     # per-kernel CUDA-event profile of 3 more steps of the same workload (rank 0 reports).  The two encoder
     # chains are serialised for these steps: with both streams active a kernel's event interval would also
@@ -465,6 +802,13 @@ def run_ours(a):
     _abi.profile(False)
     model.cfg.overlap_encoders = True
     final_loss = float(tr.last_losses[0].item())
+
+    dpc = None
+    if world > 1 and not a.no_extras:
+        try:
+            dpc = dp_check(dctx, world, rank, a.precision)
+        except Exception as e:
+            dpc = {"ok": False, "error": repr(e)}
 
     if rank != 0:
         if world > 1:
@@ -515,19 +859,27 @@ def run_ours(a):
         except Exception as e:                     # keep the in-step number
             roofline_gather["isolated_error"] = repr(e)
     # tensor-pipe utilisation is quoted on the 12*L*d^2 projection/FFN part only (fwd + 2x bwd),
-    # over the time of the kernels that hold those contractions
+    # over the time of the kernels that hold those contractions.  `issued` counts the MMAs the split-operand mode
+    # actually issues for them (3 FP16-pair products per chain GEMM, 6 BF16-triple products per weight gradient).
+    strip = lambda n: n.split("_tc")[0].split("_16")[0].split("_x3")[0]
     gemm_ms = sum(e["ms_per_step"] for e in breakdown
-                  if e["kernel"].split("_tc")[0].split("_16")[0].split("_x3")[0] in ("k_ln_qkv", "k_proj_ffn", "k_ffn_bwd", "k_qkv_bwd", "k_wgrad"))
+                  if strip(e["kernel"]) in ("k_ln_qkv", "k_proj_ffn", "k_ffn_bwd", "k_qkv_bwd", "k_wgrad"))
     gemm_flop = 3.0 * 4 * 12 * L * D * D * B          # 2 blocks x 2 encoders, fwd + dX + dW
+    issued = {"x3": (2 * 3 + 6) / 3.0}.get(a.precision, 1.0)
     tensor_pipe = None if gemm_ms <= 0 else {
         "flop_per_step": gemm_flop, "ms_in_gemm_kernels": gemm_ms, "achieved_tflops": gemm_flop / (gemm_ms / 1e3) / 1e12,
         "peak_tflops": pk["tensor"], "frac": gemm_flop / (gemm_ms / 1e3) / 1e12 / pk["tensor"],
-        "note": "d=128 chains move 5-11 fp32 activation tensors per 3-6 GEMMs (32-64 flop/B): HBM-bound, see per-kernel frac"}
+        "issued_mma_tflops": issued * gemm_flop / (gemm_ms / 1e3) / 1e12,
+        "issued_frac": issued * gemm_flop / (gemm_ms / 1e3) / 1e12 / pk["tensor"],
+        "note": "d=128 chains move 5-11 fp32 activation tensors per 3-6 GEMMs (32-64 flop/B): HBM-bound, see per-kernel frac; "
+                "issued_* counts the extra piece products of the fp32-accurate split"}
     line = {
         "metric": "train_seqs_per_sec", "value": Bg / (ms_step / 1e3), "unit": "seq/s", "n_gpus": world,
         "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": {"fp32": "f32", "x3": "f32", "tf32": "tf32", "bf16": "bf16"}[a.precision], "data": "synthetic",
+        "vs_baseline": None, "dtype": {"fp32": "f32", "x3": "f32", "tf32": "tf32", "bf16": "bf16"}[a.precision],
+        "data": "synthetic",
         "config": {"workload": workload_name(a), "global_batch": Bg, "seq_len": L, "parallelism": f"dp{world}",
+                   "precision": a.precision + ": " + PREC_NOTE[a.precision],
                    "l2": "no explicit flush: each step streams ~8 GB of activations, far larger than the 126 MB L2",
                    "table_update": ("dense" if a.dense_table else "row-sparse lazy Adam (exact dense semantics)") if world == 1
                    else f"table_sync={tr.table_sync}"},
@@ -538,26 +890,31 @@ def run_ours(a):
         "roofline": roofline,
         "roofline_gather": roofline_gather,
         "tensor_pipe": tensor_pipe,
+        "precisions": precisions,
         "kernel_breakdown": breakdown[:12],
         "kernel_tail_ms": {e["kernel"]: round(e["ms_per_step"], 4) for e in breakdown[12:]},
         "final_loss": final_loss,
     }
-    try:
-        line["eval"] = eval_users_per_sec(a)
-    except Exception as e:
-        line["eval"] = {"value": None, "error": repr(e)}
-    try:
-        line["eval_full_catalogue"] = eval_full_catalogue_users_per_sec(a)
-    except Exception as e:
-        line["eval_full_catalogue"] = {"value": None, "error": repr(e)}
+    if dpc is not None:
+        line["dp_check"] = dpc
+    if not a.no_extras:
+        for key, fn in (("eval", eval_users_per_sec), ("eval_full_catalogue", eval_full_catalogue_users_per_sec)):
+            try:
+                line[key] = fn(a, pk)
+            except Exception as e:
+                line[key] = {"value": None, "error": repr(e)}
+        if world == 1:
+            try:
+                line["c1"] = c1_ours(a.precision)
+                if not a.no_cpu_baseline:
+                    line["c1"]["cpu_baseline"] = c1_reference_cpu()
+            except Exception as e:
+                line["c1"] = {"value": None, "error": repr(e)}
     if world == 1 and not a.no_cpu_baseline:
         try:
-            v, ms, cores = cpu_reference_steps(a, 2, 1, a.cpu_sample)
-            line["cpu_baseline"] = {"value": v, "unit": "seq/s", "cores": cores, "kind": "port", "ms_per_step": ms,
-                                    "sample": f"{a.cpu_sample} sequences per step of the same workload, 1 warm-up + 2 "
-                                              f"timed steps; oracle port + torch.optim.Adam, closed-form ItC"}
+            line["cpu_baseline"] = cpu_train_baseline(a, 2, 1, a.cpu_sample, "closed_form_itc")
         except Exception as e:  # the baseline is reported beside the number, never a reason to lose it
-            line["cpu_baseline"] = {"value": None, "unit": "seq/s", "cores": os.cpu_count(), "kind": "port",
+            line["cpu_baseline"] = {"value": None, "unit": "seq/s", "cores": os.cpu_count(), "kind": "reference",
                                     "sample": f"failed: {e!r}"}
     print(json.dumps(line), flush=True)
     if world > 1:

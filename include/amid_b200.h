@@ -36,6 +36,9 @@ typedef struct {
     float p;            /* drop probability (reference: 0.5 everywhere, model_seq.py:335,350,355) */
     uint64_t seed;      /* per-step seed */
     uint32_t site_base; /* first site id used by this call (an encoder uses 7 sites) */
+    int32_t batch_offset; /* position of this call's first sample in the GLOBAL batch: the keep bits are indexed by
+                           * global sample, so a data-parallel rank draws exactly the bits a single GPU would draw for
+                           * its slice (0 on a single GPU) */
 } amid_dropout;
 
 /* One Log2feats encoder (model_seq.py:331-357).  Used for parameters (read) and for

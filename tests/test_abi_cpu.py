@@ -109,7 +109,7 @@ def test_bench_and_entry_points_compile_and_parse(monkeypatch):
     bench = importlib.import_module("bench")
     monkeypatch.setattr(sys, "argv", ["bench.py", "--gpus", "2", "--steps", "5", "--warmup", "3", "--impl", "reference"])
     a = bench.parse()
-    assert (a.gpus, a.steps, a.warmup, a.impl, a.precision, a.table_sync, a.ids) == (2, 5, 3, "reference", "bf16", "auto", "uniform")
+    assert (a.gpus, a.steps, a.warmup, a.impl, a.precision, a.table_sync, a.ids) == (2, 5, 3, "reference", "x3", "auto", "uniform")
     w = bench.kernel_work("k_attn_bwd_mma", 1024, 200, 2)
     assert w["byte"] == 8 * 1024 * 200 * 128 * 4 and w["flop"] > 0
     rng = np.random.default_rng(0)
