@@ -286,11 +286,13 @@ class Trainer:
         self.flush()
         return evaluate.Catalogue(self.P, self.cfg, pool_d1, pool_d2)
 
-    def evaluate_full_catalogue(self, cat, batches):
+    def evaluate_full_catalogue(self, cat, batches, fast: bool = True):
         """HR/NDCG/MRR of every user against the whole pool of its target domain.  Under data parallelism each
-        rank passes its own contiguous block of whole eval batches; the rank lists are gathered in rank order."""
+        rank passes its own contiguous block of whole eval batches; the rank lists are gathered in rank order.
+        ``fast`` = graph-replayed forwards, one rank launch per domain, one read-back (same result)."""
         from . import evaluate
-        return evaluate.evaluate_full_catalogue(self.P, self.cfg, cat, batches, self.dist)
+        fn = evaluate.evaluate_full_catalogue_fast if fast else evaluate.evaluate_full_catalogue
+        return fn(self.P, self.cfg, cat, list(batches), self.dist)
 
     def full_table(self) -> torch.Tensor:
         """The whole [V,128] item table on every rank (checkpoint / state_dict); pending lazy-Adam rows are flushed."""

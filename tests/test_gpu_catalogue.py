@@ -120,3 +120,55 @@ def test_catalogue_saturated_ties_fall_back_to_numpy_rule():
         assert np.all(rn == (-row).argsort().argsort()[0])
         row[0] = row[0] - 1e-7
         assert np.all(rf == (-row).argsort().argsort()[0])
+
+
+@pytest.mark.parametrize("graph", [False, True])
+def test_fast_full_catalogue_equals_per_batch_path(graph):
+    """evaluate_full_catalogue_fast (graph-replayed forwards, one rank launch per domain, one read-back, ties resolved at
+    the end) returns exactly the metrics of the per-batch path, on several batches with overlap lists."""
+    from amid_b200 import evaluate
+    P, m, tr, batch, pool_d1, pool_d2 = _setup(B=16, n1=300, n2=410, seed=21)
+    cat = tr.catalogue(pool_d1, pool_d2)
+    rng = np.random.default_rng(4)
+    batches = []
+    for k in range(3):
+        b = {kk: v.clone() for kk, v in batch.items()}
+        perm = torch.from_numpy(rng.permutation(16))
+        b = {kk: v[perm].contiguous() for kk, v in b.items()}
+        b["overlap_label"] = torch.from_numpy(rng.integers(0, 2, 16))
+        batches.append({kk: v.cuda() for kk, v in b.items()})
+    want = evaluate.evaluate_full_catalogue(tr.P, tr.cfg, cat, batches)
+    got = evaluate.evaluate_full_catalogue_fast(tr.P, tr.cfg, cat, batches, graph=graph)
+    assert set(got) == set(want)
+    for k in want:
+        assert got[k] == want[k], k
+
+
+def test_fast_full_catalogue_saturated_ties():
+    from amid_b200 import evaluate
+    P, m, tr, batch, pool_d1, pool_d2 = _setup(B=8, n1=130, n2=70, seed=3)
+    with torch.no_grad():
+        tr.P["predictModule.fc.2.bias"].fill_(60.0)
+        tr.P["predictModule.fc.2.weight"].zero_()
+    dev = {k: v.cuda() for k, v in batch.items()}
+    cat = tr.catalogue(pool_d1, pool_d2)
+    want = evaluate.evaluate_full_catalogue(tr.P, tr.cfg, cat, [dev, dev])
+    got = evaluate.evaluate_full_catalogue_fast(tr.P, tr.cfg, cat, [dev, dev])
+    assert got == want
+
+
+def test_graphed_eval_forward_equals_eager():
+    """CUDA-graph replay of the eval forward (C1 shape) returns the eager probabilities bit for bit, batch after batch."""
+    from amid_b200 import evaluate
+    P, m, tr, batch, pool_d1, pool_d2 = _setup(B=16, n1=300, n2=410, seed=5)
+    dev = {k: v.cuda() for k, v in batch.items()}
+    B, L = dev["seq_d1"].shape
+    rng = np.random.default_rng(0)
+    C = 7
+    gf = evaluate.GraphedForward(tr.P, tr.cfg, B, L, C)
+    for it in range(3):
+        neg = torch.from_numpy(rng.integers(0, 700, (B, C - 1))).cuda()
+        b = {**dev, "neg_samples": neg, "seq_d1": torch.roll(dev["seq_d1"], it, 0).contiguous()}
+        want = tr.scores(b)
+        got = gf.run(b)
+        assert torch.equal(got, want)
