@@ -106,6 +106,8 @@ _SIGS = {
     "amid_adam_dense": (c_int32, [P, P, P, P, c_int64, c_int32, c_float, c_float, c_float, c_float, P]),
     "amid_adam_rows_lazy": (c_int32, [P, P, P, P, P, P, P, c_int64, c_int32, c_float, c_float, c_float, c_float, P]),
     "amid_adam_rows_flush": (c_int32, [P, P, P, P, c_int64, c_int32, c_float, c_float, c_float, c_float, P]),
+    "amid_shard_plan_workspace_bytes": (c_int64, [c_int64]),
+    "amid_shard_plan": (c_int32, [P, c_int64, c_int64, c_int32, P, P, P, P, P, c_int64, P]),
     "amid_rank_counts": (c_int32, [P, c_int64, c_int32, c_float, P, P, P]),
     "amid_batch_build": (c_int32, [POINTER(BatchSource), P, c_int32, c_int32, c_int32, c_int32, c_int64, c_uint64,
                                   POINTER(BatchOut), P]),

@@ -432,3 +432,99 @@ extern "C" int amid_adam_rows_flush(float* table, float* m, float* v, int32_t* l
     AMID_LAUNCH_CHECK("k_adam_rows_flush");
     return 0;
 }
+
+// ------------------------------------------------------------------ row-sharded table: the lookup plan of one step
+// (BASELINE config 4; amid_b200/sharded.py).  owner = id mod G, owner-local row = id div G.  One sort of the keys
+// owner * Vs + local puts the step's ids in bucket order (by owner, ascending id inside); run-length encoding yields the
+// unique rows, an exclusive scan their first positions, and two small kernels emit, entirely on the device,
+//   uniq_local[u]   owner-local row index of unique row u (bucket order = the order of the step table)
+//   virtual_ids[p]  row of the step table for every requested position p
+//   send_counts[o]  unique rows requested from owner o
+//   flags           {number of unique rows (a trailing group of out-of-range ids included), out-of-range seen}
+namespace amid {
+__global__ void k_plan_keys(const int64_t* __restrict__ ids, int64_t n, int64_t V, uint32_t G, uint32_t Vs,
+                            uint32_t* __restrict__ keys, uint32_t* __restrict__ vals, int* __restrict__ flags) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int64_t id = ids[i];
+    const bool ok = id >= 0 && id < V;
+    if (!ok) atomicOr(flags + 1, 1);
+    keys[i] = ok ? (uint32_t)(id % G) * Vs + (uint32_t)(id / G) : G * Vs;
+    vals[i] = (uint32_t)i;
+}
+__global__ void k_plan_emit(const uint32_t* __restrict__ vals, const uint32_t* __restrict__ ukeys, const int* __restrict__ offsets,
+                            const int* __restrict__ n_uniq, int64_t n, uint32_t Vs, int64_t* __restrict__ uniq_local,
+                            int64_t* __restrict__ virtual_ids, int* __restrict__ flags) {
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    const int nu = n_uniq[0];
+    int lo = 0, hi = nu;                       // last u with offsets[u] <= p
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (offsets[mid] <= p) lo = mid; else hi = mid;
+    }
+    virtual_ids[vals[p]] = lo;
+    if (offsets[lo] == p) uniq_local[lo] = (int64_t)(ukeys[lo] % Vs);
+    if (p == 0) flags[0] = nu;
+}
+__global__ void k_plan_counts(const uint32_t* __restrict__ ukeys, const int* __restrict__ n_uniq, uint32_t G, uint32_t Vs,
+                              int64_t* __restrict__ send_counts) {
+    const uint32_t o = threadIdx.x;
+    if (o >= G) return;
+    const int nu = n_uniq[0];
+    auto lower = [&](uint32_t key) {
+        int lo = 0, hi = nu;
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (ukeys[mid] < key) lo = mid + 1; else hi = mid;
+        }
+        return lo;
+    };
+    send_counts[o] = (int64_t)(lower((o + 1) * Vs) - lower(o * Vs));
+}
+}  // namespace amid
+
+extern "C" int64_t amid_shard_plan_workspace_bytes(int64_t n) {
+    if (n <= 0) return -1;
+    return (int64_t)carve(nullptr, n).total;
+}
+extern "C" int amid_shard_plan(const int64_t* ids, int64_t n, int64_t V, int32_t G, int64_t* uniq_local, int64_t* virtual_ids,
+                               int32_t* flags, int64_t* send_counts, void* workspace, int64_t workspace_bytes, amid_stream_t s_) {
+    cudaStream_t s = (cudaStream_t)s_;
+    AMID_REQUIRE(ids && uniq_local && virtual_ids && flags && send_counts && workspace, "shard_plan: null argument");
+    AMID_REQUIRE(n > 0 && n < (1ll << 31) && V > 0 && G >= 1 && G <= 1024, "shard_plan: bad sizes");
+    const int64_t Vs = (V + G - 1) / G;
+    AMID_REQUIRE(Vs * G < 0xFFFFFFFFll, "shard_plan: V=%lld does not fit 32-bit keys", (long long)V);
+    AMID_REQUIRE(((uintptr_t)workspace & 255) == 0, "shard_plan: misaligned workspace");
+    SegWs w = carve(workspace, n);
+    AMID_REQUIRE((int64_t)w.total <= workspace_bytes, "shard_plan: workspace too small");
+    cudaError_t e = cudaMemsetAsync(flags, 0, 2 * sizeof(int32_t), s);
+    if (e != cudaSuccess) return set_error(-2, "shard_plan: memset: %s", cudaGetErrorString(e));
+    AMID_K("k_plan_keys", s);
+    k_plan_keys<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(ids, n, V, (uint32_t)G, (uint32_t)Vs, w.keys_in, w.vals_in, flags);
+    AMID_LAUNCH_CHECK("k_plan_keys");
+    int end_bit = 1;
+    while (end_bit < 32 && (1ull << end_bit) < (unsigned long long)(Vs * G) + 1) ++end_bit;
+    size_t tb = w.cub_bytes;
+    AMID_K("cub_radix_sort_pairs", s);
+    e = cub::DeviceRadixSort::SortPairs(w.cub_tmp, tb, w.keys_in, w.keys_out, w.vals_in, w.vals_out, (int)n, 0, end_bit, s);
+    ::amid::prof_end();
+    if (e != cudaSuccess) return set_error(-2, "shard_plan: radix sort: %s", cudaGetErrorString(e));
+    int* n_uniq = w.n_long;                   // scratch int of the carve-up
+    AMID_K("cub_rle_scan", s);
+    tb = w.cub_bytes;
+    e = cub::DeviceRunLengthEncode::Encode(w.cub_tmp, tb, w.keys_out, w.ukeys, w.counts, n_uniq, (int)n, s);
+    if (e != cudaSuccess) return set_error(-2, "shard_plan: run-length encode: %s", cudaGetErrorString(e));
+    tb = w.cub_bytes;
+    e = cub::DeviceScan::ExclusiveSum(w.cub_tmp, tb, w.counts, w.offsets, (int)n, s);
+    ::amid::prof_end();
+    if (e != cudaSuccess) return set_error(-2, "shard_plan: scan: %s", cudaGetErrorString(e));
+    AMID_K("k_plan_emit", s);
+    k_plan_emit<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(w.vals_out, w.ukeys, w.offsets, n_uniq, n, (uint32_t)Vs, uniq_local,
+                                                            virtual_ids, flags);
+    AMID_LAUNCH_CHECK("k_plan_emit");
+    AMID_K("k_plan_counts", s);
+    k_plan_counts<<<1, 1024, 0, s>>>(w.ukeys, n_uniq, (uint32_t)G, (uint32_t)Vs, send_counts);
+    AMID_LAUNCH_CHECK("k_plan_counts");
+    return 0;
+}

@@ -91,11 +91,33 @@ class ShardedTable:
         return torch.stack(parts, 1).reshape(self.Vs * self.world, D)[:self.V].contiguous()
 
     # -------------------------------------------------------------- the step's lookup
-    def lookup(self, ids: torch.Tensor) -> Route:
-        if ids.dtype != torch.int64 or ids.dim() != 1:
-            raise ValueError("ids must be a flat int64 tensor")
+    def _plan(self, ids: torch.Tensor):
+        """(send_local [U], virtual_ids [R], send_splits, recv_splits): the step's unique rows in bucket order, the row of
+        the step table for every position, and the all-to-all split sizes.  On CUDA tensors this is ONE call into the
+        library (amid_shard_plan: sort + run-length encode + scan + emit kernels) and one device->host read of
+        2G + 2 integers; the torch expression below only serves the CPU routing test (tests/test_dp_gloo.py), which
+        injects its own gather."""
         G = self.world
-        oob = ((ids < 0) | (ids >= self.V)).any().to(torch.int64).reshape(1)   # read back together with the bucket sizes
+        if ids.is_cuda:
+            from .hotpath import _ptr, _stream
+            n = ids.numel()
+            dev = ids.device
+            uniq_local = torch.empty(n, device=dev, dtype=torch.int64)
+            virt = torch.empty(n, device=dev, dtype=torch.int64)
+            flags = torch.empty(2, device=dev, dtype=torch.int32)
+            send_counts = torch.empty(G, device=dev, dtype=torch.int64)
+            wsb = _abi.lib().amid_shard_plan_workspace_bytes(n)
+            ws = torch.empty(wsb, device=dev, dtype=torch.uint8)
+            _abi.call("amid_shard_plan", _ptr(ids), n, self.V, G, _ptr(uniq_local), _ptr(virt), _ptr(flags), _ptr(send_counts),
+                      _ptr(ws), wsb, _stream())
+            recv_counts = torch.empty_like(send_counts)
+            self.dist.all_to_all_single(recv_counts, send_counts, group=self.group)
+            host = torch.cat((send_counts, recv_counts, flags.to(torch.int64))).tolist()   # the one host read of a lookup
+            if host[-1]:
+                raise IndexError("sharded lookup: item id out of range")
+            send_splits, recv_splits = host[:G], host[G:2 * G]
+            return uniq_local[:sum(send_splits)], virt, send_splits, recv_splits
+        oob = ((ids < 0) | (ids >= self.V)).any().to(torch.int64).reshape(1)
         uniq, inv = torch.unique(ids, return_inverse=True)                 # sorted ascending
         dest = uniq % G
         order = torch.argsort(dest, stable=True)                           # bucket by owner, ascending id inside
@@ -103,18 +125,23 @@ class ShardedTable:
         send_counts = torch.bincount(dest, minlength=G)
         recv_counts = torch.empty_like(send_counts)
         self.dist.all_to_all_single(recv_counts, send_counts, group=self.group)
-        host = torch.cat((send_counts, recv_counts, oob)).tolist()             # the one device->host read of a lookup
-        send_splits, recv_splits = host[:G], host[G:2 * G]
+        host = torch.cat((send_counts, recv_counts, oob)).tolist()
         if host[-1]:
             raise IndexError("sharded lookup: item id out of range")
-        recv_local = torch.empty(sum(recv_splits), device=ids.device, dtype=torch.int64)
-        self.dist.all_to_all_single(recv_local, send_local, recv_splits, send_splits, group=self.group)
-        out_rows = self._gather(self.shard, recv_local)                    # owner side: csrc/gather.cu
-        rows = torch.empty(uniq.numel(), D, device=ids.device, dtype=torch.float32)
-        self.dist.all_to_all_single(rows, out_rows, send_splits, recv_splits, group=self.group)
         slot_of = torch.empty_like(order)                                  # unique index -> row of the step table
         slot_of[order] = torch.arange(order.numel(), device=ids.device)
-        return Route(rows, slot_of[inv].contiguous(), send_splits, recv_splits, recv_local)
+        return send_local, slot_of[inv].contiguous(), host[:G], host[G:2 * G]
+
+    def lookup(self, ids: torch.Tensor) -> Route:
+        if ids.dtype != torch.int64 or ids.dim() != 1:
+            raise ValueError("ids must be a flat int64 tensor")
+        send_local, virtual_ids, send_splits, recv_splits = self._plan(ids.contiguous())
+        recv_local = torch.empty(sum(recv_splits), device=ids.device, dtype=torch.int64)
+        self.dist.all_to_all_single(recv_local, send_local.contiguous(), recv_splits, send_splits, group=self.group)
+        out_rows = self._gather(self.shard, recv_local)                    # owner side: csrc/gather.cu
+        rows = torch.empty(sum(send_splits), D, device=ids.device, dtype=torch.float32)
+        self.dist.all_to_all_single(rows, out_rows, send_splits, recv_splits, group=self.group)
+        return Route(rows, virtual_ids, send_splits, recv_splits, recv_local)
 
     def push_grads(self, route: Route, grad_rows: torch.Tensor) -> torch.Tensor:
         """grad_rows [U,128], one per step-table row (bucket order) -> the gradient rows of every rank's requests to

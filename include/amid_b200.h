@@ -255,6 +255,15 @@ int amid_adam_rows_lazy(float* table, float* m, float* v, int32_t* last_step, co
 int amid_adam_rows_flush(float* table, float* m, float* v, int32_t* last_step, int64_t V, int32_t step,
                          float lr, float beta1, float beta2, float eps, amid_stream_t stream);
 
+/* ---- row-sharded table (BASELINE config 4): the lookup plan of one step, entirely on the device ------------------
+ * owner = id mod G, owner-local row = id div G.  uniq_local [n]: owner-local row of every unique id of the step in bucket
+ * order (by owner, ascending id inside) = the order of the step table; virtual_ids [n]: row of the step table for every
+ * position; send_counts [G]: unique rows requested from each owner; flags [2] = {unique groups, out-of-range id seen}.
+ * Replaces the torch.unique / argsort / bincount plan of round 1 (one sort + run-length encode + scan + 3 small kernels). */
+int64_t amid_shard_plan_workspace_bytes(int64_t n);
+int amid_shard_plan(const int64_t* ids, int64_t n, int64_t V, int32_t G, int64_t* uniq_local, int64_t* virtual_ids,
+                    int32_t* flags, int64_t* send_counts, void* workspace, int64_t workspace_bytes, amid_stream_t stream);
+
 /* ---- a10: eval ranking (utils.py:296-301, train_sr.py:114-115) ---------------------- */
 /* scores [N,C], positive in column 0.  s0 = scores[r,0] - fix (fp32).  n_greater[r] =
  * #{c>=1 : scores[r,c] > s0}, n_equal[r] = #{c>=1 : scores[r,c] == s0}.  The rank of the
