@@ -700,7 +700,8 @@ def dp_check(dctx, world, rank, precision):
 
     out = {}
     for mode in ("sparse", "dense", "sharded"):
-        tr = Trainer(build(), lr=1e-3, dist=dctx, table_sync=mode)
+        from amid_b200.hotpath import DistCtx
+        tr = Trainer(build(), lr=1e-3, dist=DistCtx(), table_sync=mode)
         shard = {k: v[rank * Bl:(rank + 1) * Bl].cuda().contiguous() for k, v in b.items()}
         loss = tr.step(shard).clone()
         g = tr.flat_g.clone()
@@ -724,6 +725,57 @@ def dp_check(dctx, world, rank, precision):
         out["config"] = (f"{world} ranks x {Bl} sequences, L={L}, V={V}, dropout 0.5 with row-indexed masks, one Adam step; "
                          f"relative Frobenius differences against a single-GPU replay of the global batch on rank 0")
     return out if rank == 0 else None
+
+
+# ------------------------------------------------------------------------------------------------
+# BASELINE config 4: 10M items per domain, row-sharded table + all-to-all lookups (multi-GPU only)
+# ------------------------------------------------------------------------------------------------
+def sharded_20m(a, dctx, world, rank, steps=6):
+    """The C3 step with V = 20,000,002 rows (10.2 GB table): the table is never replicated -- rank r keeps rows
+    {r, r+G, ...} and their Adam state, every step fetches the rows it reads with one device-planned all-to-all lookup
+    and returns the gradient rows to their owners (amid_b200/sharded.py).  Every rank calls this; rank 0 returns."""
+    import torch.distributed as dist
+    from amid_b200.engine import Trainer
+    from amid_b200.model_seq import SASRec
+    V = 20_000_002
+    B, L, C = a.batch, a.seq_len, 1 + a.neg
+    torch.manual_seed(0)
+    with torch.device("cuda"):
+        model = SASRec(user_length=0, user_emb_dim=D, item_length=V, item_emb_dim=D, seq_len=L, hid_dim=HID, bs=B * world,
+                       isInC=False, isItC=True, threshold1=0.5, threshold2=0.4, isDR=False)
+    model = model.cuda().train()
+    model.cfg.precision = a.precision
+    from amid_b200.hotpath import DistCtx
+    tr = Trainer(model, lr=5e-4, dist=DistCtx(), table_sync="sharded")    # its own context: the table routing hangs off it
+    torch.cuda.empty_cache()
+    g = torch.Generator(device="cuda").manual_seed(100 + rank)
+    ri = lambda hi, *s: torch.randint(0, hi, s, device="cuda", generator=g)        # int64 ids made on the device (SURVEY 7-7)
+    bs = [{"i_node": ri(V, B), "neg_samples": ri(V, B, C - 1), "seq_d1": ri(V, B, L), "seq_d2": ri(V, B, L),
+           "domain_id": ri(2, B), "label": torch.cat((torch.ones(B, 1), torch.zeros(B, C - 1)), 1).cuda()} for _ in range(3)]
+    for i in range(2):
+        tr.step(bs[i % 3])
+    torch.cuda.synchronize()
+    dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        losses = tr.step(bs[i % 3])
+    e1.record()
+    torch.cuda.synchronize()
+    dist.barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms.item()) / steps
+    mem = torch.cuda.max_memory_allocated() / 2**30
+    loss = float(losses[0].item())
+    del tr, model
+    torch.cuda.empty_cache()
+    if rank != 0:
+        return None
+    return {"metric": "train_seqs_per_sec", "value": B * world / (ms / 1e3), "unit": "seq/s", "ms_per_step": ms, "steps": steps,
+            "n_gpus": world, "precision": a.precision, "final_loss": loss, "peak_hbm_gib_rank0": mem,
+            "config": f"V = {V} rows (10.2 GB fp32 table, never replicated), row-sharded over {world} GPUs, per-GPU batch {B}, "
+                      f"L={L}, uniform int64 ids generated on the device, lookup plan on the device + NCCL all-to-all"}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -848,6 +900,12 @@ def run_ours(a):
             dpc = dp_check(dctx, world, rank, a.precision)
         except Exception as e:
             dpc = {"ok": False, "error": repr(e)}
+    sh20 = None
+    if world > 1 and not a.no_extras and a.items == 894820:
+        try:
+            sh20 = sharded_20m(a, dctx, world, rank)
+        except Exception as e:
+            sh20 = {"value": None, "error": repr(e)}
     efc = None
     if not a.no_extras and tr.table_sync != "sharded":
         try:
@@ -942,6 +1000,8 @@ def run_ours(a):
     }
     if dpc is not None:
         line["dp_check"] = dpc
+    if sh20 is not None:
+        line["sharded_20M"] = sh20
     if not a.no_extras:
         try:
             line["eval"] = eval_users_per_sec(a, pk)
