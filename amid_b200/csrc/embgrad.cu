@@ -361,6 +361,9 @@ extern "C" int amid_embgrad_segreduce(const int64_t* ids, const float* grad_rows
                                                     0, end_bit, s);
     ::amid::prof_end();
     if (e != cudaSuccess) return set_error(-2, "embgrad: radix sort: %s", cudaGetErrorString(e));
+    // the scan below runs over all n slots while the encoder writes only the first n_uniq counts: define the rest
+    e = cudaMemsetAsync(w.counts, 0, (size_t)n * sizeof(int), s);
+    if (e != cudaSuccess) return set_error(-2, "embgrad: memset: %s", cudaGetErrorString(e));
     AMID_K("cub_rle_scan", s);
     tb = w.cub_bytes;
     e = cub::DeviceRunLengthEncode::Encode(w.cub_tmp, tb, w.keys_out, w.ukeys, w.counts, n_uniq, (int)n, s);
@@ -511,6 +514,8 @@ extern "C" int amid_shard_plan(const int64_t* ids, int64_t n, int64_t V, int32_t
     ::amid::prof_end();
     if (e != cudaSuccess) return set_error(-2, "shard_plan: radix sort: %s", cudaGetErrorString(e));
     int* n_uniq = w.n_long;                   // scratch int of the carve-up
+    e = cudaMemsetAsync(w.counts, 0, (size_t)n * sizeof(int), s);
+    if (e != cudaSuccess) return set_error(-2, "shard_plan: memset: %s", cudaGetErrorString(e));
     AMID_K("cub_rle_scan", s);
     tb = w.cub_bytes;
     e = cub::DeviceRunLengthEncode::Encode(w.cub_tmp, tb, w.keys_out, w.ukeys, w.counts, n_uniq, (int)n, s);

@@ -1179,7 +1179,7 @@ static int encoder_bwd_impl(const amid_encoder_tensors* P, const float* x0, cons
             x3::WgradJobsX wx;
             for (int j = 0; j < 6; ++j) { wx.dY[j] = wj.dY[j]; wx.X[j] = wj.X[j]; }
             AMID_K("k_wgrad_x3", stream);
-            x3::k_wgrad_x3<<<dim3(SW, 6), 256, x3::WGRADX_SMEM, stream>>>(wx, M, wpart, bpart);
+            x3::k_wgrad_x3<<<dim3(SW, 6), x3::WGX_THREADS, x3::WGRADX_SMEM, stream>>>(wx, M, wpart, bpart);
             AMID_LAUNCH_CHECK("k_wgrad_x3");
         } else if (mode == 2) {
             tc16::WgradJobs16 w16;

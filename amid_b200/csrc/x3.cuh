@@ -788,12 +788,14 @@ __device__ __forceinline__ void split_bf16x3(float a, float b, uint32_t& p0, uin
     const float sa = ra - __uint_as_float(p1 << 16), sb = rb - __uint_as_float(p1 & 0xFFFF0000u);
     p2 = pack_bf16(sa, sb);
 }
+constexpr int WGX_THREADS = 512;                     // 16 warps: the split / store work of a sub-tile is issue-bound
+constexpr int WGX_IT = SUB_ROWS / (WGX_THREADS / 32);
 // rows [row0, row0+64) of g[M,128] -> three BF16 piece sub-tiles at dst, dst + 16 KB, dst + 32 KB
-__device__ __forceinline__ void fill_sub3(uint8_t* dst, const float4 (&v)[8]) {
+__device__ __forceinline__ void fill_sub3(uint8_t* dst, const float4 (&v)[WGX_IT]) {
     const int c4 = threadIdx.x & 31, rb = threadIdx.x >> 5;
 #pragma unroll
-    for (int it = 0; it < 8; ++it) {
-        const int r = it * 8 + rb;
+    for (int it = 0; it < WGX_IT; ++it) {
+        const int r = it * (WGX_THREADS / 32) + rb;
         uint32_t a0, a1, a2, b0, b1, b2;
         split_bf16x3(v[it].x, v[it].y, a0, a1, a2);
         split_bf16x3(v[it].z, v[it].w, b0, b1, b2);
@@ -803,11 +805,11 @@ __device__ __forceinline__ void fill_sub3(uint8_t* dst, const float4 (&v)[8]) {
         *reinterpret_cast<uint2*>(dst + 2 * SUBP_BYTES + off) = make_uint2(a2, b2);
     }
 }
-__device__ __forceinline__ void load_sub(float4 (&v)[8], const float* __restrict__ g, int row0, int M) {
+__device__ __forceinline__ void load_sub(float4 (&v)[WGX_IT], const float* __restrict__ g, int row0, int M) {
     const int c4 = threadIdx.x & 31, rb = threadIdx.x >> 5;
 #pragma unroll
-    for (int it = 0; it < 8; ++it) {
-        const int r = row0 + it * 8 + rb;
+    for (int it = 0; it < WGX_IT; ++it) {
+        const int r = row0 + it * (WGX_THREADS / 32) + rb;
         v[it] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (r < M) v[it] = __ldg(reinterpret_cast<const float4*>(g + (size_t)r * D) + c4);
     }
@@ -816,7 +818,7 @@ struct WgradJobsX {
     const float* dY[6];
     const float* X[6];
 };
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(WGX_THREADS, 1)
 k_wgrad_x3(WgradJobsX jobs, int M, float* __restrict__ wpart /*[6][S][128*128]*/, float* __restrict__ bpart /*[6][S][128]*/) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ uint64_t bars[2];
@@ -828,7 +830,7 @@ k_wgrad_x3(WgradJobsX jobs, int M, float* __restrict__ wpart /*[6][S][128*128]*/
     const int S = gridDim.x;
     if ((threadIdx.x >> 5) == 0) tmem_alloc(&tmem_s, 256);
     if (threadIdx.x == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); fence_barrier_init(); }
-    for (int i = threadIdx.x; i < ONESX_BYTES / 4; i += 256) reinterpret_cast<uint32_t*>(Ones)[i] = 0x3F803F80u;
+    for (int i = threadIdx.x; i < ONESX_BYTES / 4; i += WGX_THREADS) reinterpret_cast<uint32_t*>(Ones)[i] = 0x3F803F80u;
     fence_async_smem();
     fence_before();
     __syncthreads();
@@ -845,7 +847,7 @@ k_wgrad_x3(WgradJobsX jobs, int M, float* __restrict__ wpart /*[6][S][128*128]*/
     auto sub_of = [&](int i) { return 2 * (blockIdx.x + (i >> 1) * S) + (i & 1); };
     int n_it = 2 * my_pairs;
     if (n_it && sub_of(n_it - 1) >= subs) --n_it;
-    float4 vy[8], vx[8];
+    float4 vy[WGX_IT], vx[WGX_IT];
     if (n_it) { load_sub(vy, dY, sub_of(0) * SUB_ROWS, M); load_sub(vx, X, sub_of(0) * SUB_ROWS, M); }
     int it = 0;
     for (; it < n_it; ++it) {
@@ -883,6 +885,7 @@ k_wgrad_x3(WgradJobsX jobs, int M, float* __restrict__ wpart /*[6][S][128*128]*/
     if (it >= 2) { const int b = it & 1; mbar_wait(&bars[b], phase[b]); phase[b] ^= 1; }
     if (it >= 1) { const int b = (it - 1) & 1; mbar_wait(&bars[b], phase[b]); phase[b] ^= 1; }
     fence_after();
+    if (threadIdx.x < 256) {             // the first 8 warps read the accumulators out (lane quarter = warp & 3)
     Epi e;
     float* wp = wpart + ((size_t)blockIdx.y * S + blockIdx.x) * D * D;
 #pragma unroll 1
@@ -907,6 +910,7 @@ k_wgrad_x3(WgradJobsX jobs, int M, float* __restrict__ wpart /*[6][S][128*128]*/
             a[0] = 0.f;
         }
         bpart[((size_t)blockIdx.y * S + blockIdx.x) * D + e.row] = a[0];
+    }
     }
     fence_before();
     __syncthreads();

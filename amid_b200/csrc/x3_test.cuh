@@ -77,7 +77,7 @@ extern "C" int amid_x3_wgrad_test(const float* dy, const float* x, int32_t M, fl
     x3::WgradJobsX j;
     for (int i = 0; i < 6; ++i) { j.dY[i] = dy; j.X[i] = x; }
     AMID_K("k_wgrad_x3", s_);
-    x3::k_wgrad_x3<<<dim3(n_ctas, 1), 256, x3::WGRADX_SMEM, (cudaStream_t)s_>>>(j, M, wpart, bpart);
+    x3::k_wgrad_x3<<<dim3(n_ctas, 1), x3::WGX_THREADS, x3::WGRADX_SMEM, (cudaStream_t)s_>>>(j, M, wpart, bpart);
     AMID_LAUNCH_CHECK("k_wgrad_x3");
     return 0;
 }
