@@ -12,7 +12,7 @@ LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libamid_b200.so")
 SOURCES = ["abi.cu", "gather.cu", "encoder.cu", "mim.cu", "score.cu", "catalogue.cu", "pipeline.cu", "embgrad.cu", "tc_test.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-              "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC"]
+              "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC"] + (os.environ.get("AMID_NVCC_EXTRA", "").split())
 
 
 def _nvcc() -> str:

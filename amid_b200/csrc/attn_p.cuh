@@ -1,0 +1,551 @@
+// Pipelined causal attention (head_dim 16, 64 <= L <= 256) on tcgen05 at fp32-level accuracy (FP16-pair split of
+// x3.cuh): persistent CTAs (one per SM), warp-specialised, tensor memory double-buffered between two groups of
+// softmax warps, SINGLE-PASS backward.
+//
+// What changed against attn_tc.cuh (one CTA per (sample, head), serial phases, two CTAs per SM):
+//   * one thread of a dedicated warp issues every tcgen05.mma and tracks completion with mbarriers; sixteen
+//     element-wise warps form two sets that work on alternating score blocks, so that the MMAs of one set run
+//     while the other set is in its exp / dropout / split loop ("ping-pong");
+//   * the backward visits every (query, key) pair ONCE (attn_tc.cuh recomputes S and dP in a second, transposed
+//     pass for dK / dV): a set turns its block S, dP [128 queries x 64 keys] into Pd = dropout(P) and dS and stores
+//     both as FP16 pairs into a shared-memory staging tile [query rows][64 keys] (SWIZZLE_128B).  The SAME bytes
+//     are the K-major A operand of dQ += dS K (rows = queries) and the MN-major A operand of dK += dS^T Q and
+//     dV += Pd^T dO (rows = keys);
+//   * no transposed operand copies: k / q / dO enter those three GEMMs as MN-major B operands straight from the
+//     row tiles [position][k0 | k1 | v0 | v1] and [position][q0 | q1 | g0 | g1];
+//   * piece products by stacking: for dK / dV the two A pieces are the two 64-row halves of one M = 128 operand
+//     (leading-dimension offset = distance between the piece tiles), B = b0 then b1 into the same 16 columns, so
+//     lanes [0,64) hold a0 (b0 + b1) and lanes [64,128) a1 (b0 + b1) -- the full product; for dQ B = [k0 | k1] is
+//     one N = 32 operand.  Two MMAs per k-step instead of three;
+//   * the next head's q / k / v / dO / o rows are fetched into registers before the wait for the current head's
+//     last MMAs, so the HBM latency overlaps the drain.
+// Arithmetic as attn_tc.cuh (torch/nn/functional.py:6630-6647), same dropout bits.
+#pragma once
+#include "attn_tc.cuh"
+
+namespace amid {
+namespace attn_p {
+using namespace tc;
+using namespace attn_tc;
+
+constexpr int PMAXL = 256, PMINL = 64;
+constexpr int NTH = 608;                            // 16 element-wise warps + 3 MMA-issuing warps
+constexpr int ROWT_BYTES = 256 * 128;               // row tile: 256 positions x [4 pieces of 16 fp16]
+constexpr int STG_TILE = 128 * 128;                 // [128 query rows][64 keys] fp16
+constexpr int STG_SET = 4 * STG_TILE;               // Pd piece 0, Pd piece 1, dS piece 0, dS piece 1
+constexpr size_t PBWD_SMEM = 2 * (size_t)ROWT_BYTES + 2 * (size_t)STG_SET + 1024;
+constexpr uint32_t C_DP = 64, C_DQ = 256, C_DK = 320, C_DV = 384;   // buffer b: S at 128 b, dP at 128 b + 64; dQ[qt] 32 cols; dK[kh] 16; dV[kh] 32
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void named_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+
+// descriptor halves: low word = (address >> 4) | (leading-dimension offset >> 4) << 16, high word constant
+// (stride offset 1024 B, version 1, SWIZZLE_128B); an address offset of x bytes is + (x >> 4) on the low word
+constexpr uint32_t DESC_HI = (1024u >> 4) | (1u << 14) | (2u << 29);
+__device__ __forceinline__ uint32_t dlo_k(uint32_t addr) { return (addr >> 4) | (1u << 16); }                       // lbo = 16
+__device__ __forceinline__ uint32_t dlo_m(uint32_t addr) { return (addr >> 4) | ((uint32_t)(STG_TILE >> 4) << 16); } // lbo = one staging tile
+__device__ __forceinline__ void mma_lo(uint32_t tmem_d, uint32_t alo, uint32_t blo, uint32_t idesc, uint32_t accum) {
+    asm volatile(
+        "{\n.reg .pred p;\n.reg .b64 da, db;\nsetp.ne.b32 p, %4, 0;\nmov.b64 da, {%1, %5};\nmov.b64 db, {%2, %5};\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n}"
+        ::"r"(tmem_d), "r"(alo), "r"(blo), "r"(idesc), "r"(accum), "r"(DESC_HI) : "memory");
+}
+__device__ __forceinline__ void mma_lo_ts(uint32_t tmem_d, uint32_t tmem_a, uint32_t blo, uint32_t idesc, uint32_t accum) {
+    asm volatile(
+        "{\n.reg .pred p;\n.reg .b64 db;\nsetp.ne.b32 p, %4, 0;\nmov.b64 db, {%2, %5};\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %3, p;\n}"
+        ::"r"(tmem_d), "r"(tmem_a), "r"(blo), "r"(idesc), "r"(accum), "r"(DESC_HI) : "memory");
+}
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+// S = Q K^T (3 piece products) and dP = dO V^T into [tS, tS + 64) and [tS + 64, tS + 128); al / bl = low descriptor
+// words of the first query row / first key row
+__device__ __forceinline__ void issue_sdp(uint32_t tS, uint32_t al, uint32_t bl, int N) {
+    const uint32_t id = idesc_f16(N, false, false);
+    mma_lo(tS, al, bl, id, 0u);                      // q0 k0
+    mma_lo(tS, al + 2, bl, id, 1u);                  // q1 k0
+    mma_lo(tS, al, bl + 2, id, 1u);                  // q0 k1
+    mma_lo(tS + C_DP, al + 4, bl + 4, id, 0u);       // g0 v0
+    mma_lo(tS + C_DP, al + 6, bl + 4, id, 1u);       // g1 v0
+    mma_lo(tS + C_DP, al + 4, bl + 6, id, 1u);       // g0 v1
+}
+// unit u of a head: key blocks of 64 outer, query tiles of 128 from the diagonal on
+__device__ __forceinline__ void unit_at(int u, int nqt, int& kh, int& qt) {
+    kh = 0;
+    for (;;) {
+        const int c = nqt - (kh >> 1);
+        if (u < c) break;
+        u -= c;
+        ++kh;
+    }
+    qt = (kh >> 1) + u;
+}
+
+#ifdef AMID_ATTN_DBG
+__device__ long long g_dbg[20][256];
+#define DBG(tag) do { if (blockIdx.x == 0 && (threadIdx.x & 31) == 0 && dbg_i < 254) { g_dbg[threadIdx.x >> 5][dbg_i++] = (long long)(tag); g_dbg[threadIdx.x >> 5][dbg_i++] = clock64(); } } while (0)
+#else
+#define DBG(tag) do { } while (0)
+#endif
+
+struct ShPB {
+    uint64_t bar_tiles;       // 16 arrivals: the operand tiles (and ls / dl) of the current head are written
+    uint64_t bar_sready[2];   // tcgen05.commit: S and dP of set s are in tensor memory
+    uint64_t bar_full[2];     // 16 arrivals: every warp stored its part of the staging tiles and is done reading S / dP
+    uint64_t bar_free[2];     // 2 x tcgen05.commit (dK and dV issuers): the MMAs that read the staging tiles of set s are complete
+    uint64_t bar_done;        // 3 x tcgen05.commit: every MMA of the head is complete
+    uint64_t bar_kvgo;        // 1 arrival per unit: the S / dP issuer has queued its MMAs (dK / dV go behind them)
+    uint32_t tmem;
+    float red[4][16];
+    float ls[256];            // lse * log2(e) per query (+inf for rows >= L)
+    float dl[256];            // delta_i = <dO_i, O_i>
+};
+
+struct HeadScal { float f, fdp, sc_q, sc_k, sc_v; };
+struct HeadRegs {             // one head's rows as fetched from HBM: thread = (row r0 + 128 i, features 4 c4 .. 4 c4 + 3)
+    float4 q[2], k[2], v[2], g[2], o[2];
+    float lse[2];
+};
+__device__ __forceinline__ void fetch_head(HeadRegs& h, const float* __restrict__ q, const float* __restrict__ k,
+                                           const float* __restrict__ v, const float* __restrict__ o, const float* __restrict__ dO,
+                                           const float* __restrict__ lse, int bh, int L, int tid) {
+    const int b = bh / H, hd = bh % H;
+    const size_t base = (size_t)b * L * D + hd * DH;
+    const int c4 = tid & 3, r0 = tid >> 2;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const int R = r0 + 128 * i;
+        h.q[i] = h.k[i] = h.v[i] = h.g[i] = h.o[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        h.lse[i] = INFINITY;
+        if (R < L) {
+            const size_t off = base + (size_t)R * D + 4 * c4;
+            h.q[i] = __ldg(reinterpret_cast<const float4*>(q + off));
+            h.k[i] = __ldg(reinterpret_cast<const float4*>(k + off));
+            h.v[i] = __ldg(reinterpret_cast<const float4*>(v + off));
+            h.g[i] = __ldg(reinterpret_cast<const float4*>(dO + off));
+            h.o[i] = __ldg(reinterpret_cast<const float4*>(o + off));
+            if (c4 == 0) h.lse[i] = __ldg(lse + (size_t)bh * L + R);
+        }
+    }
+}
+
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred = 0;
+    asm volatile("{\n.reg .pred P1;\nelect.sync _|P1, 0xffffffff;\nselp.u32 %0, 1, 0, P1;\n}" : "=r"(pred));
+    return pred != 0;
+}
+struct Geo {                  // per-launch geometry (depends on L only)
+    int L, nqt, NKP, nkh, nunits;
+};
+__device__ __forceinline__ Geo make_geo(int L) {
+    Geo g;
+    g.L = L;
+    g.nqt = (L + 127) >> 7;
+    g.NKP = (L + 15) & ~15;
+    g.nkh = (g.NKP + 63) >> 6;
+    g.nunits = 0;
+    for (int kh = 0; kh < g.nkh; ++kh) g.nunits += g.nqt - (kh >> 1);
+    return g;
+}
+
+// ---- MMA-issuing warps.  The whole warp runs the control flow (warp-uniform values stay in uniform registers and
+// ptxas emits back-to-back UTCHMMA); elect.sync picks the lane that issues.
+// role 0: S / dP of both sets and dQ.
+__device__ __forceinline__ void mma_role_sq(ShPB& sh, const Geo g, uint32_t tmem, uint32_t qg, uint32_t kv, uint32_t stg, int nbh) {
+    constexpr uint32_t idq = idesc_f16(32, false, true);
+    const uint32_t qgl = dlo_k(qg), kvl = dlo_k(kv);
+    uint32_t cnt_full[2] = {0u, 0u}, nhead = 0;
+    int dbg_i = 0;
+    for (int bh = blockIdx.x; bh < nbh; bh += gridDim.x, ++nhead) {
+        DBG(100);
+        mbar_wait(&sh.bar_tiles, nhead & 1);
+        fence_after();
+        DBG(101);
+        for (int u = 0; u < min(2, g.nunits); ++u) {
+            int kh, qt;
+            unit_at(u, g.nqt, kh, qt);
+            if (elect_one()) {
+                issue_sdp(tmem + 128 * u, qgl + (uint32_t)(128 * qt) * 8, kvl + (uint32_t)(64 * kh) * 8, min(64, g.NKP - 64 * kh));
+                mma_commit(&sh.bar_sready[u]);
+            }
+            __syncwarp();
+        }
+        for (int u = 0; u < g.nunits; ++u) {
+            const int s = u & 1;
+            int kh, qt, kh2 = 0, qt2 = 0;
+            unit_at(u, g.nqt, kh, qt);
+            const bool more = u + 2 < g.nunits;
+            if (more) unit_at(u + 2, g.nqt, kh2, qt2);
+            const uint32_t a2 = qgl + (uint32_t)(128 * qt2) * 8, b2 = kvl + (uint32_t)(64 * kh2) * 8;
+            const int N2 = min(64, g.NKP - 64 * kh2);
+            const int nkq = min(64, g.NKP - 64 * kh) >> 4;
+            const uint32_t tq = tmem + C_DQ + 32 * qt;
+            const uint32_t ta = tmem + 128 * s, bl = kvl + (uint32_t)(64 * kh) * 8;
+            mbar_wait(&sh.bar_full[s], cnt_full[s] & 1);
+            ++cnt_full[s];
+            fence_after();
+            DBG(110 + u);
+            if (elect_one()) {
+                // dQ[qt] += dS K : A = dS pieces in tensor memory (in place over the consumed score columns: chunk c holds
+                // piece 0 in columns [16c, 16c+8) and piece 1 in [16c+8, 16c+16)), B = [k0 | k1] MN-major, N = 32
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) {
+                    if (ks < nkq) {
+                        mma_lo_ts(tq, ta + 16 * ks, bl + ks * 128, idq, (kh > 0 || ks > 0) ? 1u : 0u);
+                        mma_lo_ts(tq, ta + 16 * ks + 8, bl + ks * 128, idq, 1u);
+                    }
+                }
+                // the same thread issues the next S / dP into this buffer: tcgen05.mma of one thread execute in order
+                if (more) {
+                    issue_sdp(tmem + 128 * s, a2, b2, N2);
+                    mma_commit(&sh.bar_sready[s]);
+                }
+                if (u == g.nunits - 1) mma_commit(&sh.bar_done);
+                mbar_arrive(&sh.bar_kvgo);
+            }
+            __syncwarp();
+            DBG(120 + u);
+        }
+    }
+}
+// role 1: dK[kh] += dS^T Q;  role 2: dV[kh] += Pd^T dO.  A = the two pieces stacked along M (MN-major, leading-dimension
+// offset = one staging tile), B = b0 then b1 (MN-major, N = 16) into the same 16 accumulator columns.
+template <int ROLE>
+__device__ __forceinline__ void mma_role_kv(ShPB& sh, const Geo g, uint32_t tmem, uint32_t qg, uint32_t stg, int nbh) {
+    constexpr uint32_t idk = idesc_f16(16, true, true), idv = idesc_f16(32, true, true);
+    const uint32_t qgl = dlo_k(qg) + (ROLE == 2 ? 4u : 0u);
+    uint32_t cnt_full[2] = {0u, 0u}, cnt_go = 0;
+    for (int bh = blockIdx.x; bh < nbh; bh += gridDim.x) {
+        for (int u = 0; u < g.nunits; ++u) {
+            const int s = u & 1;
+            int kh, qt;
+            unit_at(u, g.nqt, kh, qt);
+            const int nks = min(8, (min(g.L, 128 * (qt + 1)) - 128 * qt + 15) >> 4);
+            const int ks0 = max(0, (64 * kh - 128 * qt) >> 4);        // queries before the first key of the block are masked
+            const uint32_t td = ROLE == 1 ? tmem + C_DK + 16 * kh : tmem + C_DV + 32 * kh;
+            const uint32_t al = dlo_m(stg + (uint32_t)s * STG_SET + (ROLE == 1 ? 2 * STG_TILE : 0));
+            const uint32_t bl = qgl + (uint32_t)(128 * qt) * 8;
+            const bool first = qt == (kh >> 1);
+            mbar_wait(&sh.bar_full[s], cnt_full[s] & 1);
+            ++cnt_full[s];
+            mbar_wait(&sh.bar_kvgo, cnt_go & 1);
+            ++cnt_go;
+            fence_after();
+            if (elect_one()) {
+#pragma unroll
+                for (int ks = 0; ks < 8; ++ks) {
+                    if (ks >= ks0 && ks < nks) {
+                        const uint32_t acc = (first && ks == ks0) ? 0u : 1u;
+                        if (ROLE == 1) {
+                            mma_lo(td, al + ks * 128, bl + ks * 128, idk, acc);
+                            mma_lo(td, al + ks * 128, bl + ks * 128 + 2, idk, 1u);
+                        } else {
+                            mma_lo(td, al + ks * 128, bl + ks * 128, idv, acc);        // [a0 ; a1] x [g0 | g1]
+                        }
+                    }
+                }
+                mma_commit(&sh.bar_free[s]);
+                if (u == g.nunits - 1) mma_commit(&sh.bar_done);
+            }
+            __syncwarp();
+        }
+    }
+}
+
+// one chunk of a unit: 16 keys of this thread's query row.  S, dP (raw accumulators) -> Pd = dropout(P), dS as FP16 pairs
+template <bool TRAIN, bool DIAG>
+__device__ __forceinline__ void bwd_chunk(uint32_t ts, uint32_t tp, float f, float li, float Di, float fdp, float dsc, int nvalid,
+                                          uint32_t seed, uint32_t site, uint32_t g0, uint32_t thr24,
+                                          uint32_t (&pd0)[8], uint32_t (&pd1)[8], uint32_t (&ds0)[8], uint32_t (&ds1)[8]) {
+    float sx[16], dp[16];
+    tmem_ld16(ts, sx);
+    tmem_ld16(tp, dp);
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+        uint32_t r = 0u;
+        if (TRAIN) r = rng4(seed, site, (uint64_t)(g0 + g));
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int cc = 4 * g + e;
+            float p = ex2(fmaf(sx[cc], f, -li));
+            if (DIAG) p = cc < nvalid ? p : 0.f;
+            float k2 = dsc;
+            if (TRAIN) k2 = (e == 3 ? r : (r << (24 - 8 * e))) >= thr24 ? dsc : 0.f;
+            sx[cc] = p * k2;                                   // Pd
+            dp[cc] = p * fmaf(dp[cc] * k2, fdp, -Di);          // dS (scaled by sds)
+        }
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        split_f16x2(sx[2 * e], sx[2 * e + 1], pd0[e], pd1[e]);
+        split_f16x2(dp[2 * e], dp[2 * e + 1], ds0[e], ds1[e]);
+    }
+}
+
+template <bool TRAIN>
+__global__ void __launch_bounds__(NTH, 1)
+k_attn_bwd_p(const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v,
+             const float* __restrict__ o, const float* __restrict__ lse, const float* __restrict__ dO,
+             float* __restrict__ dq, float* __restrict__ dk, float* __restrict__ dv, int L, int nbh, DropCfg dc, uint32_t site) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ ShPB sh;
+    uint8_t* QG = align1k(smem_raw);                // [position][q0 | q1 | g0 | g1]
+    uint8_t* KV = QG + ROWT_BYTES;                  // [position][k0 | k1 | v0 | v1]
+    uint8_t* STG = KV + ROWT_BYTES;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const Geo g = make_geo(L);
+    const int nqt = g.nqt, NKP = g.NKP, nkh = g.nkh, Lp4 = ((L + 3) & ~3) >> 2;
+    if (warp == 16) tmem_alloc(&sh.tmem, 512);
+    if (tid == 0) {
+        mbar_init(&sh.bar_tiles, 16);
+        for (int s = 0; s < 2; ++s) { mbar_init(&sh.bar_sready[s], 1); mbar_init(&sh.bar_full[s], 16); mbar_init(&sh.bar_free[s], 2); }
+        mbar_init(&sh.bar_done, 3);
+        mbar_init(&sh.bar_kvgo, 1);
+        fence_barrier_init();
+    }
+    fence_before();
+    __syncthreads();
+    fence_after();
+    const uint32_t tmem = sh.tmem;
+    const uint32_t qg = smem_u32(QG), kv = smem_u32(KV), stg = smem_u32(STG);
+
+    if (warp == 16) {
+        mma_role_sq(sh, g, tmem, qg, kv, stg, nbh);
+    } else if (warp == 17) {
+        mma_role_kv<1>(sh, g, tmem, qg, stg, nbh);
+    } else if (warp == 18) {
+        mma_role_kv<2>(sh, g, tmem, qg, stg, nbh);
+    } else {
+        // =============================================================== element-wise warps
+        const int lq = warp & 3, cq = warp >> 2;          // lane quarter (query rows), 16-key chunk of a unit
+        const uint32_t tl = tmem + ((uint32_t)(32 * lq) << 16);
+        const int c4 = tid & 3, r0 = tid >> 2;
+        const int rr = 32 * lq + lane;                                         // row inside a query tile
+        const uint32_t rowb = (uint32_t)((rr >> 3) * 1024 + (rr & 7) * 128);
+        const uint32_t x0 = (((uint32_t)(2 * cq) ^ (uint32_t)rr) & 7u) << 4, x1 = x0 ^ 16u;   // 16-byte units of this chunk
+        const uint32_t thr24 = dc.thr16 << 24;
+        const float dsc = TRAIN ? dc.scale : 1.0f;
+        uint32_t cnt_buf[2] = {0u, 0u}, nhead = 0;       // units started on each buffer (all heads); heads started
+        int dbg_i = 0;
+        // one head's rows, converted: FP16 pair pieces of this thread's 2 x 4 features of q, dO, k, v; delta; lse
+        uint2 cv[2][8];
+        float cdl[2], cls[2];
+        HeadScal hs;                                     // of the converted head
+        HeadRegs hr;
+        // stage A: rows from L2 / HBM into registers, the head after it into L2, per-warp maxima into shared memory
+        auto prep_a = [&](int hb) {
+            fetch_head(hr, q, k, v, o, dO, lse, hb, L, tid);
+            const int nb = hb + gridDim.x;
+            if (nb < nbh && tid < L) {               // 64-byte row slices: one prefetch per (tensor, row)
+                const size_t noff = (size_t)(nb / H) * L * D + (nb % H) * DH + (size_t)tid * D;
+                prefetch_l2(q + noff); prefetch_l2(k + noff); prefetch_l2(v + noff); prefetch_l2(dO + noff); prefetch_l2(o + noff);
+            }
+            float mx[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                mx[0] = amax4(hr.q[i], mx[0]); mx[1] = amax4(hr.k[i], mx[1]); mx[2] = amax4(hr.v[i], mx[2]); mx[3] = amax4(hr.g[i], mx[3]);
+            }
+#pragma unroll
+            for (int kx = 0; kx < 4; ++kx) {
+                const float w = warp_max(mx[kx]);
+                if (lane == 0) sh.red[kx][warp] = w;
+            }
+        };
+        // stage B (after a barrier of the 512 element-wise threads): power-of-two scales, FP16 pair pieces, delta
+        auto prep_b = [&]() {
+            float mx[4];
+#pragma unroll
+            for (int kx = 0; kx < 4; ++kx) {
+                float r = sh.red[kx][lane & 15];
+#pragma unroll
+                for (int off = 8; off > 0; off >>= 1) r = fmaxf(r, __shfl_xor_sync(0xffffffffu, r, off));
+                mx[kx] = r;
+            }
+            float sq, iq, sk, ik, sv, iv, sg, ig, sds, ids;
+            pow2_scale(mx[0], sq, iq); pow2_scale(mx[1], sk, ik); pow2_scale(mx[2], sv, iv); pow2_scale(mx[3], sg, ig);
+            pow2_scale(64.0f * mx[3] * mx[2] * dsc, sds, ids);        // |dS| <= |dPd| + |delta| <= 2 * 16 gmax vmax scale
+            hs.f = iq * ik * LOG2E;                  // raw S -> log2 domain
+            hs.fdp = ig * iv * sds;                  // raw dP (times the keep scale) -> dPd * sds
+            hs.sc_q = 0.25f * ids * ik; hs.sc_k = ids * iq; hs.sc_v = ig;
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                float dsum = hr.g[i].x * hr.o[i].x + hr.g[i].y * hr.o[i].y + hr.g[i].z * hr.o[i].z + hr.g[i].w * hr.o[i].w;
+                dsum += __shfl_xor_sync(0xffffffffu, dsum, 1);
+                dsum += __shfl_xor_sync(0xffffffffu, dsum, 2);
+                cdl[i] = dsum * sds;
+                cls[i] = hr.lse[i] * LOG2E;
+                split4(hr.q[i], sq, cv[i][0], cv[i][1]);
+                split4(hr.g[i], sg, cv[i][2], cv[i][3]);
+                split4(hr.k[i], sk, cv[i][4], cv[i][5]);
+                split4(hr.v[i], sv, cv[i][6], cv[i][7]);
+            }
+        };
+        if ((int)blockIdx.x < nbh) {
+            prep_a(blockIdx.x);
+            named_sync(1, 512);
+            prep_b();
+        }
+        for (int bh = blockIdx.x; bh < nbh; bh += gridDim.x, ++nhead) {
+            DBG(1);
+            const int b = bh / H, hd = bh % H;
+            const size_t base = (size_t)b * L * D + hd * DH;
+            const HeadScal cur = hs;
+            // ---- this head's converted rows into the operand tiles (every MMA of the previous head is complete)
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const int R = r0 + 128 * i;
+                if (c4 == 0) { sh.dl[R] = cdl[i]; sh.ls[R] = cls[i]; }
+                // 16-byte unit u of row R sits at ((u ^ R) & 7) << 4: pieces at units {0,1}, {2,3}, {4,5}, {6,7}
+                const uint32_t ob = (uint32_t)((R >> 3) * 1024 + (R & 7) * 128) + (((((uint32_t)c4 >> 1) ^ (uint32_t)R) & 7u) << 4) + (c4 & 1) * 8;
+                *reinterpret_cast<uint2*>(QG + ob) = cv[i][0];
+                *reinterpret_cast<uint2*>(QG + (ob ^ 0x20u)) = cv[i][1];
+                *reinterpret_cast<uint2*>(QG + (ob ^ 0x40u)) = cv[i][2];
+                *reinterpret_cast<uint2*>(QG + (ob ^ 0x60u)) = cv[i][3];
+                *reinterpret_cast<uint2*>(KV + ob) = cv[i][4];
+                *reinterpret_cast<uint2*>(KV + (ob ^ 0x20u)) = cv[i][5];
+                *reinterpret_cast<uint2*>(KV + (ob ^ 0x40u)) = cv[i][6];
+                *reinterpret_cast<uint2*>(KV + (ob ^ 0x60u)) = cv[i][7];
+            }
+            fence_async_smem();
+            named_sync(1, 512);                       // ls / dl visible to every element-wise thread
+            if (lane == 0) mbar_arrive(&sh.bar_tiles);
+            DBG(3);
+            const uint32_t rbase = ((uint32_t)bh + dc.bh_off) * (uint32_t)L;
+
+            // ---- every unit of the head: this warp owns one 16-key chunk of its 32 query rows
+#pragma unroll 1
+            for (int u = 0; u < g.nunits; ++u) {
+                const int bf = u & 1;
+                int kh, qt;
+                unit_at(u, nqt, kh, qt);
+                const int Rw = 128 * qt + 32 * lq, i = Rw + lane;
+                const int rowlim = min(128 * (qt + 1), (L + 15) & ~15);      // query rows the MMAs of this unit read
+                const int j0 = 64 * kh + 16 * cq;                            // first key of the chunk
+                const bool store = Rw < rowlim && j0 < NKP;
+                const bool work = store && j0 <= Rw + 31 && Rw < L;
+                uint32_t pd0[8], pd1[8], ds0[8], ds1[8];
+                DBG(90 + u);
+                mbar_wait(&sh.bar_sready[bf], cnt_buf[bf] & 1);
+                fence_after();
+                DBG(10 + u);
+                if (work) {
+                    const float li = sh.ls[i], Di = sh.dl[i];
+                    const uint32_t g0 = (rbase + (uint32_t)min(i, L - 1)) * (uint32_t)Lp4 + (uint32_t)(j0 >> 2);
+                    const uint32_t ts = tl + 128 * bf + 16 * cq;
+                    if (j0 + 15 > Rw)
+                        bwd_chunk<TRAIN, true>(ts, ts + C_DP, cur.f, li, Di, cur.fdp, dsc, i - j0 + 1, dc.seed, site, g0, thr24, pd0, pd1, ds0, ds1);
+                    else
+                        bwd_chunk<TRAIN, false>(ts, ts + C_DP, cur.f, li, Di, cur.fdp, dsc, 16, dc.seed, site, g0, thr24, pd0, pd1, ds0, ds1);
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) pd0[e] = pd1[e] = ds0[e] = ds1[e] = 0u;
+                }
+                // the MMAs that read this buffer's previous staging tiles (unit u - 2)
+                DBG(20 + u);
+                if (cnt_buf[bf] > 0) mbar_wait(&sh.bar_free[bf], (cnt_buf[bf] - 1) & 1);
+                ++cnt_buf[bf];
+                DBG(30 + u);
+                if (store) {
+                    tmem_st8(tl + 128 * bf + 16 * cq, ds0);            // dS pieces in place: the A operand of dQ += dS K
+                    tmem_st8(tl + 128 * bf + 16 * cq + 8, ds1);
+                    uint8_t* sb = STG + bf * STG_SET + rowb;
+                    *reinterpret_cast<uint4*>(sb + x0) = make_uint4(pd0[0], pd0[1], pd0[2], pd0[3]);
+                    *reinterpret_cast<uint4*>(sb + x1) = make_uint4(pd0[4], pd0[5], pd0[6], pd0[7]);
+                    *reinterpret_cast<uint4*>(sb + STG_TILE + x0) = make_uint4(pd1[0], pd1[1], pd1[2], pd1[3]);
+                    *reinterpret_cast<uint4*>(sb + STG_TILE + x1) = make_uint4(pd1[4], pd1[5], pd1[6], pd1[7]);
+                    *reinterpret_cast<uint4*>(sb + 2 * STG_TILE + x0) = make_uint4(ds0[0], ds0[1], ds0[2], ds0[3]);
+                    *reinterpret_cast<uint4*>(sb + 2 * STG_TILE + x1) = make_uint4(ds0[4], ds0[5], ds0[6], ds0[7]);
+                    *reinterpret_cast<uint4*>(sb + 3 * STG_TILE + x0) = make_uint4(ds1[0], ds1[1], ds1[2], ds1[3]);
+                    *reinterpret_cast<uint4*>(sb + 3 * STG_TILE + x1) = make_uint4(ds1[4], ds1[5], ds1[6], ds1[7]);
+                }
+                DBG(60 + u);
+                fence_async_smem();
+                DBG(70 + u);
+                tmem_st_wait();
+                fence_before();
+                DBG(80 + u);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&sh.bar_full[bf]);
+                DBG(40 + u);
+            }
+            // ---- the next head: fetch (from L2), scales and conversion while this head's last MMAs drain
+            DBG(50);
+            if (bh + (int)gridDim.x < nbh) {
+                prep_a(bh + gridDim.x);
+                named_sync(1, 512);
+                prep_b();
+            }
+            DBG(51);
+            mbar_wait(&sh.bar_done, nhead & 1);
+            fence_after();
+            DBG(52);
+            // ---- accumulators -> HBM.  warp = (lane quarter lq, c): dQ of query tile c, dK / dV of key block c
+            float* xch = reinterpret_cast<float*>(STG);          // [key block][tensor][64 keys][20] (staging tiles are free now)
+            if (cq < nqt && 128 * cq + 32 * lq < L) {
+                const int i = 128 * cq + 32 * lq + lane;
+                float a[16], bq[16];
+                tmem_ld16(tl + C_DQ + 32 * cq, a);
+                tmem_ld16(tl + C_DQ + 32 * cq + 16, bq);
+                if (i < L) {
+                    float4* dst = reinterpret_cast<float4*>(dq + base + (size_t)i * D);
+#pragma unroll
+                    for (int x = 0; x < 4; ++x)
+                        dst[x] = make_float4((a[4 * x] + bq[4 * x]) * cur.sc_q, (a[4 * x + 1] + bq[4 * x + 1]) * cur.sc_q,
+                                             (a[4 * x + 2] + bq[4 * x + 2]) * cur.sc_q, (a[4 * x + 3] + bq[4 * x + 3]) * cur.sc_q);
+                }
+            }
+            // lanes [64,128) hold the products of the second A piece: through shared memory to the lanes of the first
+            if (cq < nkh && lq >= 2) {
+                float a[16], a2[16];
+                float4* d0 = reinterpret_cast<float4*>(xch + ((size_t)(cq * 2 + 0) * 64 + 32 * (lq - 2) + lane) * 20);
+                float4* d1 = reinterpret_cast<float4*>(xch + ((size_t)(cq * 2 + 1) * 64 + 32 * (lq - 2) + lane) * 20);
+                tmem_ld16(tl + C_DK + 16 * cq, a);
+#pragma unroll
+                for (int x = 0; x < 4; ++x) d0[x] = make_float4(a[4 * x], a[4 * x + 1], a[4 * x + 2], a[4 * x + 3]);
+                tmem_ld16(tl + C_DV + 32 * cq, a);
+                tmem_ld16(tl + C_DV + 32 * cq + 16, a2);
+#pragma unroll
+                for (int x = 0; x < 4; ++x)
+                    d1[x] = make_float4(a[4 * x] + a2[4 * x], a[4 * x + 1] + a2[4 * x + 1], a[4 * x + 2] + a2[4 * x + 2], a[4 * x + 3] + a2[4 * x + 3]);
+            }
+            fence_before();
+            named_sync(1, 512);
+            if (cq < nkh && lq < 2 && 64 * cq + 32 * lq < L) {
+                const int j = 64 * cq + 32 * lq + lane;
+                const float4* s0 = reinterpret_cast<const float4*>(xch + ((size_t)(cq * 2 + 0) * 64 + 32 * lq + lane) * 20);
+                const float4* s1 = reinterpret_cast<const float4*>(xch + ((size_t)(cq * 2 + 1) * 64 + 32 * lq + lane) * 20);
+                float4* dK = reinterpret_cast<float4*>(dk + base + (size_t)j * D);
+                float4* dV = reinterpret_cast<float4*>(dv + base + (size_t)j * D);
+                float a[16], a2[16];
+                tmem_ld16(tl + C_DK + 16 * cq, a);
+                if (j < L) {
+#pragma unroll
+                    for (int x = 0; x < 4; ++x) {
+                        const float4 w0 = s0[x];
+                        dK[x] = make_float4((a[4 * x] + w0.x) * cur.sc_k, (a[4 * x + 1] + w0.y) * cur.sc_k, (a[4 * x + 2] + w0.z) * cur.sc_k,
+                                            (a[4 * x + 3] + w0.w) * cur.sc_k);
+                    }
+                }
+                tmem_ld16(tl + C_DV + 32 * cq, a);
+                tmem_ld16(tl + C_DV + 32 * cq + 16, a2);
+                if (j < L) {
+#pragma unroll
+                    for (int x = 0; x < 4; ++x) {
+                        const float4 w1 = s1[x];
+                        dV[x] = make_float4((a[4 * x] + a2[4 * x] + w1.x) * cur.sc_v, (a[4 * x + 1] + a2[4 * x + 1] + w1.y) * cur.sc_v,
+                                            (a[4 * x + 2] + a2[4 * x + 2] + w1.z) * cur.sc_v, (a[4 * x + 3] + a2[4 * x + 3] + w1.w) * cur.sc_v);
+                    }
+                }
+            }
+            fence_before();
+            DBG(53);
+        }
+    }
+    fence_before();
+    __syncthreads();
+    if (warp == 16) tmem_dealloc(tmem, 512);
+}
+
+}  // namespace attn_p
+}  // namespace amid

@@ -14,6 +14,8 @@
 #include "encoder_tc16.cuh"
 #include "x3.cuh"
 #include "attn_tc.cuh"
+#include "attn_p.cuh"
+#include <algorithm>
 
 namespace amid {
 
@@ -726,6 +728,15 @@ k_reduce_ln(const float* __restrict__ part, int S, float* __restrict__ dw, float
 // ----------------------------------------------------------------------------------
 // host side
 // ----------------------------------------------------------------------------------
+static int sm_count() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    }
+    return n;
+}
 static int ensure_smem(const void* fn, size_t bytes) {
     cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
     if (e != cudaSuccess) return set_error(-3, "cudaFuncSetAttribute(%zu): %s", bytes, cudaGetErrorString(e));

@@ -118,6 +118,11 @@ extern "C" int amid_attn_fwd_test(const float* q, const float* k, const float* v
     return 0;
 }
 
+#ifdef AMID_ATTN_DBG
+extern "C" int amid_attn_dbg_read(long long* out) {
+    return (int)cudaMemcpyFromSymbol(out, attn_p::g_dbg, sizeof(long long) * 20 * 256);
+}
+#endif
 extern "C" int amid_attn_bwd_test(const float* q, const float* k, const float* v, const float* o, const float* lse,
                                   const float* dO, float* dq, float* dk, float* dv, int32_t B, int32_t L,
                                   const amid_dropout* drop, uint32_t site, int32_t impl, amid_stream_t s_) {
@@ -143,6 +148,13 @@ extern "C" int amid_attn_bwd_test(const float* q, const float* k, const float* v
             attn::k_attn_bwd_mma<true><<<B * H, attn::NWB * 32, smem, stream>>>(q, k, v, o, lse, dO, dq, dk, dv, L, dc, site);
             AMID_LAUNCH_CHECK("k_attn_bwd_mma3");
         }
+    } else if (impl == 4) {
+        AMID_REQUIRE(L >= attn_p::PMINL && L <= attn_p::PMAXL, "attn_bwd_test: pipelined tcgen05 path needs %d <= L <= %d", attn_p::PMINL, attn_p::PMAXL);
+        auto kfn = dc.train ? attn_p::k_attn_bwd_p<true> : attn_p::k_attn_bwd_p<false>;
+        if (int rc = ensure_smem((const void*)kfn, attn_p::PBWD_SMEM)) return rc;
+        AMID_K("k_attn_bwd_p", stream);
+        kfn<<<std::min(B * H, sm_count()), attn_p::NTH, attn_p::PBWD_SMEM, stream>>>(q, k, v, o, lse, dO, dq, dk, dv, L, B * H, dc, site);
+        AMID_LAUNCH_CHECK("k_attn_bwd_p");
     } else {
         AMID_REQUIRE(L <= attn_tc::MAXL, "attn_bwd_test: tcgen05 path needs L <= %d", attn_tc::MAXL);
         if (int rc = ensure_smem((const void*)attn_tc::k_attn_bwd_tc, attn_tc::BWD_SMEM)) return rc;
