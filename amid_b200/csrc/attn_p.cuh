@@ -547,5 +547,225 @@ k_attn_bwd_p(const float* __restrict__ q, const float* __restrict__ k, const flo
     if (warp == 16) tmem_dealloc(tmem, 512);
 }
 
+
+// ================================================================================================
+// forward: one CTA per (sample, head), 256 threads, two CTAs per SM (tensor memory: 224 score columns + 32 for O).
+// Against attn_tc::k_attn_fwd_tc: v enters P V as an MN-major B operand straight from the row tile [k0 | k1 | v0 | v1]
+// (no transposed copies, no 2-byte scatter stores in the prologue), [v0 | v1] is ONE N = 32 operand (two MMAs per
+// k-step, O = columns [0,16) + [16,32)), warp 0 issues the MMAs through elect.sync (back-to-back UTCHMMA), the
+// exp / dropout / split loop is specialised on training mode and on diagonal chunks.
+// ================================================================================================
+constexpr size_t PFWD_SMEM = 2 * (size_t)ROWT_BYTES + 1024;
+constexpr uint32_t CF_O = 224;
+
+struct ShPF {
+    uint64_t bar;
+    uint32_t tmem;
+    float red[3][8];
+    float xm[2][128];
+    float xl[2][128];
+};
+
+// P = 2^(S f - m) of 32 consecutive keys, row sum, dropout, FP16 pairs in place
+template <bool TRAIN, bool DIAG>
+__device__ __forceinline__ float fwd_chunk(uint32_t taddr, float f, float m, int lane, uint32_t seed, uint32_t site, uint32_t g0,
+                                           uint32_t thr24) {
+    float a[32];
+    uint32_t p0[16], p1[16];
+    tmem_ld32(taddr, a);
+    float l = 0.f;
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+        uint32_t r = 0u;
+        if (TRAIN) r = rng4(seed, site, (uint64_t)(g0 + g));
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int cc = 4 * g + e;
+            float p = ex2(fmaf(a[cc], f, -m));
+            if (DIAG) p = cc <= lane ? p : 0.f;
+            l += p;
+            if (TRAIN) p = (e == 3 ? r : (r << (24 - 8 * e))) >= thr24 ? p : 0.f;
+            a[cc] = p;
+        }
+    }
+#pragma unroll
+    for (int e = 0; e < 16; ++e) split_f16x2(a[2 * e], a[2 * e + 1], p0[e], p1[e]);
+    tmem_st16(taddr, p0);
+    tmem_st16(taddr + 16, p1);
+    return l;
+}
+
+template <bool TRAIN>
+__global__ void __launch_bounds__(256, 2)
+k_attn_fwd_p(const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v, float* __restrict__ o,
+             float* __restrict__ lse, int L, DropCfg dc, uint32_t site) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ ShPF sh;
+    uint8_t* Qp = align1k(smem_raw);                // [position][q0 | q1 | - | -]
+    uint8_t* KV = Qp + ROWT_BYTES;                  // [position][k0 | k1 | v0 | v1]
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int bh = blockIdx.x, b = bh / H, hd = bh % H;
+    const size_t base = (size_t)b * L * D + hd * DH;
+    const int ntile = (L + 127) >> 7, NKP = (L + 15) & ~15, Lp4 = ((L + 3) & ~3) >> 2;
+    if (warp == 0) tmem_alloc(&sh.tmem, 256);
+    if (tid == 0) { mbar_init(&sh.bar, 1); fence_barrier_init(); }
+    // ---- head slices -> registers, per-slice maxima, FP16 pair row tiles
+    const int c4 = tid & 3, r0 = tid >> 2;
+    float4 vq[4], vk[4], vv[4];
+    float mx[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int R = r0 + 64 * i;
+        vq[i] = vk[i] = vv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (R < L) {
+            const size_t off = base + (size_t)R * D + 4 * c4;
+            vq[i] = __ldg(reinterpret_cast<const float4*>(q + off));
+            vk[i] = __ldg(reinterpret_cast<const float4*>(k + off));
+            vv[i] = __ldg(reinterpret_cast<const float4*>(v + off));
+        }
+        mx[0] = amax4(vq[i], mx[0]); mx[1] = amax4(vk[i], mx[1]); mx[2] = amax4(vv[i], mx[2]);
+    }
+#pragma unroll
+    for (int kx = 0; kx < 3; ++kx) {
+        const float w = warp_max(mx[kx]);
+        if (lane == 0) sh.red[kx][warp] = w;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kx = 0; kx < 3; ++kx) {
+        float r = sh.red[kx][lane & 7];
+#pragma unroll
+        for (int off = 4; off > 0; off >>= 1) r = fmaxf(r, __shfl_xor_sync(0xffffffffu, r, off));
+        mx[kx] = r;
+    }
+    float sq, iq, sk, ik, sv, iv;
+    pow2_scale(mx[0], sq, iq); pow2_scale(mx[1], sk, ik); pow2_scale(mx[2], sv, iv);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int R = r0 + 64 * i;
+        const uint32_t ob = (uint32_t)((R >> 3) * 1024 + (R & 7) * 128) + (((((uint32_t)c4 >> 1) ^ (uint32_t)R) & 7u) << 4) + (c4 & 1) * 8;
+        uint2 p0, p1;
+        split4(vq[i], sq, p0, p1);
+        *reinterpret_cast<uint2*>(Qp + ob) = p0;
+        *reinterpret_cast<uint2*>(Qp + (ob ^ 0x20u)) = p1;
+        split4(vk[i], sk, p0, p1);
+        *reinterpret_cast<uint2*>(KV + ob) = p0;
+        *reinterpret_cast<uint2*>(KV + (ob ^ 0x20u)) = p1;
+        split4(vv[i], sv, p0, p1);
+        *reinterpret_cast<uint2*>(KV + (ob ^ 0x40u)) = p0;
+        *reinterpret_cast<uint2*>(KV + (ob ^ 0x60u)) = p1;
+    }
+    fence_async_smem();
+    fence_before();
+    __syncthreads();
+    fence_after();
+    const uint32_t tmem = sh.tmem;
+    const uint32_t tl = tmem + ((uint32_t)(32 * (warp & 3)) << 16);
+    const int half = warp >> 2, row = 32 * (warp & 3) + lane;
+    const float f = iq * ik * LOG2E;               // raw accumulator -> scores in the log2 domain
+    const float osc = (TRAIN ? dc.scale : 1.0f) * iv;
+    const uint32_t thr24 = dc.thr16 << 24;
+    const uint32_t ql = dlo_k(smem_u32(Qp)), kl = dlo_k(smem_u32(KV));
+    constexpr uint32_t idv = idesc_f16(32, false, true);
+    uint32_t phase = 0;
+#pragma unroll 1
+    for (int t = 0; t < ntile; ++t) {
+        const int Nk = min(NKP, 128 * (t + 1));
+        if (warp == 0) {
+            if (elect_one()) {
+                const uint32_t id = idesc_f16(Nk, false, false);
+                const uint32_t qa = ql + (uint32_t)(128 * t) * 8;
+                mma_lo(tmem, qa, kl, id, 0u);            // q0 k0
+                mma_lo(tmem, qa + 2, kl, id, 1u);        // q1 k0
+                mma_lo(tmem, qa, kl + 2, id, 1u);        // q0 k1
+                mma_commit(&sh.bar);
+            }
+            __syncwarp();
+        }
+        mbar_wait(&sh.bar, phase);
+        phase ^= 1;
+        fence_after();
+        const int Rw = 128 * t + 32 * (warp & 3);           // first query row of this warp
+        const int i = Rw + lane;
+        const bool wvalid = Rw < L;
+        const int nch = (Nk + 31) >> 5, cdiag = Rw >> 5;
+        // ---- row maximum (raw accumulator units)
+        float mraw = -INFINITY;
+        if (wvalid) {
+#pragma unroll 1
+            for (int c = half; c <= cdiag; c += 2) {
+                float a[32];
+                tmem_ld32(tl + 32 * c, a);
+                if (c == cdiag) {
+#pragma unroll
+                    for (int e = 0; e < 32; ++e)
+                        if (e > lane) a[e] = -INFINITY;
+                }
+#pragma unroll
+                for (int e = 0; e < 32; ++e) mraw = fmaxf(mraw, a[e]);
+            }
+        }
+        sh.xm[half][row] = mraw;
+        __syncthreads();
+        const float m = fmaxf(sh.xm[0][row], sh.xm[1][row]) * f;
+        // ---- P = 2^(S f - m), row sum, dropout, FP16 pairs in place
+        float l = 0.f;
+        if (wvalid) {
+            const uint32_t rb4 = (((uint32_t)bh + dc.bh_off) * (uint32_t)L + (uint32_t)min(i, L - 1)) * (uint32_t)Lp4;
+#pragma unroll 1
+            for (int c = half; c < nch; c += 2) {
+                if (c < cdiag) {
+                    l += fwd_chunk<TRAIN, false>(tl + 32 * c, f, m, lane, dc.seed, site, rb4 + 8 * c, thr24);
+                } else if (c == cdiag) {
+                    l += fwd_chunk<TRAIN, true>(tl + 32 * c, f, m, lane, dc.seed, site, rb4 + 8 * c, thr24);
+                } else {
+                    uint32_t z[16];
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) z[e] = 0u;
+                    tmem_st16(tl + 32 * c, z);
+                    tmem_st16(tl + 32 * c + 16, z);
+                }
+            }
+        }
+        sh.xl[half][row] = l;
+        tmem_st_wait();
+        fence_before();
+        __syncthreads();
+        if (warp == 0) {
+            fence_after();
+            if (elect_one()) {
+                // O[128 x 32] = P [v0 | v1]: A = P pieces in tensor memory, B = MN-major rows of the key / value tile
+                for (int kk = 0; kk < (Nk >> 4); ++kk) {
+                    const uint32_t a0 = tmem + 32 * (kk >> 1) + 8 * (kk & 1), bl = kl + (uint32_t)kk * 128 + 4;
+                    mma_lo_ts(tmem + CF_O, a0, bl, idv, kk ? 1u : 0u);
+                    mma_lo_ts(tmem + CF_O, a0 + 16, bl, idv, 1u);
+                }
+                mma_commit(&sh.bar);
+            }
+            __syncwarp();
+        }
+        mbar_wait(&sh.bar, phase);
+        phase ^= 1;
+        fence_after();
+        if (half == 0 && wvalid) {               // warp-uniform: tcgen05.ld is a warp-collective instruction
+            float a[32];
+            tmem_ld32(tl + CF_O, a);
+            if (i < L) {
+                const float lt = sh.xl[0][row] + sh.xl[1][row];
+                const float sc = osc / lt;
+                float4* dst = reinterpret_cast<float4*>(o + base + (size_t)i * D);
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    dst[u] = make_float4((a[4 * u] + a[16 + 4 * u]) * sc, (a[4 * u + 1] + a[17 + 4 * u]) * sc,
+                                         (a[4 * u + 2] + a[18 + 4 * u]) * sc, (a[4 * u + 3] + a[19 + 4 * u]) * sc);
+                lse[(size_t)bh * L + i] = m * LN2 + logf(lt);
+            }
+        }
+        fence_before();
+        __syncthreads();
+    }
+    if (warp == 0) tmem_dealloc(tmem, 256);
+}
+
 }  // namespace attn_p
 }  // namespace amid

@@ -1122,7 +1122,15 @@ static int encoder_bwd_impl(const amid_encoder_tensors* P, const float* x0, cons
         if (mode == 3) {
             const size_t mma_smem = (size_t)((L + 15) / 16 * 16) * (4 * attn::LDS + 2) * sizeof(float);
             if (int rc = ensure_smem((const void*)attn::k_attn_bwd_mma<true>, mma_smem)) return rc;
-            if (L >= attn_tc::MINL && L <= attn_tc::MAXL) {
+            if (L >= attn_p::PMINL && L <= attn_p::PMAXL) {       // single-pass pipelined kernel, persistent CTAs
+                auto kfn = dc.train ? attn_p::k_attn_bwd_p<true> : attn_p::k_attn_bwd_p<false>;
+                if (int rc = ensure_smem((const void*)kfn, attn_p::PBWD_SMEM)) return rc;
+                AMID_K("k_attn_bwd_p", stream);
+                kfn<<<std::min(B * H, sm_count()), attn_p::NTH, attn_p::PBWD_SMEM, stream>>>(S->q[i], S->k[i], S->v[i], S->o[i], S->lse[i], dO,
+                                                                                             dq, dk, dv, L, B * H, dc,
+                                                                                             dc.site_base + site_attn(i));
+                AMID_LAUNCH_CHECK("k_attn_bwd_p");
+            } else if (L >= attn_tc::MINL && L <= attn_tc::MAXL) {
                 if (int rc = ensure_smem((const void*)attn_tc::k_attn_bwd_tc, attn_tc::BWD_SMEM)) return rc;
                 AMID_K("k_attn_bwd_tc", stream);
                 attn_tc::k_attn_bwd_tc<<<B * H, 256, attn_tc::BWD_SMEM, stream>>>(S->q[i], S->k[i], S->v[i], S->o[i], S->lse[i], dO, dq,

@@ -108,6 +108,13 @@ extern "C" int amid_attn_fwd_test(const float* q, const float* k, const float* v
             attn::k_attn_fwd_mma<true><<<B * H, attn::NW * 32, smem, stream>>>(q, k, v, o, lse, L, dc, site);
             AMID_LAUNCH_CHECK("k_attn_fwd_mma3");
         }
+    } else if (impl == 4) {
+        AMID_REQUIRE(L >= attn_p::PMINL && L <= attn_tc::MAXL, "attn_fwd_test: pipelined tcgen05 path needs %d <= L <= %d", attn_p::PMINL, attn_tc::MAXL);
+        auto kfn = dc.train ? attn_p::k_attn_fwd_p<true> : attn_p::k_attn_fwd_p<false>;
+        if (int rc = ensure_smem((const void*)kfn, attn_p::PFWD_SMEM)) return rc;
+        AMID_K("k_attn_fwd_p", stream);
+        kfn<<<B * H, 256, attn_p::PFWD_SMEM, stream>>>(q, k, v, o, lse, L, dc, site);
+        AMID_LAUNCH_CHECK("k_attn_fwd_p");
     } else {
         AMID_REQUIRE(L <= attn_tc::MAXL, "attn_fwd_test: tcgen05 path needs L <= %d", attn_tc::MAXL);
         if (int rc = ensure_smem((const void*)attn_tc::k_attn_fwd_tc, attn_tc::FWD_SMEM)) return rc;
