@@ -811,12 +811,12 @@ static int encoder_fwd_impl(const amid_encoder_tensors* P, const float* x0, cons
                                                                     W + 2 * x3::WIMG_BYTES, wi, P->in_b[i], S->qn[i], S->st1[i],
                                                                     S->q[i], S->k[i], S->v[i]);
             AMID_LAUNCH_CHECK("k_ln_qkv_x3");
-            if (L >= attn_tc::MINL && L <= attn_tc::MAXL) {      // scores in tensor memory
-                if (int rc = ensure_smem((const void*)attn_tc::k_attn_fwd_tc, attn_tc::FWD_SMEM)) return rc;
-                AMID_K("k_attn_fwd_tc", stream);
-                attn_tc::k_attn_fwd_tc<<<B * H, 256, attn_tc::FWD_SMEM, stream>>>(S->q[i], S->k[i], S->v[i], S->o[i], S->lse[i], L, dc,
-                                                                                  dc.site_base + site_attn(i));
-                AMID_LAUNCH_CHECK("k_attn_fwd_tc");
+            if (L >= attn_p::PMINL && L <= attn_tc::MAXL) {      // scores in tensor memory
+                auto kfn = dc.train ? attn_p::k_attn_fwd_p<true> : attn_p::k_attn_fwd_p<false>;
+                if (int rc = ensure_smem((const void*)kfn, attn_p::PFWD_SMEM)) return rc;
+                AMID_K("k_attn_fwd_p", stream);
+                kfn<<<B * H, 256, attn_p::PFWD_SMEM, stream>>>(S->q[i], S->k[i], S->v[i], S->o[i], S->lse[i], L, dc, dc.site_base + site_attn(i));
+                AMID_LAUNCH_CHECK("k_attn_fwd_p");
             } else {
                 AMID_K("k_attn_fwd_mma3", stream);
                 attn::k_attn_fwd_mma<true><<<B * H, attn::NW * 32, mma_smem, stream>>>(S->q[i], S->k[i], S->v[i], S->o[i], S->lse[i],

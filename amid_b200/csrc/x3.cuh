@@ -63,6 +63,12 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
+// one lane of a converged warp (the pattern ptxas recognises: MMAs behind it issue without a per-instruction election loop)
+__device__ __forceinline__ bool elect_one_sync() {
+    uint32_t pred = 0;
+    asm volatile("{\n.reg .pred P1;\nelect.sync _|P1, 0xffffffff;\nselp.u32 %0, 1, 0, P1;\n}" : "=r"(pred));
+    return pred != 0;
+}
 // ---- bulk asynchronous copy global -> shared (TMA engine, 1-D), completion counted in bytes on an mbarrier
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
@@ -166,11 +172,14 @@ __device__ __forceinline__ void run_gemm_x3(SharedX& sh, uint32_t acc_off, const
     tmem_st_wait();
     fence_before();
     __syncthreads();
-    if (threadIdx.x == 0) {
+    if ((threadIdx.x >> 5) == 0) {          // warp-uniform issue path: elect.sync lets ptxas emit back-to-back UTCHMMA
         mbar_wait(&sh.bar_w, ph_w);
         fence_after();
-        issue_gemm_x3(sh.tmem, acc_off, smem_u32(Wbuf), accumulate);
-        mma_commit(&sh.bar_mma);
+        if (elect_one_sync()) {
+            issue_gemm_x3(sh.tmem, acc_off, smem_u32(Wbuf), accumulate);
+            mma_commit(&sh.bar_mma);
+        }
+        __syncwarp();
     }
     ph_w ^= 1;
     mbar_wait(&sh.bar_mma, ph_mma);
@@ -859,7 +868,7 @@ k_wgrad_x3(WgradJobsX jobs, int M, float* __restrict__ wpart /*[6][S][128*128]*/
         if (it + 1 < n_it) { load_sub(vy, dY, sub_of(it + 1) * SUB_ROWS, M); load_sub(vx, X, sub_of(it + 1) * SUB_ROWS, M); }
         fence_async_smem();
         __syncthreads();
-        if (threadIdx.x == 0) {
+        if ((threadIdx.x >> 5) == 0 && elect_one_sync()) {
             fence_after();
             const uint32_t a = smem_u32(buf), x = a + 3 * SUBP_BYTES, o = smem_u32(Ones);
 #pragma unroll
