@@ -13,11 +13,11 @@ dq, dk, dv = (torch.empty(B * L, D, device="cuda") for _ in range(3))
 drop = Dropout(1, 0.5, 12345, 0)
 for _ in range(2):
     call("amid_attn_bwd_test", hp._ptr(q), hp._ptr(k), hp._ptr(v), hp._ptr(o), hp._ptr(lse), hp._ptr(dO), hp._ptr(dq), hp._ptr(dk),
-         hp._ptr(dv), B, L, C.byref(drop), 1, 4, hp._stream())
+         hp._ptr(dv), B, L, C.byref(drop), 1, int(sys.argv[1]) if len(sys.argv) > 1 else 4, hp._stream())
 torch.cuda.synchronize()
 buf = (C.c_longlong * (20 * 256))()
 lib().amid_attn_dbg_read(buf)
-for w in (10, 16):
+for w in (10,):
     row = buf[w * 256:(w + 1) * 256]
     t0 = row[1]
     print("warp", w, " ".join(f"{row[i]}:{row[i + 1] - t0}" for i in range(0, 250, 2) if row[i]))
