@@ -424,6 +424,8 @@ k_attn_bwd_p(const float* __restrict__ q, const float* __restrict__ k, const flo
                 const int j0 = 64 * kh + 16 * cq;                            // first key of the chunk
                 const bool store = Rw < rowlim && j0 < NKP;
                 const bool work = store && j0 <= Rw + 31 && Rw < L;
+                // the dK / dV MMAs skip the query k-steps that lie entirely before the key block: those staging rows are never read
+                const bool sstore = store && 32 * lq + 32 > max(0, 64 * kh - 128 * qt);
                 uint32_t pd0[8], pd1[8], ds0[8], ds1[8];
                 DBG(90 + u);
                 mbar_wait(&sh.bar_sready[bf], cnt_buf[bf] & 1);
@@ -449,6 +451,8 @@ k_attn_bwd_p(const float* __restrict__ q, const float* __restrict__ k, const flo
                 if (store) {
                     tmem_st8(tl + 128 * bf + 16 * cq, ds0);            // dS pieces in place: the A operand of dQ += dS K
                     tmem_st8(tl + 128 * bf + 16 * cq + 8, ds1);
+                }
+                if (sstore) {
                     uint8_t* sb = STG + bf * STG_SET + rowb;
                     *reinterpret_cast<uint4*>(sb + x0) = make_uint4(pd0[0], pd0[1], pd0[2], pd0[3]);
                     *reinterpret_cast<uint4*>(sb + x1) = make_uint4(pd0[4], pd0[5], pd0[6], pd0[7]);

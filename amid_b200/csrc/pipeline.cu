@@ -32,9 +32,36 @@ __device__ __forceinline__ uint32_t mix32(uint32_t x) {
     x ^= x >> 16; x *= 0x7FEB352Du; x ^= x >> 15; x *= 0x846CA68Bu; x ^= x >> 16;
     return x;
 }
-__device__ __forceinline__ int64_t gcd64(int64_t a, int64_t b) {
-    while (b) { const int64_t t = a % b; a = b; b = t; }
-    return a;
+// Keyed bijection of [0, P): a 4-round Feistel network on 2 x h bits (2^(2h) >= P, < 4P) with cycle walking (a value that falls
+// outside [0, P) is permuted again; the orbit of a point of [0, P) returns to [0, P), so the restriction is a bijection).
+// perm(0), perm(1), ... is therefore a duplicate-free pseudo-random order of the pool, and its first K admissible elements are a
+// pseudo-random K-subset -- the role random.sample plays in the reference sampler (dataset_seq.py:176-199).
+struct Feistel {
+    uint32_t key[4];
+    int h;
+    uint32_t mask;
+};
+__device__ __forceinline__ Feistel make_feistel(int64_t P, uint32_t k0, uint32_t k1) {
+    Feistel f;
+    int bits = 1;
+    while (((int64_t)1 << bits) < P) ++bits;
+    f.h = (bits + 1) >> 1;
+    f.mask = (1u << f.h) - 1u;
+    f.key[0] = k0; f.key[1] = k1; f.key[2] = mix32(k0 ^ 0x9E3779B1u); f.key[3] = mix32(k1 ^ 0x85EBCA77u);
+    return f;
+}
+__device__ __forceinline__ int64_t feistel_perm(const Feistel& f, int64_t x, int64_t P) {
+    do {
+        uint32_t l = (uint32_t)(x >> f.h), r = (uint32_t)x & f.mask;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const uint32_t t = l ^ (mix32(r ^ f.key[i]) & f.mask);
+            l = r;
+            r = t;
+        }
+        x = ((int64_t)l << f.h) | r;
+    } while (x >= P);
+    return x;
 }
 
 __global__ void __launch_bounds__(128)
@@ -67,20 +94,14 @@ k_build_batch(BatchSrc s, BatchDst d, const int64_t* __restrict__ rows, int64_t 
     const int64_t eo = s.ex_offs[row], ne = s.ex_offs[row + 1] - eo;
     const uint32_t h1 = mix32((uint32_t)seed ^ mix32((uint32_t)row * 0x9E3779B1u + 0x85EBCA77u));
     const uint32_t h2 = mix32((uint32_t)(seed >> 32) ^ mix32((uint32_t)(row >> 32) + h1 + 0xC2B2AE3Du));
-    const int64_t start = (int64_t)(((uint64_t)h1 << 16 ^ h2) % (uint64_t)P);
-    int64_t stride = 1;
-    if (P > 2) {
-        stride = 1 + (int64_t)(((uint64_t)h2 << 16 ^ h1) % (uint64_t)(P - 1));
-        while (gcd64(stride, P) != 1) stride = stride % (P - 1) + 1;       // terminates: 1 is coprime to everything
-    }
+    const Feistel fe = make_feistel(P, h1, h2);
     int cnt = 0;
     for (int64_t j0 = 0; j0 < P && cnt < K; j0 += 32) {
         const int64_t j = j0 + lane;
         bool ok = j < P;
         int64_t cand = 0;
         if (ok) {
-            const int64_t pos = (int64_t)(((unsigned __int128)(uint64_t)j * (uint64_t)stride + (uint64_t)start) % (uint64_t)P);
-            cand = pool[pos];
+            cand = pool[feistel_perm(fe, j, P)];
             for (int64_t e = 0; e < ne; ++e)
                 if (s.ex_vals[eo + e] == cand) { ok = false; break; }
         }

@@ -830,7 +830,7 @@ struct WgradJobsX {
 __global__ void __launch_bounds__(WGX_THREADS, 1)
 k_wgrad_x3(WgradJobsX jobs, int M, float* __restrict__ wpart /*[6][S][128*128]*/, float* __restrict__ bpart /*[6][S][128]*/) {
     extern __shared__ uint8_t smem_raw[];
-    __shared__ uint64_t bars[2];
+    __shared__ uint64_t bars[2];           // tcgen05.commit: the MMAs that read buffer b are complete
     __shared__ uint32_t tmem_s;
     uint8_t* buf0 = align1k(smem_raw);
     uint8_t* Ones = buf0 + 2 * WG_BUF_BYTES;
@@ -867,7 +867,7 @@ k_wgrad_x3(WgradJobsX jobs, int M, float* __restrict__ wpart /*[6][S][128*128]*/
         fill_sub3(buf + 3 * SUBP_BYTES, vx);
         if (it + 1 < n_it) { load_sub(vy, dY, sub_of(it + 1) * SUB_ROWS, M); load_sub(vx, X, sub_of(it + 1) * SUB_ROWS, M); }
         fence_async_smem();
-        __syncthreads();
+        __syncthreads();          // (an mbarrier hand-off that lets the other 15 warps run ahead was measured 40 % slower)
         if ((threadIdx.x >> 5) == 0 && elect_one_sync()) {
             fence_after();
             const uint32_t a = smem_u32(buf), x = a + 3 * SUBP_BYTES, o = smem_u32(Ones);

@@ -12,11 +12,10 @@ Two modes:
     used as given; every field is then bit-identical to the reference's collated batch (tests/test_gpu_pipeline.py).
     Evaluation PARITY with the reference protocol requires this mode.
   * ``batch(rows, k=..., seed=...)``: negatives are drawn on the device: k distinct items of the target domain's
-    pool outside the user's full own-domain sequence, reproducible in (seed, row).  The draw is an affine walk
-    (random start, random coprime stride) over the id-sorted pool, NOT random.sample's uniform k-subset: a user's
-    negatives form an arithmetic progression in pool order, so sampled HR/NDCG can differ systematically from the
-    reference protocol when item ids correlate with popularity.  Use it for training throughput; use replay mode
-    when the metric has to match the reference.
+    pool outside the user's full own-domain sequence, reproducible in (seed, row).  The draw is the first k admissible items of a
+    keyed pseudo-random PERMUTATION of the pool (4-round Feistel network with cycle walking, keyed by (seed, row)): a
+    duplicate-free pseudo-random k-subset, the role random.sample plays in the reference sampler.  The stream differs from
+    Python's, so bit-for-bit evaluation parity with the reference protocol still requires replay mode.
 """
 from __future__ import annotations
 

@@ -68,6 +68,17 @@ def test_device_sampler_respects_the_reference_constraints():
     assert set(counts) <= admissible and len(counts) >= 0.9 * len(admissible)
     exp = reps / len(admissible)
     assert max(counts.values()) < 3.0 * exp
+    # the k draws of a row are a pseudo-random subset, not an arithmetic progression in pool order (the signature of an
+    # affine walk over the sorted pool): equal consecutive gaps must be the exception
+    dom = int(z["in_domain"][2])
+    order = {v: i for i, v in enumerate(sorted(pools[dom]))}
+    P = len(order)
+    ap = 0
+    for s in range(200):
+        x = ds.batch(torch.tensor([2]), k=3, seed=5000 + s)["neg_samples"][0].tolist()
+        p0, p1, p2 = (order[v] for v in x)
+        ap += ((p1 - p0) % P) == ((p2 - p1) % P)
+    assert ap < 60, ap
 
 
 def test_sampler_reports_an_exhausted_pool_and_bad_rows():
