@@ -95,7 +95,8 @@ struct ShPB {
     uint64_t bar_full[2];     // 16 arrivals: every warp stored its part of the staging tiles and is done reading S / dP
     uint64_t bar_free[2];     // 2 x tcgen05.commit (dK and dV issuers): the MMAs that read the staging tiles of set s are complete
     uint64_t bar_done;        // 3 x tcgen05.commit: every MMA of the head is complete
-    uint64_t bar_kvgo;        // 1 arrival per unit: the S / dP issuer has queued its MMAs (dK / dV go behind them)
+    uint64_t bar_kvgo[2];     // 1 arrival per unit (indexed by unit parity): the S / dP issuer has queued its MMAs, dK / dV go behind
+                              // them.  Two barriers: with one, a dK / dV issuer that wakes up late could find it two phases ahead
     uint32_t tmem;
     float red[4][16];
     float ls[256];            // lse * log2(e) per query (+inf for rows >= L)
@@ -202,7 +203,7 @@ __device__ __forceinline__ void mma_role_sq(ShPB& sh, const Geo g, uint32_t tmem
                     mma_commit(&sh.bar_sready[s]);
                 }
                 if (u == g.nunits - 1) mma_commit(&sh.bar_done);
-                mbar_arrive(&sh.bar_kvgo);
+                mbar_arrive(&sh.bar_kvgo[s]);
             }
             __syncwarp();
             DBG(120 + u);
@@ -215,7 +216,7 @@ template <int ROLE>
 __device__ __forceinline__ void mma_role_kv(ShPB& sh, const Geo g, uint32_t tmem, uint32_t qg, uint32_t stg, int nbh) {
     constexpr uint32_t idk = idesc_f16(16, true, true), idv = idesc_f16(32, true, true);
     const uint32_t qgl = dlo_k(qg) + (ROLE == 2 ? 4u : 0u);
-    uint32_t cnt_full[2] = {0u, 0u}, cnt_go = 0;
+    uint32_t cnt_full[2] = {0u, 0u};
     for (int bh = blockIdx.x; bh < nbh; bh += gridDim.x) {
         for (int u = 0; u < g.nunits; ++u) {
             const int s = u & 1;
@@ -228,9 +229,8 @@ __device__ __forceinline__ void mma_role_kv(ShPB& sh, const Geo g, uint32_t tmem
             const uint32_t bl = qgl + (uint32_t)(128 * qt) * 8;
             const bool first = qt == (kh >> 1);
             mbar_wait(&sh.bar_full[s], cnt_full[s] & 1);
+            mbar_wait(&sh.bar_kvgo[s], cnt_full[s] & 1);
             ++cnt_full[s];
-            mbar_wait(&sh.bar_kvgo, cnt_go & 1);
-            ++cnt_go;
             fence_after();
             if (elect_one()) {
 #pragma unroll
@@ -301,7 +301,8 @@ k_attn_bwd_p(const float* __restrict__ q, const float* __restrict__ k, const flo
         mbar_init(&sh.bar_tiles, 16);
         for (int s = 0; s < 2; ++s) { mbar_init(&sh.bar_sready[s], 1); mbar_init(&sh.bar_full[s], 16); mbar_init(&sh.bar_free[s], 2); }
         mbar_init(&sh.bar_done, 3);
-        mbar_init(&sh.bar_kvgo, 1);
+        mbar_init(&sh.bar_kvgo[0], 1);
+        mbar_init(&sh.bar_kvgo[1], 1);
         fence_barrier_init();
     }
     fence_before();
@@ -763,6 +764,357 @@ k_attn_fwd_p(const float* __restrict__ q, const float* __restrict__ k, const flo
                     dst[u] = make_float4((a[4 * u] + a[16 + 4 * u]) * sc, (a[4 * u + 1] + a[17 + 4 * u]) * sc,
                                          (a[4 * u + 2] + a[18 + 4 * u]) * sc, (a[4 * u + 3] + a[19 + 4 * u]) * sc);
                 lse[(size_t)bh * L + i] = m * LN2 + logf(lt);
+            }
+        }
+        fence_before();
+        __syncthreads();
+    }
+    if (warp == 0) tmem_dealloc(tmem, 256);
+}
+
+
+// ================================================================================================
+// backward, two-pass variant: attn_tc::k_attn_bwd_tc (one CTA per (sample, head), 256 threads, two CTAs per SM, S / dP and
+// the in-place Pd / dS pieces in tensor memory, pass A by query rows for dQ, pass B by key rows for dV / dK) with the
+// operand handling of this file: no transposed copies (k, dO, q enter the second GEMMs as MN-major B operands from the row
+// tiles), [b0 | b1] as one N = 32 operand (two MMAs per k-step instead of three), elect.sync issue with low-word descriptors.
+// Score blocks are 96 columns wide so that S, dP (2 x 96) and two 32-column accumulators fit 256 TMEM columns.
+// It computes every score twice but keeps two independent CTAs per SM, which the single-pass kernel cannot.
+// ================================================================================================
+constexpr int T2_BW = 96;
+constexpr int T2_ROWS = 224;                       // positions per row tile (L <= 224)
+constexpr size_t T2_SMEM = ((size_t)T2_ROWS + 256) * 128 + 1024;   // the k | v tile is read 128 rows at a time from row 128
+constexpr uint32_t T2_X = 0, T2_Y = T2_BW, T2_A1 = 192, T2_A2 = 224;
+
+struct ShT2 {
+    // Two barriers, not one: after the wait for a block's second GEMMs there is no CTA barrier before warp 0 commits the next
+    // block's S / dP.  With a single mbarrier a warp that wakes up late from that wait could find the barrier TWO phases ahead,
+    // read its parity as "not complete" and wait forever.  With one barrier per GEMM kind, two commits on the same barrier are
+    // always separated by a __syncthreads that every thread reaches only after its previous wait on that barrier.
+    uint64_t bar_s, bar_g;
+    uint32_t tmem;
+    float red[4][8];
+    __align__(16) float ls[256];          // lse * log2(e) per query (+inf for rows >= L)
+    __align__(16) float dl[256];          // delta_i * sds
+};
+
+// pass A chunk (16 keys of this thread's query row): dS scaled by sds into sx
+template <bool TRAIN, bool DIAG>
+__device__ __forceinline__ void t2_chunk_a(uint32_t ts, uint32_t tp, float f, float li, float Di, float fdp, float dsc, int nvalid,
+                                           uint32_t seed, uint32_t site, uint32_t g0, uint32_t thr24, float (&sx)[16]) {
+    float dp[16];
+    tmem_ld16(ts, sx);
+    tmem_ld16(tp, dp);
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+        uint32_t r = 0u;
+        if (TRAIN) r = rng4(seed, site, (uint64_t)(g0 + g));
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int c = 4 * g + e;
+            float p = ex2(fmaf(sx[c], f, -li));
+            if (DIAG) p = c < nvalid ? p : 0.f;
+            float k2 = dsc;
+            if (TRAIN) k2 = (e == 3 ? r : (r << (24 - 8 * e))) >= thr24 ? dsc : 0.f;
+            sx[c] = p * fmaf(dp[c] * k2, fdp, -Di);
+        }
+    }
+}
+// pass B chunk (16 queries i0.. of this thread's key row j): Pd into sx, dS (scaled) into dp.  jrel = j - i0: query e is
+// masked when e < jrel.  The four keys of a dropout hash group sit in four neighbouring lanes: lane x of the quad hashes the
+// queries e = x, x+4, x+8, x+12 of the chunk and the quad exchanges them.
+template <bool TRAIN, bool DIAG>
+__device__ __forceinline__ void t2_chunk_b(uint32_t ts, uint32_t tp, float f, float fdp, float dsc, const float* __restrict__ lsp,
+                                           const float* __restrict__ dlp, int jrel, int i0, int L, int Lp4, int lane, int jb,
+                                           uint32_t seed, uint32_t site, uint32_t hbase, uint32_t thr24, float (&sx)[16], float (&dp)[16]) {
+    tmem_ld16(ts, sx);
+    tmem_ld16(tp, dp);
+    uint32_t hv[4] = {0u, 0u, 0u, 0u};
+    if (TRAIN) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int qi = min(i0 + (lane & 3) + 4 * u, L - 1);
+            hv[u] = rng4(seed, site, (uint64_t)(hbase + (uint32_t)qi * (uint32_t)Lp4));
+        }
+    }
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+        const float4 l4 = *reinterpret_cast<const float4*>(lsp + 4 * g), d4 = *reinterpret_cast<const float4*>(dlp + 4 * g);
+        const float la[4] = {l4.x, l4.y, l4.z, l4.w}, da[4] = {d4.x, d4.y, d4.z, d4.w};
+#pragma unroll
+        for (int x = 0; x < 4; ++x) {
+            const int e = 4 * g + x;
+            float p = ex2(fmaf(sx[e], f, -la[x]));
+            if (DIAG) p = e < jrel ? 0.f : p;
+            float k2 = dsc;
+            if (TRAIN) {
+                const uint32_t r = __shfl_sync(0xffffffffu, hv[g], (lane & ~3) | x);
+                k2 = (r << jb) >= thr24 ? dsc : 0.f;
+            }
+            sx[e] = p * k2;
+            dp[e] = p * fmaf(dp[e] * k2, fdp, -da[x]);
+        }
+    }
+}
+
+template <bool TRAIN>
+__global__ void __launch_bounds__(256, 2)
+k_attn_bwd_t2(const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v,
+              const float* __restrict__ o, const float* __restrict__ lse, const float* __restrict__ dO,
+              float* __restrict__ dq, float* __restrict__ dk, float* __restrict__ dv, int L, DropCfg dc, uint32_t site) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ ShT2 sh;
+    uint8_t* QG = align1k(smem_raw);               // [position][q0 | q1 | g0 | g1]
+    uint8_t* KV = QG + T2_ROWS * 128;              // [position][k0 | k1 | v0 | v1]
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int bh = blockIdx.x, b = bh / H, hd = bh % H;
+    const size_t base = (size_t)b * L * D + hd * DH;
+    const int ntile = (L + 127) >> 7, NKP = (L + 15) & ~15, nblk = (NKP + T2_BW - 1) / T2_BW, Lp4 = ((L + 3) & ~3) >> 2;
+    if (warp == 0) tmem_alloc(&sh.tmem, 256);
+    if (tid == 0) { mbar_init(&sh.bar_s, 1); mbar_init(&sh.bar_g, 1); fence_barrier_init(); }
+    const int c4 = tid & 3, r0 = tid >> 2;
+    float4 vq[4], vk[4], vv[4], vg[4];
+    float dsum[4];
+    float mx[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int R = r0 + 64 * i;
+        vq[i] = vk[i] = vv[i] = vg[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        float ds = 0.f;
+        if (R < L) {
+            const size_t off = base + (size_t)R * D + 4 * c4;
+            vq[i] = __ldg(reinterpret_cast<const float4*>(q + off));
+            vk[i] = __ldg(reinterpret_cast<const float4*>(k + off));
+            vv[i] = __ldg(reinterpret_cast<const float4*>(v + off));
+            vg[i] = __ldg(reinterpret_cast<const float4*>(dO + off));
+            const float4 oo = __ldg(reinterpret_cast<const float4*>(o + off));
+            ds = vg[i].x * oo.x + vg[i].y * oo.y + vg[i].z * oo.z + vg[i].w * oo.w;
+        }
+        ds += __shfl_xor_sync(0xffffffffu, ds, 1);
+        ds += __shfl_xor_sync(0xffffffffu, ds, 2);
+        dsum[i] = ds;
+        if (c4 == 0) sh.ls[R] = R < L ? lse[(size_t)bh * L + R] * LOG2E : INFINITY;
+        mx[0] = amax4(vq[i], mx[0]); mx[1] = amax4(vk[i], mx[1]); mx[2] = amax4(vv[i], mx[2]); mx[3] = amax4(vg[i], mx[3]);
+    }
+#pragma unroll
+    for (int kx = 0; kx < 4; ++kx) {
+        const float w = warp_max(mx[kx]);
+        if (lane == 0) sh.red[kx][warp] = w;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kx = 0; kx < 4; ++kx) {
+        float r = sh.red[kx][lane & 7];
+#pragma unroll
+        for (int off = 4; off > 0; off >>= 1) r = fmaxf(r, __shfl_xor_sync(0xffffffffu, r, off));
+        mx[kx] = r;
+    }
+    float sq, iq, sk, ik, sv, iv, sg, ig, sds, ids;
+    pow2_scale(mx[0], sq, iq); pow2_scale(mx[1], sk, ik); pow2_scale(mx[2], sv, iv); pow2_scale(mx[3], sg, ig);
+    const float dsc = TRAIN ? dc.scale : 1.0f;
+    pow2_scale(64.0f * mx[3] * mx[2] * dsc, sds, ids);        // |dS| <= |dPd| + |delta| <= 2 * 16 gmax vmax scale
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int R = r0 + 64 * i;
+        if (c4 == 0) sh.dl[R] = dsum[i] * sds;
+        if (R < T2_ROWS) {
+            const uint32_t ob = (uint32_t)((R >> 3) * 1024 + (R & 7) * 128) + (((((uint32_t)c4 >> 1) ^ (uint32_t)R) & 7u) << 4) + (c4 & 1) * 8;
+            uint2 a0, a1, b0, b1;
+            split4(vq[i], sq, a0, a1);
+            split4(vg[i], sg, b0, b1);
+            *reinterpret_cast<uint2*>(QG + ob) = a0;
+            *reinterpret_cast<uint2*>(QG + (ob ^ 0x20u)) = a1;
+            *reinterpret_cast<uint2*>(QG + (ob ^ 0x40u)) = b0;
+            *reinterpret_cast<uint2*>(QG + (ob ^ 0x60u)) = b1;
+            split4(vk[i], sk, a0, a1);
+            split4(vv[i], sv, b0, b1);
+            *reinterpret_cast<uint2*>(KV + ob) = a0;
+            *reinterpret_cast<uint2*>(KV + (ob ^ 0x20u)) = a1;
+            *reinterpret_cast<uint2*>(KV + (ob ^ 0x40u)) = b0;
+            *reinterpret_cast<uint2*>(KV + (ob ^ 0x60u)) = b1;
+        }
+    }
+    fence_async_smem();
+    fence_before();
+    __syncthreads();
+    fence_after();
+    const uint32_t tmem = sh.tmem;
+    const uint32_t tl = tmem + ((uint32_t)(32 * (warp & 3)) << 16);
+    const int half = warp >> 2;
+    const float f = iq * ik * LOG2E;               // raw S -> log2 domain
+    const float fdp = ig * iv * sds;               // raw dP (times the keep scale) -> dPd * sds
+    const uint32_t thr24 = dc.thr16 << 24;
+    const uint32_t qgl = dlo_k(smem_u32(QG)), kvl = dlo_k(smem_u32(KV));
+    constexpr uint32_t id32 = idesc_f16(32, false, true);
+    uint32_t ph_s = 0, ph_g = 0;
+
+    // ---------------- pass A: rows = queries; dQ[128 x 32] += dS [k0 | k1]
+    // (Issuing the consuming MMAs of a block together with the S / dP MMAs of the next block under one commit -- one MMA round
+    // trip per block instead of two -- was measured: 809 us against 751 us.  The two CTAs of an SM interleave better when a
+    // block's two waits are short than when its one wait is long.)
+#pragma unroll 1
+    for (int t = 0; t < ntile; ++t) {
+        const int Rw = 128 * t + 32 * (warp & 3), i = Rw + lane;
+        const bool wvalid = Rw < L;
+        const int last_q = min(L, 128 * (t + 1)) - 1;
+        const float li = sh.ls[i], Di = sh.dl[i];
+        const uint32_t rb4 = (((uint32_t)bh + dc.bh_off) * (uint32_t)L + (uint32_t)min(i, L - 1)) * (uint32_t)Lp4;
+        bool first = true;
+#pragma unroll 1
+        for (int kb = 0; kb < nblk; ++kb) {
+            const int key0 = T2_BW * kb;
+            if (key0 > last_q) break;
+            const int Nb = min(min(T2_BW, NKP - key0), ((last_q - key0) & ~15) + 16);      // no key beyond the tile's last query
+            if (warp == 0) {
+                if (elect_one()) {
+                    const uint32_t id = idesc_f16(Nb, false, false);
+                    const uint32_t a = qgl + (uint32_t)(128 * t) * 8, bb = kvl + (uint32_t)key0 * 8;
+                    mma_lo(tmem + T2_X, a, bb, id, 0u);              // q0 k0
+                    mma_lo(tmem + T2_X, a + 2, bb, id, 1u);          // q1 k0
+                    mma_lo(tmem + T2_X, a, bb + 2, id, 1u);          // q0 k1
+                    mma_lo(tmem + T2_Y, a + 4, bb + 4, id, 0u);      // g0 v0
+                    mma_lo(tmem + T2_Y, a + 6, bb + 4, id, 1u);      // g1 v0
+                    mma_lo(tmem + T2_Y, a + 4, bb + 6, id, 1u);      // g0 v1
+                    mma_commit(&sh.bar_s);
+                }
+                __syncwarp();
+            }
+            mbar_wait(&sh.bar_s, ph_s);
+            ph_s ^= 1;
+            fence_after();
+            if (wvalid) {
+#pragma unroll 1
+                for (int ch = half; ch < Nb / 16; ch += 2) {
+                    const int j0 = key0 + 16 * ch;
+                    if (j0 > Rw + 31) { zero16(tl + T2_X + 16 * ch); continue; }
+                    float sx[16];
+                    if (j0 + 15 > Rw)
+                        t2_chunk_a<TRAIN, true>(tl + T2_X + 16 * ch, tl + T2_Y + 16 * ch, f, li, Di, fdp, dsc, i - j0 + 1, dc.seed, site,
+                                                rb4 + (uint32_t)(j0 >> 2), thr24, sx);
+                    else
+                        t2_chunk_a<TRAIN, false>(tl + T2_X + 16 * ch, tl + T2_Y + 16 * ch, f, li, Di, fdp, dsc, 16, dc.seed, site,
+                                                 rb4 + (uint32_t)(j0 >> 2), thr24, sx);
+                    put16(tl + T2_X + 16 * ch, sx);
+                }
+            }
+            tmem_st_wait();
+            fence_before();
+            __syncthreads();
+            if (warp == 0) {
+                fence_after();
+                if (elect_one()) {
+                    for (int kk = 0; kk < Nb / 16; ++kk) {
+                        const uint32_t a0 = tmem + T2_X + 16 * kk, bl = kvl + (uint32_t)(key0 + 16 * kk) * 8;
+                        mma_lo_ts(tmem + T2_A1, a0, bl, id32, (first && kk == 0) ? 0u : 1u);
+                        mma_lo_ts(tmem + T2_A1, a0 + 8, bl, id32, 1u);
+                    }
+                    mma_commit(&sh.bar_g);
+                }
+                __syncwarp();
+            }
+            first = false;
+            mbar_wait(&sh.bar_g, ph_g);
+            ph_g ^= 1;
+            fence_after();
+        }
+        if (half == 0 && wvalid) {
+            float a[32];
+            tmem_ld32(tl + T2_A1, a);
+            if (i < L) {
+                const float sc = 0.25f * ids * ik;
+                float4* dst = reinterpret_cast<float4*>(dq + base + (size_t)i * D);
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    dst[u] = make_float4((a[4 * u] + a[16 + 4 * u]) * sc, (a[4 * u + 1] + a[17 + 4 * u]) * sc,
+                                         (a[4 * u + 2] + a[18 + 4 * u]) * sc, (a[4 * u + 3] + a[19 + 4 * u]) * sc);
+            }
+        }
+        fence_before();
+        __syncthreads();
+    }
+
+    // ---------------- pass B: rows = keys; dV[128 x 32] += Pd^T [g0 | g1], dK[128 x 32] += dS^T [q0 | q1]
+#pragma unroll 1
+    for (int t = 0; t < ntile; ++t) {
+        const int Jw = 128 * t + 32 * (warp & 3), j = Jw + lane;
+        const bool wvalid = Jw < L;
+        const uint32_t jg = (uint32_t)(j >> 2);
+        const int jb = 24 - 8 * (j & 3);
+        const uint32_t hbase = (((uint32_t)bh + dc.bh_off) * (uint32_t)L) * (uint32_t)Lp4 + jg;
+        bool first = true;
+#pragma unroll 1
+        for (int qb = 0; qb < nblk; ++qb) {
+            int q0 = T2_BW * qb;
+            int Nb = min(T2_BW, NKP - q0);
+            if (q0 + Nb <= 128 * t) continue;              // every query of the block precedes every key of the tile
+            if (q0 < 128 * t) { Nb -= 128 * t - q0; q0 = 128 * t; }      // no query before the tile's first key
+            if (warp == 0) {
+                if (elect_one()) {
+                    const uint32_t id = idesc_f16(Nb, false, false);
+                    const uint32_t a = kvl + (uint32_t)(128 * t) * 8, bb = qgl + (uint32_t)q0 * 8;
+                    mma_lo(tmem + T2_X, a, bb, id, 0u);              // k0 q0
+                    mma_lo(tmem + T2_X, a + 2, bb, id, 1u);          // k1 q0
+                    mma_lo(tmem + T2_X, a, bb + 2, id, 1u);          // k0 q1
+                    mma_lo(tmem + T2_Y, a + 4, bb + 4, id, 0u);      // v0 g0
+                    mma_lo(tmem + T2_Y, a + 6, bb + 4, id, 1u);      // v1 g0
+                    mma_lo(tmem + T2_Y, a + 4, bb + 6, id, 1u);      // v0 g1
+                    mma_commit(&sh.bar_s);
+                }
+                __syncwarp();
+            }
+            mbar_wait(&sh.bar_s, ph_s);
+            ph_s ^= 1;
+            fence_after();
+            if (wvalid) {
+#pragma unroll 1
+                for (int ch = half; ch < Nb / 16; ch += 2) {
+                    const int i0 = q0 + 16 * ch;
+                    if (i0 + 15 < Jw) { zero16(tl + T2_X + 16 * ch); zero16(tl + T2_Y + 16 * ch); continue; }
+                    float sx[16], dp[16];
+                    if (Jw + 31 > i0)
+                        t2_chunk_b<TRAIN, true>(tl + T2_X + 16 * ch, tl + T2_Y + 16 * ch, f, fdp, dsc, sh.ls + i0, sh.dl + i0, j - i0, i0, L, Lp4,
+                                                lane, jb, dc.seed, site, hbase, thr24, sx, dp);
+                    else
+                        t2_chunk_b<TRAIN, false>(tl + T2_X + 16 * ch, tl + T2_Y + 16 * ch, f, fdp, dsc, sh.ls + i0, sh.dl + i0, 0, i0, L, Lp4,
+                                                 lane, jb, dc.seed, site, hbase, thr24, sx, dp);
+                    put16(tl + T2_X + 16 * ch, sx);
+                    put16(tl + T2_Y + 16 * ch, dp);
+                }
+            }
+            tmem_st_wait();
+            fence_before();
+            __syncthreads();
+            if (warp == 0) {
+                fence_after();
+                if (elect_one()) {
+                    for (int kk = 0; kk < Nb / 16; ++kk) {
+                        const uint32_t ax = tmem + T2_X + 16 * kk, ay = tmem + T2_Y + 16 * kk;
+                        const uint32_t bl = qgl + (uint32_t)(q0 + 16 * kk) * 8;
+                        const uint32_t acc = (first && kk == 0) ? 0u : 1u;
+                        mma_lo_ts(tmem + T2_A1, ax, bl + 4, id32, acc);         // Pd^T [g0 | g1]
+                        mma_lo_ts(tmem + T2_A1, ax + 8, bl + 4, id32, 1u);
+                        mma_lo_ts(tmem + T2_A2, ay, bl, id32, acc);             // dS^T [q0 | q1]
+                        mma_lo_ts(tmem + T2_A2, ay + 8, bl, id32, 1u);
+                    }
+                    mma_commit(&sh.bar_g);
+                }
+                __syncwarp();
+            }
+            first = false;
+            mbar_wait(&sh.bar_g, ph_g);
+            ph_g ^= 1;
+            fence_after();
+        }
+        if (wvalid) {                                    // half 0 stores dv, half 1 stores dk
+            float a[32];
+            tmem_ld32(tl + (half == 0 ? T2_A1 : T2_A2), a);
+            if (j < L) {
+                const float sc = half == 0 ? ig : ids * iq;
+                float4* dst = reinterpret_cast<float4*>((half == 0 ? dv : dk) + base + (size_t)j * D);
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    dst[u] = make_float4((a[4 * u] + a[16 + 4 * u]) * sc, (a[4 * u + 1] + a[17 + 4 * u]) * sc,
+                                         (a[4 * u + 2] + a[18 + 4 * u]) * sc, (a[4 * u + 3] + a[19 + 4 * u]) * sc);
             }
         }
         fence_before();

@@ -485,6 +485,7 @@ k_attn_bwd_tc(const float* __restrict__ q, const float* __restrict__ k, const fl
             mbar_wait(&sh.bar, phase);
             phase ^= 1;
             fence_after();
+            __syncthreads();      // no thread may still be in this wait when the next commit on the same barrier is issued
         }
         if (half == 0 && wvalid) {
             float a[16];
@@ -583,6 +584,7 @@ k_attn_bwd_tc(const float* __restrict__ q, const float* __restrict__ k, const fl
             mbar_wait(&sh.bar, phase);
             phase ^= 1;
             fence_after();
+            __syncthreads();      // no thread may still be in this wait when the next commit on the same barrier is issued
         }
         if (wvalid) {                                    // half 0 stores dv, half 1 stores dk
             float a[16];

@@ -1122,7 +1122,14 @@ static int encoder_bwd_impl(const amid_encoder_tensors* P, const float* x0, cons
         if (mode == 3) {
             const size_t mma_smem = (size_t)((L + 15) / 16 * 16) * (4 * attn::LDS + 2) * sizeof(float);
             if (int rc = ensure_smem((const void*)attn::k_attn_bwd_mma<true>, mma_smem)) return rc;
-            if (L >= attn_p::PMINL && L <= attn_p::PMAXL) {       // single-pass pipelined kernel, persistent CTAs
+            if (L >= attn_tc::MINL && L <= attn_tc::MAXL) {       // two-pass kernel, two CTAs per SM (741 us at the C3 shape)
+                auto kfn = dc.train ? attn_p::k_attn_bwd_t2<true> : attn_p::k_attn_bwd_t2<false>;
+                if (int rc = ensure_smem((const void*)kfn, attn_p::T2_SMEM)) return rc;
+                AMID_K("k_attn_bwd_t2", stream);
+                kfn<<<B * H, 256, attn_p::T2_SMEM, stream>>>(S->q[i], S->k[i], S->v[i], S->o[i], S->lse[i], dO, dq, dk, dv, L, dc,
+                                                             dc.site_base + site_attn(i));
+                AMID_LAUNCH_CHECK("k_attn_bwd_t2");
+            } else if (L >= attn_p::PMINL && L <= attn_p::PMAXL) {       // single-pass pipelined kernel, persistent CTAs (805 us)
                 auto kfn = dc.train ? attn_p::k_attn_bwd_p<true> : attn_p::k_attn_bwd_p<false>;
                 if (int rc = ensure_smem((const void*)kfn, attn_p::PBWD_SMEM)) return rc;
                 AMID_K("k_attn_bwd_p", stream);

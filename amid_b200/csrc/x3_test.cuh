@@ -162,6 +162,13 @@ extern "C" int amid_attn_bwd_test(const float* q, const float* k, const float* v
         AMID_K("k_attn_bwd_p", stream);
         kfn<<<std::min(B * H, sm_count()), attn_p::NTH, attn_p::PBWD_SMEM, stream>>>(q, k, v, o, lse, dO, dq, dk, dv, L, B * H, dc, site);
         AMID_LAUNCH_CHECK("k_attn_bwd_p");
+    } else if (impl == 5) {
+        AMID_REQUIRE(L <= attn_tc::MAXL, "attn_bwd_test: two-pass tcgen05 path needs L <= %d", attn_tc::MAXL);
+        auto kfn = dc.train ? attn_p::k_attn_bwd_t2<true> : attn_p::k_attn_bwd_t2<false>;
+        if (int rc = ensure_smem((const void*)kfn, attn_p::T2_SMEM)) return rc;
+        AMID_K("k_attn_bwd_t2", stream);
+        kfn<<<B * H, 256, attn_p::T2_SMEM, stream>>>(q, k, v, o, lse, dO, dq, dk, dv, L, dc, site);
+        AMID_LAUNCH_CHECK("k_attn_bwd_t2");
     } else {
         AMID_REQUIRE(L <= attn_tc::MAXL, "attn_bwd_test: tcgen05 path needs L <= %d", attn_tc::MAXL);
         if (int rc = ensure_smem((const void*)attn_tc::k_attn_bwd_tc, attn_tc::BWD_SMEM)) return rc;

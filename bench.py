@@ -416,7 +416,7 @@ def kernel_work(name, B, L, C):
         "k_mim_scores_mma": {"flop": 2.0 * B * L * L * D, "byte": 2 * act},
         "k_mim_scores_tc5": {"flop": 3 * 2.0 * B * L * L * D, "byte": 2 * act},   # 3xTF32: three MMAs per product
     }
-    for suffix in ("", "_mma", "_mma3", "_tc", "_p"):
+    for suffix in ("", "_mma", "_mma3", "_tc", "_p", "_t2"):
         table["k_attn_fwd" + suffix] = {"flop": attn_full, "byte": 4 * act}          # r: q k v     w: o
         table["k_attn_bwd" + suffix] = {"flop": 2.5 * attn_full, "byte": 8 * act}    # r: q k v o dO   w: dq dk dv
     for k, (f, b) in chain.items():

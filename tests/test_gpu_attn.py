@@ -8,8 +8,8 @@ import torch
 
 pytestmark = pytest.mark.gpu
 D, H, DH = 128, 8, 16
-IMPLS = {"fp32": 0, "mma_tf32": 1, "mma_3xtf32": 2, "tcgen05": 3, "tcgen05_p": 4}
-TOL = {"fp32": 3e-6, "mma_tf32": 3e-3, "mma_3xtf32": 3e-6, "tcgen05": 3e-6, "tcgen05_p": 3e-6}
+IMPLS = {"fp32": 0, "mma_tf32": 1, "mma_3xtf32": 2, "tcgen05": 3, "tcgen05_p": 4, "tcgen05_t2": 5}
+TOL = {"fp32": 3e-6, "mma_tf32": 3e-3, "mma_3xtf32": 3e-6, "tcgen05": 3e-6, "tcgen05_p": 3e-6, "tcgen05_t2": 3e-6}
 
 
 def _ref_fwd(q, k, v, L, keep, scale):
@@ -53,6 +53,8 @@ def test_attention_forward_all_impls(impl, B, L, train):
     from amid_b200._abi import Dropout, call
     if impl == "tcgen05_p" and L < 64:
         pytest.skip("the pipelined kernels cover 64 <= L <= 256 (shorter sequences take the mma.sync path)")
+    if impl == "tcgen05_t2":
+        pytest.skip("tcgen05_t2 is a backward kernel")
     q, k, v = _inputs(B, L, 100 * B + L, spread=(L == 130))
     drop = Dropout(1 if train else 0, 0.5, 9876543210, 8)
     site = 8 + 4
@@ -79,7 +81,7 @@ def test_attention_backward_all_impls(impl, B, L, train):
     from amid_b200._abi import Dropout, call
     if impl == "tcgen05_p" and L < 64:
         pytest.skip("the pipelined kernels cover 64 <= L <= 256 (shorter sequences take the mma.sync path)")
-    if B > 8 and impl != "tcgen05_p":
+    if B > 8 and impl not in ("tcgen05_p", "tcgen05_t2"):
         pytest.skip("many-heads-per-CTA cases exercise the persistent kernels")
     q, k, v = _inputs(B, L, 7 * B + L)
     g = torch.Generator().manual_seed(L)
