@@ -484,6 +484,10 @@ k_attn_bwd_p(const float* __restrict__ q, const float* __restrict__ k, const flo
             DBG(51);
             mbar_wait(&sh.bar_done, nhead & 1);
             fence_after();
+            // The exchange buffer below aliases staging set 0.  Its stores are ordered after every warp's last staging stores
+            // through bar_full -> tcgen05.commit -> bar_done; this CTA barrier states the same order in a form that
+            // compute-sanitizer's racecheck can see (it does not follow commits that arrive on an mbarrier).
+            named_sync(1, 512);
             DBG(52);
             // ---- accumulators -> HBM.  warp = (lane quarter lq, c): dQ of query tile c, dK / dV of key block c
             float* xch = reinterpret_cast<float*>(STG);          // [key block][tensor][64 keys][20] (staging tiles are free now)
