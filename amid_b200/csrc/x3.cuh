@@ -69,6 +69,18 @@ __device__ __forceinline__ bool elect_one_sync() {
     asm volatile("{\n.reg .pred P1;\nelect.sync _|P1, 0xffffffff;\nselp.u32 %0, 1, 0, P1;\n}" : "=r"(pred));
     return pred != 0;
 }
+// rows [row0, row0+128) of a [M,128] fp32 tensor into L2 (512 lines of 128 B, two per thread of a 256-thread CTA), issued
+// right before a GEMM wait for the tile the NEXT stage of the chain reads: that load then pays an L2 hit instead of an HBM
+// round trip in the middle of the chain.  (Prefetching everything at kernel start was measured slower: the requests compete
+// with the first demand loads.)
+__device__ __forceinline__ void prefetch_tile_l2(const float* __restrict__ g, int row0, int M) {
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        const int idx = threadIdx.x * 2 + j, r = row0 + (idx >> 2);
+        if (r < M) asm volatile("prefetch.global.L2 [%0];" ::"l"(g + (size_t)r * D + (idx & 3) * 32));
+    }
+}
+
 // ---- bulk asynchronous copy global -> shared (TMA engine, 1-D), completion counted in bytes on an mbarrier
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
@@ -415,6 +427,7 @@ k_proj_ffn_x3(const float* __restrict__ o, const float* __restrict__ qn, int M, 
     uint32_t ph_mma = 0, ph_w = 0;
     float inv_a = global_to_a(sh, e, sm.stage, tl, o, wbase, rv);
     // ---- x1 = Qn + o Wo^T + bo ; y = LN2(x1)
+    prefetch_tile_l2(qn, row0, M);
     run_gemm_x3(sh, 0, sm.W, false, ph_mma, ph_w);
     load_w_bulk(sh, sm.W, img_1);
     {
@@ -615,6 +628,8 @@ k_ffn_bwd_x3(const float* __restrict__ dxo, const float* __restrict__ h, const f
         put_a32(tl, e.cb + 32, g[1], sc);
     }
     // ---- dhpre = (do2 W2) * scale * [h > 0]
+    prefetch_tile_l2(h, row0, M);
+    prefetch_tile_l2(x1, row0, M);
     run_gemm_x3(sh, 0, sm.W, false, ph_mma, ph_w);
     load_w_bulk(sh, sm.W, img_1t);
     {
@@ -717,8 +732,11 @@ k_qkv_bwd_x3(const float* __restrict__ dq, const float* __restrict__ dk, const f
     float mean = 0.f, rstd = 0.f;
     if (valid) { mean = st1[(size_t)gr * 2]; rstd = st1[(size_t)gr * 2 + 1]; }
     const float inv_q = global_to_a(sh, e, sm.stage, tl, dq, wbase, rv);
+    prefetch_tile_l2(dx1, row0, M);
+    prefetch_tile_l2(xin, row0, M);
     run_gemm_x3(sh, 0, sm.W, false, ph_mma, ph_w);
     load_w_bulk(sh, sm.W, img_kt);
+    prefetch_tile_l2(dk, row0, M);
     {
         const float f = inv_q * __ldg(winv);
 #pragma unroll 1
@@ -755,6 +773,7 @@ k_qkv_bwd_x3(const float* __restrict__ dq, const float* __restrict__ dk, const f
         cur = target;
         put_a32(tl, e.cb, v0, sc);
         put_a32(tl, e.cb + 32, v1, sc);
+        if (g == 0) prefetch_tile_l2(dv, row0, M);
         run_gemm_x3(sh, 0, sm.W, true, ph_mma, ph_w);
         if (g == 0) load_w_bulk(sh, sm.W, img_vt);
         inv_a *= wi;
