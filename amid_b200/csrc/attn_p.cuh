@@ -668,6 +668,13 @@ k_attn_fwd_p(const float* __restrict__ q, const float* __restrict__ k, const flo
     fence_before();
     __syncthreads();
     fence_after();
+    {   // head slices of the CTA that will follow on this SM slot (CTAs are dispatched in index order, two per SM) into L2
+        const int nb = bh + 2 * 148;
+        if (nb < (int)gridDim.x && tid < L) {
+            const size_t noff = (size_t)(nb / H) * L * D + (nb % H) * DH + (size_t)tid * D;
+            prefetch_l2(q + noff); prefetch_l2(k + noff); prefetch_l2(v + noff);
+        }
+    }
     const uint32_t tmem = sh.tmem;
     const uint32_t tl = tmem + ((uint32_t)(32 * (warp & 3)) << 16);
     const int half = warp >> 2, row = 32 * (warp & 3) + lane;
@@ -942,6 +949,13 @@ k_attn_bwd_t2(const float* __restrict__ q, const float* __restrict__ k, const fl
     fence_before();
     __syncthreads();
     fence_after();
+    {   // head slices of the CTA that will follow on this SM slot (CTAs are dispatched in index order, two per SM) into L2
+        const int nb = bh + 2 * 148;
+        if (nb < (int)gridDim.x && tid < L) {
+            const size_t noff = (size_t)(nb / H) * L * D + (nb % H) * DH + (size_t)tid * D;
+            prefetch_l2(q + noff); prefetch_l2(k + noff); prefetch_l2(v + noff); prefetch_l2(dO + noff); prefetch_l2(o + noff);
+        }
+    }
     const uint32_t tmem = sh.tmem;
     const uint32_t tl = tmem + ((uint32_t)(32 * (warp & 3)) << 16);
     const int half = warp >> 2;

@@ -81,6 +81,9 @@ __device__ __forceinline__ void prefetch_tile_l2(const float* __restrict__ g, in
     }
 }
 
+// CTAs are dispatched in index order and two are resident per SM: the tile this SM slot will most probably process next
+constexpr int NEXT_SLOT_TILES = 2 * 148;
+
 // ---- bulk asynchronous copy global -> shared (TMA engine, 1-D), completion counted in bytes on an mbarrier
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
@@ -386,6 +389,7 @@ k_ln_qkv_x3(const float* __restrict__ x, int M, const float* __restrict__ ln_w, 
         }
         if (valid && e.cb == 0) { st1[(size_t)gr * 2] = mean; st1[(size_t)gr * 2 + 1] = rstd; }
     }
+    prefetch_tile_l2(x, row0 + NEXT_SLOT_TILES * 128, M);       // the first load of the CTA that follows on this slot
     run_gemm_x3(sh, 0, sm.W, false, ph_mma, ph_w);
     {
         const float f = inv_qn * __ldg(winv);
@@ -493,6 +497,7 @@ k_proj_ffn_x3(const float* __restrict__ o, const float* __restrict__ qn, int M, 
         parked_to_a(tl, e, sc);
     }
     // ---- xout = (dropout2(h W2^T + b2) + y) * ~tmask  (+ last LayerNorm)
+    prefetch_tile_l2(o, row0 + NEXT_SLOT_TILES * 128, M);
     run_gemm_x3(sh, 0, sm.W, false, ph_mma, ph_w);
     {
         const float f = inv_a * __ldg(winv + 2);
@@ -690,6 +695,7 @@ k_ffn_bwd_x3(const float* __restrict__ dxo, const float* __restrict__ h, const f
         }
     }
     // ---- dO = dx1 Wo
+    prefetch_tile_l2(dxo, row0 + NEXT_SLOT_TILES * 128, M);
     run_gemm_x3(sh, 0, sm.W, false, ph_mma, ph_w);
     {
         const float f = inv_a * __ldg(winv + 2);
@@ -774,6 +780,7 @@ k_qkv_bwd_x3(const float* __restrict__ dq, const float* __restrict__ dk, const f
         put_a32(tl, e.cb, v0, sc);
         put_a32(tl, e.cb + 32, v1, sc);
         if (g == 0) prefetch_tile_l2(dv, row0, M);
+        else prefetch_tile_l2(dq, row0 + NEXT_SLOT_TILES * 128, M);
         run_gemm_x3(sh, 0, sm.W, true, ph_mma, ph_w);
         if (g == 0) load_w_bulk(sh, sm.W, img_vt);
         inv_a *= wi;
