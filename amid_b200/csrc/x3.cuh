@@ -807,8 +807,7 @@ constexpr int SUB_ROWS = 64;
 constexpr int SUBP_BYTES = SUB_ROWS * 128 * 2;       // one BF16 piece of a [64][128] sub-tile: 16 KB (2 chunks of 8 KB)
 constexpr int SUB_CHUNK = SUB_ROWS * 128;            // bytes between the two 64-feature chunks
 constexpr int WG_BUF_BYTES = 6 * SUBP_BYTES;         // dY pieces 0..2, X pieces 0..2
-constexpr int ONESX_BYTES = 16 * 128;                // [16 rows][64 tokens] BF16 ones, K-major
-constexpr size_t WGRADX_SMEM = 2 * (size_t)WG_BUF_BYTES + ONESX_BYTES + 1024;    // 195 KB
+constexpr size_t WGRADX_SMEM = 2 * (size_t)WG_BUF_BYTES + 1024;    // 193 KB
 __device__ __forceinline__ uint32_t sub_off8(int r, int u) {
     return (uint32_t)((u >> 3) * SUB_CHUNK + (r >> 3) * 1024 + (r & 7) * 128 + (((u & 7) ^ (r & 7)) << 4));
 }
@@ -859,13 +858,11 @@ k_wgrad_x3(WgradJobsX jobs, int M, float* __restrict__ wpart /*[6][S][128*128]*/
     __shared__ uint64_t bars[2];           // tcgen05.commit: the MMAs that read buffer b are complete
     __shared__ uint32_t tmem_s;
     uint8_t* buf0 = align1k(smem_raw);
-    uint8_t* Ones = buf0 + 2 * WG_BUF_BYTES;
     const float* __restrict__ dY = jobs.dY[blockIdx.y];
     const float* __restrict__ X = jobs.X[blockIdx.y];
     const int S = gridDim.x;
     if ((threadIdx.x >> 5) == 0) tmem_alloc(&tmem_s, 256);
     if (threadIdx.x == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); fence_barrier_init(); }
-    for (int i = threadIdx.x; i < ONESX_BYTES / 4; i += WGX_THREADS) reinterpret_cast<uint32_t*>(Ones)[i] = 0x3F803F80u;
     fence_async_smem();
     fence_before();
     __syncthreads();
@@ -874,7 +871,6 @@ k_wgrad_x3(WgradJobsX jobs, int M, float* __restrict__ wpart /*[6][S][128*128]*/
     const int subs = (M + SUB_ROWS - 1) / SUB_ROWS;
     uint32_t phase[2] = {0u, 0u};
     constexpr uint32_t id_w = idesc_bf16(128, true, true);
-    constexpr uint32_t id_b = idesc_bf16(16, true, false);
     // sub-tiles are dealt in pairs so that a CTA streams 128 consecutive tokens at a time; the global loads of sub-tile
     // i+1 are issued before sub-tile i is split and stored, so their latency hides behind the conversion and the MMAs
     const int pairs = (subs + 1) / 2;
@@ -883,6 +879,10 @@ k_wgrad_x3(WgradJobsX jobs, int M, float* __restrict__ wpart /*[6][S][128*128]*/
     int n_it = 2 * my_pairs;
     if (n_it && sub_of(n_it - 1) >= subs) --n_it;
     float4 vy[WGX_IT], vx[WGX_IT];
+    // bias gradient = column sums of dY: accumulated on the CUDA cores from the rows this thread converts anyway (thread =
+    // 4 columns, fixed row order) instead of three more N = 16 MMAs per k-step against a tile of ones -- the MMAs of this kernel
+    // are bound by their 8 KB of shared-memory operand reads, and those three read the 4 KB A operand once more each
+    float4 bsum = make_float4(0.f, 0.f, 0.f, 0.f);
     if (n_it) { load_sub(vy, dY, sub_of(0) * SUB_ROWS, M); load_sub(vx, X, sub_of(0) * SUB_ROWS, M); }
     int it = 0;
     for (; it < n_it; ++it) {
@@ -891,27 +891,25 @@ k_wgrad_x3(WgradJobsX jobs, int M, float* __restrict__ wpart /*[6][S][128*128]*/
         uint8_t* buf = buf0 + b * WG_BUF_BYTES;
         fill_sub3(buf, vy);
         fill_sub3(buf + 3 * SUBP_BYTES, vx);
+#pragma unroll
+        for (int r = 0; r < WGX_IT; ++r) { bsum.x += vy[r].x; bsum.y += vy[r].y; bsum.z += vy[r].z; bsum.w += vy[r].w; }
         if (it + 1 < n_it) { load_sub(vy, dY, sub_of(it + 1) * SUB_ROWS, M); load_sub(vx, X, sub_of(it + 1) * SUB_ROWS, M); }
         fence_async_smem();
         __syncthreads();          // (an mbarrier hand-off that lets the other 15 warps run ahead was measured 40 % slower)
         if ((threadIdx.x >> 5) == 0 && elect_one_sync()) {
             fence_after();
-            const uint32_t a = smem_u32(buf), x = a + 3 * SUBP_BYTES, o = smem_u32(Ones);
+            const uint32_t a = smem_u32(buf), x = a + 3 * SUBP_BYTES;
 #pragma unroll
             for (int ks = 0; ks < SUB_ROWS / 16; ++ks) {
                 const uint32_t acc = (it || ks) ? 1u : 0u;
                 const uint64_t a0 = desc_sub_mn(a, ks), a1 = desc_sub_mn(a + SUBP_BYTES, ks), a2 = desc_sub_mn(a + 2 * SUBP_BYTES, ks);
                 const uint64_t x0 = desc_sub_mn(x, ks), x1 = desc_sub_mn(x + SUBP_BYTES, ks), x2 = desc_sub_mn(x + 2 * SUBP_BYTES, ks);
-                const uint64_t on = make_desc(o + ks * 32, 16, 1024);
                 mma_bf16(tmem, a0, x0, id_w, acc);
                 mma_bf16(tmem, a0, x1, id_w, 1u);
                 mma_bf16(tmem, a1, x0, id_w, 1u);
                 mma_bf16(tmem, a0, x2, id_w, 1u);
                 mma_bf16(tmem, a1, x1, id_w, 1u);
                 mma_bf16(tmem, a2, x0, id_w, 1u);
-                mma_bf16(tmem + 128, a0, on, id_b, acc);
-                mma_bf16(tmem + 128, a1, on, id_b, 1u);
-                mma_bf16(tmem + 128, a2, on, id_b, 1u);
             }
             mma_commit(&bars[b]);
         }
@@ -937,15 +935,17 @@ k_wgrad_x3(WgradJobsX jobs, int M, float* __restrict__ wpart /*[6][S][128*128]*/
         for (int i = 0; i < 32; i += 4)
             *reinterpret_cast<float4*>(wp + (size_t)e.row * D + c0 + i) = make_float4(a[i], a[i + 1], a[i + 2], a[i + 3]);
     }
-    if (e.cb == 0) {
-        float a[32];
-        if (it) {
-            tmem_ld32(tmem + e.lane_addr + 128, a);
-        } else {
-            a[0] = 0.f;
-        }
-        bpart[((size_t)blockIdx.y * S + blockIdx.x) * D + e.row] = a[0];
     }
+    {   // bias partials: 16 row groups x 128 columns through shared memory (the operand buffers are free now), fixed order
+        float* bred = reinterpret_cast<float*>(buf0);
+        *reinterpret_cast<float4*>(bred + (threadIdx.x >> 5) * D + 4 * (threadIdx.x & 31)) = bsum;
+        __syncthreads();
+        if (threadIdx.x < D) {
+            float sacc = 0.f;
+#pragma unroll
+            for (int w = 0; w < WGX_THREADS / 32; ++w) sacc += bred[w * D + threadIdx.x];
+            bpart[((size_t)blockIdx.y * S + blockIdx.x) * D + threadIdx.x] = sacc;
+        }
     }
     fence_before();
     __syncthreads();
