@@ -103,6 +103,7 @@ _SIGS = {
     "amid_embgrad_workspace_bytes": (c_int64, [c_int64]),
     "amid_embgrad_segreduce": (c_int32, [P, P, c_int64, c_int64, P, P, P, P, c_int64, P]),
     "amid_embgrad_scatter_dense": (c_int32, [P, P, P, c_int64, P, c_int64, P]),
+    "amid_embgrad_scatter_add": (c_int32, [P, P, c_int64, c_int64, P, c_int64, P]),
     "amid_adam_dense": (c_int32, [P, P, P, P, c_int64, c_int32, c_float, c_float, c_float, c_float, P]),
     "amid_adam_rows_lazy": (c_int32, [P, P, P, P, P, P, P, c_int64, c_int32, c_float, c_float, c_float, c_float, P]),
     "amid_adam_rows_flush": (c_int32, [P, P, P, P, c_int64, c_int32, c_float, c_float, c_float, c_float, P]),

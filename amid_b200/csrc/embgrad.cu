@@ -145,6 +145,22 @@ k_scatter_dense(const int64_t* __restrict__ uniq_ids, const float* __restrict__ 
     reinterpret_cast<float4*>(dense + id * D)[lane] = reinterpret_cast<const float4*>(uniq_grads + (size_t)u * D)[lane];
 }
 
+// dense[ids[u] - id_offset, :] += rows[u, :] for u < n; ids are unique within a call (one warp per row, no atomics), rows whose id
+// falls outside [id_offset, id_offset + rows_dense) are skipped.  The owner side of the sparse reduce-scatter of the table
+// gradient: one call per sending rank, in rank order, gives a deterministic sum.
+__global__ void __launch_bounds__(256)
+k_scatter_add_dense(const int64_t* __restrict__ ids, const float* __restrict__ rows, int64_t n, int64_t id_offset,
+                    float* __restrict__ dense, int64_t rows_dense) {
+    const int lane = threadIdx.x & 31;
+    const int64_t u = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (u >= n) return;
+    const int64_t r = ids[u] - id_offset;
+    if (r < 0 || r >= rows_dense) return;
+    float4* dst = reinterpret_cast<float4*>(dense + r * D) + lane;
+    const float4 a = *dst, b = reinterpret_cast<const float4*>(rows + (size_t)u * D)[lane];
+    *dst = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+}
+
 // ------------------------------------------------------------------ Adam
 struct AdamStep {
     float w1;        // 1 - beta1   (lerp weight)
@@ -396,6 +412,16 @@ extern "C" int amid_embgrad_scatter_dense(const int64_t* uniq_ids, const float* 
     k_scatter_dense<<<(unsigned)((max_rows * 32 + 255) / 256), 256, 0, (cudaStream_t)s_>>>(uniq_ids, uniq_grads, n_uniq,
                                                                                             dense, V);
     AMID_LAUNCH_CHECK("k_scatter_dense");
+    return 0;
+}
+
+extern "C" int amid_embgrad_scatter_add(const int64_t* ids, const float* rows, int64_t n, int64_t id_offset, float* dense,
+                                       int64_t rows_dense, amid_stream_t s_) {
+    AMID_REQUIRE(dense && rows_dense > 0 && n >= 0 && (n == 0 || (ids && rows)), "embgrad_scatter_add: bad argument");
+    if (n == 0) return 0;
+    AMID_K("k_scatter_add_dense", (cudaStream_t)s_);
+    k_scatter_add_dense<<<(unsigned)((n * 32 + 255) / 256), 256, 0, (cudaStream_t)s_>>>(ids, rows, n, id_offset, dense, rows_dense);
+    AMID_LAUNCH_CHECK("k_scatter_add_dense");
     return 0;
 }
 

@@ -93,9 +93,7 @@ class Trainer:
             padded[:self.V].copy_(self.table.data)
             self.table_padded = padded
             self.table.data = padded[:self.V]                     # the parameter stays a [V,128] view
-            self.dense_g = torch.zeros(self.Vp, D, device=dev, dtype=torch.float32)
             self.shard_g = torch.empty(self.Vs, D, device=dev, dtype=torch.float32)
-            self.shard_p = torch.empty(self.Vs, D, device=dev, dtype=torch.float32)
             self.opt = [_AdamState(total, 1, dev) for _ in range(n_opt)]
             for st in self.opt:
                 st.tm = torch.zeros(self.Vs, D, device=dev, dtype=torch.float32)
@@ -228,18 +226,44 @@ class Trainer:
         return losses
 
     def _dense_table_step(self, st, uid, ug, nu, lr):
-        """Replicated table, most rows touched: dense gradient -> reduce-scatter -> Adam on this rank's
-        row shard -> all-gather of the updated rows.  Exactly torch.optim.Adam's dense semantics."""
+        """Replicated table, most rows touched: SPARSE reduce-scatter of the table gradient -> dense Adam on this rank's row
+        shard (Adam state sharded 1/N) -> all-gather of the updated rows.  Exactly torch.optim.Adam's dense semantics.
+
+        The locally pre-reduced list (uid ascending, ug) is already bucketed by owner (rank r owns rows [r Vs, (r+1) Vs)), so
+        each rank sends every owner only the rows it touched: an all-to-all of ~(N-1)/N x rows_touched x 512 B instead of a
+        dense reduce-scatter of the whole 458 MB gradient.  The owner adds the received segments in rank order (unique ids
+        inside a segment: no atomics), which fixes the summation order.  One [N,N] count exchange + host read per step."""
         import torch.distributed as tdist
-        self.dense_g.zero_()
-        call("amid_embgrad_scatter_dense", _ptr(uid), _ptr(ug), _ptr(nu), uid.numel(), _ptr(self.dense_g), self.V,
-             _stream())
-        tdist.reduce_scatter_tensor(self.shard_g, self.dense_g, group=self.dist.group)
-        r = self.dist.rank
-        self.shard_p.copy_(self.table_padded[r * self.Vs:(r + 1) * self.Vs])
-        call("amid_adam_dense", _ptr(self.shard_p), _ptr(self.shard_g), _ptr(st.tm), _ptr(st.tv), self.shard_p.numel(),
+        G, r, Vs = self.world, self.dist.rank, self.Vs
+        n = uid.numel()
+        dev = ug.device
+        valid = torch.arange(n, device=dev) < nu.to(torch.int64)
+        ids = torch.where(valid, uid, torch.full_like(uid, self.Vp))          # unused slots sort behind every owner
+        bounds = torch.arange(1, G + 1, device=dev, dtype=torch.int64) * Vs
+        ends = torch.searchsorted(ids, bounds)                                # ids < bound  (negative = flagged ids: owner 0 skips them)
+        send = torch.diff(ends, prepend=torch.zeros(1, device=dev, dtype=ends.dtype)).to(torch.int64)
+        counts = torch.empty(G * G, device=dev, dtype=torch.int64)
+        tdist.all_gather_into_tensor(counts, send, group=self.dist.group)
+        cm = counts.view(G, G).cpu()                                          # cm[s, o] = rows rank s sends to owner o
+        in_splits = cm[r].tolist()
+        out_splits = cm[:, r].tolist()
+        n_in, n_out = int(sum(in_splits)), int(sum(out_splits))
+        rid = torch.empty(n_out, device=dev, dtype=torch.int64)
+        rrows = torch.empty(n_out, D, device=dev, dtype=torch.float32)
+        tdist.all_to_all_single(rid, ids[:n_in].contiguous(), out_splits, in_splits, group=self.dist.group)
+        tdist.all_to_all_single(rrows, ug[:n_in].contiguous(), out_splits, in_splits, group=self.dist.group)
+        self.shard_g.zero_()
+        off = 0
+        for s_rank in range(G):                                               # fixed order -> deterministic sum
+            c = out_splits[s_rank]
+            if c:
+                call("amid_embgrad_scatter_add", _ptr(rid[off:off + c]), _ptr(rrows[off:off + c]), c, r * Vs, _ptr(self.shard_g), Vs,
+                     _stream())
+            off += c
+        shard_p = self.table_padded[r * Vs:(r + 1) * Vs]                      # Adam in place on the owned rows
+        call("amid_adam_dense", _ptr(shard_p), _ptr(self.shard_g), _ptr(st.tm), _ptr(st.tv), shard_p.numel(),
              st.step, lr, self.betas[0], self.betas[1], self.eps, _stream())
-        tdist.all_gather_into_tensor(self.table_padded, self.shard_p, group=self.dist.group)
+        tdist.all_gather_into_tensor(self.table_padded, shard_p, group=self.dist.group)    # in place (NCCL: sendbuff = recvbuff + rank * count)
 
     def _exchange_table_grads(self, uid, ug, nu):
         """Replicated table under DP: all-gather every rank's pre-reduced (row id, gradient row) list and reduce again

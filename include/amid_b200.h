@@ -241,6 +241,12 @@ int amid_embgrad_segreduce(const int64_t* ids, const float* grad_rows, int64_t n
 int amid_embgrad_scatter_dense(const int64_t* uniq_ids, const float* uniq_grads, const int32_t* n_uniq,
                                int64_t max_rows, float* dense, int64_t V, amid_stream_t stream);
 
+/* dense[ids[u] - id_offset,:] += rows[u,:] for u < n (ids unique within a call; ids outside [id_offset, id_offset + rows_dense)
+ * are skipped).  Owner side of the sparse reduce-scatter of the table gradient under data parallelism (engine.py): the
+ * reference has no counterpart -- it is the row-sharded form of the sum aten::embedding_dense_backward + NCCL would produce. */
+int amid_embgrad_scatter_add(const int64_t* ids, const float* rows, int64_t n, int64_t id_offset, float* dense,
+                             int64_t rows_dense, amid_stream_t stream);
+
 /* ---- a9: Adam (torch.optim.Adam, betas (.9,.999), eps 1e-8, no weight decay) -------- */
 /* dense: one fused pass over n elements; step = 1-based step number of this update. */
 int amid_adam_dense(float* p, const float* g, float* m, float* v, int64_t n, int32_t step, float lr,
