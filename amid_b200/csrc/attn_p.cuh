@@ -652,6 +652,7 @@ k_attn_fwd_p(const float* __restrict__ q, const float* __restrict__ k, const flo
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const int R = r0 + 64 * i;
+        if (R >= NKP) continue;                     // rows the MMAs never read (rows [L, NKP) are stored as zeros)
         const uint32_t ob = (uint32_t)((R >> 3) * 1024 + (R & 7) * 128) + (((((uint32_t)c4 >> 1) ^ (uint32_t)R) & 7u) << 4) + (c4 & 1) * 8;
         uint2 p0, p1;
         split4(vq[i], sq, p0, p1);
@@ -928,7 +929,7 @@ k_attn_bwd_t2(const float* __restrict__ q, const float* __restrict__ k, const fl
     for (int i = 0; i < 4; ++i) {
         const int R = r0 + 64 * i;
         if (c4 == 0) sh.dl[R] = dsum[i] * sds;
-        if (R < T2_ROWS) {
+        if (R < NKP) {                              // rows the MMAs read (rows [L, NKP) are stored as zeros)
             const uint32_t ob = (uint32_t)((R >> 3) * 1024 + (R & 7) * 128) + (((((uint32_t)c4 >> 1) ^ (uint32_t)R) & 7u) << 4) + (c4 & 1) * 8;
             uint2 a0, a1, b0, b1;
             split4(vq[i], sq, a0, a1);
