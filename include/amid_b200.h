@@ -343,7 +343,9 @@ int amid_tc_wgrad16_test(const float* dy, const float* x, int32_t M, float* part
 int amid_x3_linear_test(const float* x, const float* w, const float* b, int32_t M, float* y, void* scratch,
                         amid_stream_t stream);
 /* Attention kernels side by side (q, k, v, o: [B*L,128] with heads along the columns; lse: [B*8*L]).
- * impl 0 = fp32 CUDA cores, 1 = mma.sync TF32, 2 = mma.sync 3xTF32, 3 = tcgen05 FP16-pair split (L <= 224). */
+ * impl 0 = fp32 CUDA cores, 1 = mma.sync TF32, 2 = mma.sync 3xTF32, 3 = tcgen05 FP16-pair split, first version (L <= 224),
+ * 4 = round-2 tcgen05 kernels of attn_p.cuh (forward k_attn_fwd_p, 64 <= L <= 224; backward: single-pass persistent
+ * k_attn_bwd_p, 64 <= L <= 256), 5 = backward only: two-pass k_attn_bwd_t2 (L <= 224; the kernel the x3 train step runs). */
 int amid_attn_fwd_test(const float* q, const float* k, const float* v, float* o, float* lse, int32_t B, int32_t L,
                        const amid_dropout* drop, uint32_t site, int32_t impl, amid_stream_t stream);
 /* backward: dq is the gradient with respect to q / 0.25 (the convention of amid_encoder_bwd's chain kernels) */
