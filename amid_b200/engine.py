@@ -32,6 +32,21 @@ def pad_for_exchange(uid: torch.Tensor, ug: torch.Tensor, nu: torch.Tensor, V: i
     return uid, ug
 
 
+def owner_send_counts(uid: torch.Tensor, nu: torch.Tensor, Vs: int, G: int):
+    """Routing plan of the sparse reduce-scatter (`Trainer._dense_table_step`).  ``uid[:nu]`` are this rank's touched row
+    ids in ascending order (the output of the segmented reduction), rank o owns rows [o Vs, (o+1) Vs).  Returns the id list
+    with its unused tail replaced by the sentinel G Vs (sorts behind every owner) and the number of rows destined to each
+    owner -- contiguous runs of the list, because it is sorted.  Pure torch: runs on CPU tensors too (tests/test_dp_gloo.py)."""
+    n = uid.numel()
+    dev = uid.device
+    valid = torch.arange(n, device=dev) < nu.to(torch.int64)
+    ids = torch.where(valid, uid, torch.full_like(uid, G * Vs))
+    bounds = torch.arange(1, G + 1, device=dev, dtype=torch.int64) * Vs
+    ends = torch.searchsorted(ids, bounds)                 # ids < bound (negative = flagged ids: owner 0 skips them)
+    send = torch.diff(ends, prepend=torch.zeros(1, device=dev, dtype=ends.dtype)).to(torch.int64)
+    return ids, send
+
+
 class _AdamState:
     def __init__(self, flat_numel: int, V: int, dev):
         z = lambda *s: torch.zeros(*s, device=dev, dtype=torch.float32)
@@ -235,13 +250,8 @@ class Trainer:
         inside a segment: no atomics), which fixes the summation order.  One [N,N] count exchange + host read per step."""
         import torch.distributed as tdist
         G, r, Vs = self.world, self.dist.rank, self.Vs
-        n = uid.numel()
         dev = ug.device
-        valid = torch.arange(n, device=dev) < nu.to(torch.int64)
-        ids = torch.where(valid, uid, torch.full_like(uid, self.Vp))          # unused slots sort behind every owner
-        bounds = torch.arange(1, G + 1, device=dev, dtype=torch.int64) * Vs
-        ends = torch.searchsorted(ids, bounds)                                # ids < bound  (negative = flagged ids: owner 0 skips them)
-        send = torch.diff(ends, prepend=torch.zeros(1, device=dev, dtype=ends.dtype)).to(torch.int64)
+        ids, send = owner_send_counts(uid, nu, Vs, G)
         counts = torch.empty(G * G, device=dev, dtype=torch.int64)
         tdist.all_gather_into_tensor(counts, send, group=self.dist.group)
         cm = counts.view(G, G).cpu()                                          # cm[s, o] = rows rank s sends to owner o

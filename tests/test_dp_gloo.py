@@ -189,3 +189,62 @@ def test_sharded_table_routing_world2_gloo():
         p.join(timeout=60)
     for rank, msg in res:
         assert msg == "ok", f"rank {rank}: {msg}"
+
+
+def _rs_worker(rank, world, port, q):
+    """Sparse reduce-scatter of the table gradient (engine.Trainer._dense_table_step): routing plan + all-to-all + ordered
+    owner-side accumulation against the dense sum of every rank's gradient."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from amid_b200.engine import owner_send_counts
+        V, Dd = 37, 4
+        Vs = (V + world - 1) // world
+        g = torch.Generator().manual_seed(100 + rank)
+        touched = torch.randperm(V, generator=g)[:11 + 3 * rank].sort().values          # this rank's unique rows, ascending
+        nu = torch.tensor([touched.numel()], dtype=torch.int32)
+        cap = 20
+        uid = torch.full((cap,), 12345, dtype=torch.int64)                                # garbage behind n_uniq
+        uid[:touched.numel()] = touched
+        ug = torch.randn(cap, Dd, generator=g)
+        ids, send = owner_send_counts(uid, nu, Vs, world)
+        assert int(send.sum()) == touched.numel()
+        for o in range(world):
+            assert int(send[o]) == int(((touched >= o * Vs) & (touched < (o + 1) * Vs)).sum())
+        counts = [torch.empty(world, dtype=torch.int64) for _ in range(world)]
+        dist.all_gather(counts, send)
+        cm = torch.stack(counts)                                                          # cm[s, o]
+        in_splits, out_splits = cm[rank].tolist(), cm[:, rank].tolist()
+        n_in, n_out = sum(in_splits), sum(out_splits)
+        rid, rrows = torch.empty(n_out, dtype=torch.int64), torch.empty(n_out, Dd)
+        dist.all_to_all_single(rid, ids[:n_in].contiguous(), out_splits, in_splits)
+        dist.all_to_all_single(rrows, ug[:n_in].contiguous(), out_splits, in_splits)
+        shard = torch.zeros(Vs, Dd)
+        off = 0
+        for s_rank in range(world):                                                       # rank order, as amid_embgrad_scatter_add
+            c = out_splits[s_rank]
+            shard.index_add_(0, rid[off:off + c] - rank * Vs, rrows[off:off + c])
+            off += c
+        # dense reference: every rank's dense gradient, summed
+        dense = torch.zeros(world * Vs, Dd)
+        dense[touched] = ug[:touched.numel()]
+        dist.all_reduce(dense)
+        np.testing.assert_allclose(shard.numpy(), dense[rank * Vs:(rank + 1) * Vs].numpy(), rtol=0, atol=1e-6)
+        q.put((rank, "ok"))
+    except Exception as e:  # pragma: no cover
+        q.put((rank, repr(e)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sparse_reduce_scatter_routing_world2():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_rs_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert all(r[1] == "ok" for r in res), res
