@@ -334,6 +334,43 @@ def test_trainer_dr_two_phase_two_adams_vs_oracle(prec):
         assert_close(named[k], v, 0, 3e-5, k)
 
 
+# ------------------------------------------------------------------ C3 sequence length, several CTA waves: oracle + our masks
+@pytest.mark.parametrize("prec", PRECS)
+def test_c3_scale_train_step_vs_oracle(prec):
+    """B = 64, L = 200 (the C3 sequence length; 512 (sample, head) attention CTAs = several waves, 100 token tiles per chain
+    kernel), dropout ON with the masks the kernels export, ItC gates firing: probabilities, loss and every gradient against
+    the oracle at the fp32 tolerances, in both parity-grade modes."""
+    hp = _hp()
+    B, L, C, V, ts2 = 64, 200, 2, 997, 0.0155
+    rng = np.random.default_rng(20241)
+    P = make_params(57, V, D, L, HID, B)
+    m = build_model(P, V, L, B, ts2=ts2, precision=prec).train()
+    b = to_cuda(random_batch(rng, B, L, C, V))
+    seed = 424242
+    probs, ctx = hp.forward(m.param_dict(), m.cfg, b["i_node"], b["neg_samples"], b["seq_d1"], b["seq_d2"], train=True, seed=seed)
+    masks = {s: {k: v.cpu() for k, v in d.items()} for s, d in hp.dropout_masks(m.cfg, B, L, seed, "cuda").items()}
+    Po = {k: v.clone().requires_grad_(True) for k, v in P.items()}
+    col = {}
+    outs = oracle_forward(Po, b, isInC=False, isItC=True, ts1=0.5, ts2=ts2, isDR=False, masks=masks, collect=col)
+    pj = torch.softmax(O.mim_scores(col["enc1"], col["enc2"]), 0)
+    assert 0 < int((pj > ts2).sum()) < B, "the case is meant to have some, not all, ItC gates open"
+    if (pj - ts2).abs().min() < 1e-5:
+        pytest.skip("gate margin too small for a meaningful comparison")
+    for i, o in enumerate(outs):
+        assert_close(probs[i // 2, i % 2], o, 0, 3e-5, f"out {i}")
+    losses, dprobs = hp.loss_fwd_bwd(probs, b["label"], b["domain_id"], b["ob_label"], 0, 0.01, B)
+    lo = O.loss_cls(outs[0], outs[1], b["label"].cpu(), b["domain_id"].cpu())
+    assert_close(losses[0], lo, 3e-5, 0)
+    lo.backward()
+    G, ids_all, rows_all = hp.backward(m.param_dict(), m.cfg, ctx, dprobs)
+    for k, v in Po.items():
+        if k == "item_emb_layer.emb_item.weight":
+            uid, ug, nu = hp.segreduce(ids_all, rows_all, V)
+            assert_close(hp.dense_table_grad(uid, ug, nu, V), v.grad, 1e-3, grad_tol(v.grad), k)
+        elif v.grad is not None:
+            assert_close(G[k], v.grad, 1e-3, grad_tol(v.grad), k)
+
+
 # ------------------------------------------------------------------ train mode WITH dropout: oracle + our masks
 @pytest.mark.parametrize("prec", PRECS)
 @pytest.mark.parametrize("B,L,C,isDR", [(6, 9, 2, False), (5, 20, 3, True)])

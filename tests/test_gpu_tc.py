@@ -95,7 +95,7 @@ from helpers import (HID, O, T, assert_close, batch_from, build_model, grad_tol,
 
 
 @pytest.mark.parametrize("precision", PRECISIONS)
-@pytest.mark.parametrize("B,L,C", [(1, 1, 2), (7, 13, 5), (3, 130, 2), (9, 200, 2)])
+@pytest.mark.parametrize("B,L,C", [(1, 1, 2), (7, 13, 5), (3, 130, 2), (9, 200, 2), (64, 200, 2)])
 def test_forward_tc_vs_oracle(B, L, C, precision):
     rng = np.random.default_rng(B * 1000 + L)
     V = 211
