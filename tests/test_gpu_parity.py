@@ -750,3 +750,31 @@ def test_inc_itc_dr_training_direction_reference_golden(prec):
     want = np.zeros((V, D), dtype=np.float32)
     want[z["gtab_idx"]] = z["gtab_rows"]
     assert_close(hp.dense_table_grad(uid, ug, nu, V), want, 1e-3, grad_tol(want), "table")
+
+
+@pytest.mark.parametrize("prec", PRECS)
+def test_dr_phase2_reference_golden(prec):
+    """The doubly-robust PHASE-2 step (loss_dr_r, train_sr_dr.py:392-394) against a fixture executed by the reference with
+    dropout off (tests/golden/make_dr_phase2_golden.py): six outputs, the loss and the gradients through the C ABI."""
+    hp = _hp()
+    z = load("dr_phase2_nodrop.npz")
+    V, ts, B, L = int(z["V"]), float(z["ts"]), 16, 20
+    P = make_params(23, V, D, L, HID, B, isDR=True)
+    m = build_model(P, V, L, B, ts2=ts, isDR=True, drop_p=0.0, precision=prec).train()
+    b = batch_from(z)
+    probs, ctx = hp.forward(m.param_dict(), m.cfg, b["i_node"], b["neg_samples"], b["seq_d1"], b["seq_d2"], train=True, seed=5)
+    for i, n in enumerate(("p1", "p2", "ips1", "ips2", "g1", "g2")):
+        assert_close(probs[i // 2, i % 2], z[n], 0, 3e-5, n)
+    losses, dprobs = hp.loss_fwd_bwd(probs, b["label"], b["domain_id"], b["ob_label"], 2, 0.01, B)
+    assert_close(losses[2], z["loss_dr_r"], 3e-5, 1e-7)
+    G, ids_all, rows_all = hp.backward(m.param_dict(), m.cfg, ctx, dprobs)
+    n_checked = 0
+    for k in z:
+        if k.startswith("grad/"):
+            assert_close(G[k.split("/", 1)[1]], z[k], 1e-3, grad_tol(z[k]), k)
+            n_checked += 1
+    assert n_checked == int(z["n_grad_tensors"]) and n_checked >= 20
+    uid, ug, nu = hp.segreduce(ids_all, rows_all, V)
+    want = np.zeros((V, D), dtype=np.float32)
+    want[z["gtab_idx"]] = z["gtab_rows"]
+    assert_close(hp.dense_table_grad(uid, ug, nu, V), want, 1e-3, grad_tol(want), "table")

@@ -219,3 +219,31 @@ def test_inc_itc_dr_training_direction_golden():
     gt[T(z["gtab_idx"])] = T(z["gtab_rows"])
     got = P["item_emb_layer.emb_item.weight"].grad
     np.testing.assert_allclose(got.numpy(), gt.numpy(), rtol=1e-3, atol=1e-7 + 1e-4 * float(gt.abs().max()))
+
+
+def test_dr_phase2_training_direction_golden():
+    """F10 (tests/golden/make_dr_phase2_golden.py): the doubly-robust phase-2 loss (train_sr_dr.py:392-394) and its gradients,
+    dropout off, executed by the reference -- the fixture the GPU path meets directly in tests/test_gpu_parity.py."""
+    z = load("dr_phase2_nodrop.npz")
+    V, ts = int(z["V"]), float(z["ts"])
+    P = {k: v.clone().requires_grad_(True) for k, v in make_params(23, V, D, 20, HID, 16, isDR=True).items()}
+    outs = _fwd(P, z, isInC=False, isItC=True, ts1=0.5, ts2=ts, isDR=True)
+    for n, t in zip(("p1", "p2", "ips1", "ips2", "g1", "g2"), outs):
+        np.testing.assert_allclose(t.detach().numpy(), z[n], rtol=0, atol=2e-6, err_msg=n)
+    lab, dom, ob = T(z["in_label"]).float(), T(z["in_domain_id"]), T(z["in_ob_label"])
+    loss = O.loss_dr_r(*outs, lab, dom, ob)
+    np.testing.assert_allclose(loss.detach().numpy(), z["loss_dr_r"], rtol=2e-5)
+    loss.backward()
+    n_checked = 0
+    for k in z:
+        if k.startswith("grad/"):
+            g = z[k]
+            got = P[k.split("/", 1)[1]].grad
+            got = torch.zeros_like(P[k.split("/", 1)[1]]) if got is None else got
+            np.testing.assert_allclose(got.numpy(), g, rtol=1e-3, atol=1e-7 + 1e-4 * np.abs(g).max(), err_msg=k)
+            n_checked += 1
+    assert n_checked == int(z["n_grad_tensors"]) and n_checked >= 20
+    gt = torch.zeros(V, D)
+    gt[T(z["gtab_idx"])] = T(z["gtab_rows"])
+    np.testing.assert_allclose(P["item_emb_layer.emb_item.weight"].grad.numpy(), gt.numpy(), rtol=1e-3,
+                               atol=1e-7 + 1e-4 * float(gt.abs().max()))
