@@ -35,12 +35,16 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+// Every wait is bounded: a protocol error (a phase that never completes) must surface as a launch failure, not as a GPU that
+// hangs until somebody resets it.  try_wait suspends the thread for a hardware-defined interval per attempt, so 2^26 failed
+// attempts are many seconds -- orders of magnitude beyond any legitimate wait in these kernels.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    uint32_t ok = 0;
+    uint32_t ok = 0, spins = 0;
     do {
         asm volatile(
             "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
             : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+        if (!ok && ++spins == (1u << 26)) __trap();      // (no printf here: its stack frame costs registers in every kernel)
     } while (!ok);
 }
 
