@@ -1,25 +1,33 @@
-// Pipelined causal attention (head_dim 16, 64 <= L <= 256) on tcgen05 at fp32-level accuracy (FP16-pair split of
-// x3.cuh): persistent CTAs (one per SM), warp-specialised, tensor memory double-buffered between two groups of
-// softmax warps, SINGLE-PASS backward.
-//
-// What changed against attn_tc.cuh (one CTA per (sample, head), serial phases, two CTAs per SM):
-//   * one thread of a dedicated warp issues every tcgen05.mma and tracks completion with mbarriers; sixteen
-//     element-wise warps form two sets that work on alternating score blocks, so that the MMAs of one set run
-//     while the other set is in its exp / dropout / split loop ("ping-pong");
-//   * the backward visits every (query, key) pair ONCE (attn_tc.cuh recomputes S and dP in a second, transposed
-//     pass for dK / dV): a set turns its block S, dP [128 queries x 64 keys] into Pd = dropout(P) and dS and stores
-//     both as FP16 pairs into a shared-memory staging tile [query rows][64 keys] (SWIZZLE_128B).  The SAME bytes
-//     are the K-major A operand of dQ += dS K (rows = queries) and the MN-major A operand of dK += dS^T Q and
-//     dV += Pd^T dO (rows = keys);
-//   * no transposed operand copies: k / q / dO enter those three GEMMs as MN-major B operands straight from the
-//     row tiles [position][k0 | k1 | v0 | v1] and [position][q0 | q1 | g0 | g1];
-//   * piece products by stacking: for dK / dV the two A pieces are the two 64-row halves of one M = 128 operand
-//     (leading-dimension offset = distance between the piece tiles), B = b0 then b1 into the same 16 columns, so
-//     lanes [0,64) hold a0 (b0 + b1) and lanes [64,128) a1 (b0 + b1) -- the full product; for dQ B = [k0 | k1] is
-//     one N = 32 operand.  Two MMAs per k-step instead of three;
-//   * the next head's q / k / v / dO / o rows are fetched into registers before the wait for the current head's
-//     last MMAs, so the HBM latency overlaps the drain.
-// Arithmetic as attn_tc.cuh (torch/nn/functional.py:6630-6647), same dropout bits.
+// Round-2 causal attention kernels (head_dim 16) on tcgen05 at fp32-level accuracy (FP16-pair split of x3.cuh: every operand
+// x = s^-1 (h0 + h1), products h0 h0 + h1 h0 + h0 h1 accumulated in fp32 in tensor memory).  Three kernels:
+//   k_attn_fwd_p   forward, one CTA per (sample, head), two CTAs per SM, 64 <= L <= 224
+//   k_attn_bwd_t2  backward, two passes (rows = queries for dQ, rows = keys for dV / dK), one CTA per (sample, head), two CTAs
+//                  per SM, L <= 224 -- the kernel the x3 train step runs
+//   k_attn_bwd_p   backward, ONE pass, 148 persistent warp-specialised CTAs, 64 <= L <= 256 -- runs for 224 < L <= 256 and side
+//                  by side with the two-pass kernel in tests/test_gpu_attn.py and tools/prof_attn.py
+// What they share (and what changed against attn_tc.cuh, the first tcgen05 version):
+//   * operands live in two K-major SWIZZLE_128B ROW tiles [position][q0 | q1 | g0 | g1] and [position][k0 | k1 | v0 | v1]
+//     (128-byte rows of FP16 pair pieces).  There are no transposed copies: wherever a GEMM needs an operand the other way
+//     round (v in P V, k in dS K, q in dS^T Q, dO in Pd^T dO) the row tile is addressed as an MN-major B operand with a
+//     32 / 64-byte offset inside the swizzled row;
+//   * piece products by stacking: neighbouring pieces [b0 | b1] are one N = 32 operand, so a k-step costs two MMAs instead
+//     of three (the epilogue adds the two 16-column halves); in the single-pass kernel the two A pieces of the staged
+//     Pd / dS tiles are the two 64-row halves of one M = 128 MN-major operand (leading-dimension offset = the distance
+//     between the piece tiles);
+//   * every MMA is issued by one elect.sync lane of a converged warp with descriptors built from a low word + constant high
+//     word: ptxas emits back-to-back UTCHMMA (a `threadIdx.x == 0` branch costs a ~12-instruction election loop per MMA);
+//   * the exp / dropout / split loops are specialised on training mode and on diagonal chunks; the keep test of a dropout
+//     byte is one shift + one unsigned compare.
+// The single-pass kernel (k_attn_bwd_p): a unit = [128 queries x 64 keys]; S = Q K^T and dP = dO V^T land in one of two TMEM
+// buffers two units ahead; each of the 16 element-wise warps turns 32 rows x 16 keys into Pd = dropout(P) and dS, stores dS
+// in place (A operand of dQ += dS [k0 | k1]) and Pd, dS into one of two staging tile sets in shared memory -- the SAME bytes
+// are the MN-major A operand of dV += Pd^T [g0 | g1] and dK += dS^T q.  Three issuing warps (S / dP + dQ, dK, dV) and the
+// element-wise warps hand buffers over through mbarriers; the next head is prefetched into L2 and converted while the last
+// MMAs drain.  Measured at the C3 shape: forward 313 us, two-pass backward 741 us, single-pass backward 805 us.
+// mbarrier rule followed everywhere: two commits on one barrier are separated by a CTA barrier (or a dependency chain) that
+// every waiter of the first has passed -- otherwise a late waker can find the barrier two phases ahead and wait forever.
+// Arithmetic follows torch/nn/functional.py:6630-6647 (q pre-scaled by 0.25, -inf above the diagonal, softmax, dropout
+// without renormalisation, P v); the dropout bits are the same counter hash as every other attention kernel.
 #pragma once
 #include "attn_tc.cuh"
 
